@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on its configs[1]: audio-seconds transcribed per second,
+mt3 config, batch = 64 x 2.048 s synthetic segments per GPU, log-mel + encoder + greedy decode.
+
+A "step" is one pass of the hot path over one batch (64 segments/GPU): log-mel kernel ->
+8-layer encoder -> cross-K/V -> DEC_STEPS greedy decode steps (default 1024 = the reference's
+outputs_length with EOS never stopping the loop: random weights make EOS timing meaningless,
+so the worst case is what is timed; nothing is skipped).
+
+  python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N > 1)
+  python bench.py --impl reference ...                     (the CPU restatement on host cores)
+
+`value`  device-resident inputs, timed with CUDA events per step (L2 flushed between steps),
+         max over ranks, whole-job aggregate over N GPUs (weak scaling: 64 segments per GPU).
+`e2e`    same metric through InferenceModel.transcribe_segments with pinned HOST audio in and
+         HOST tokens out (H2D + D2H inside the timed region).
+`roofline` the dominant kernel (decode self-attention over the KV cache), algorithmic bytes per
+         launch / CUDA-event time per launch, against MEASURED_PEAKS.json's HBM copy bandwidth.
+`cpu_baseline` the torch-CPU port of the reference semantics (oracle/torch_cpu.py; the JAX/T5X
+         reference itself is not installable here) on a bounded sample, rank 0, N=1 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEG_SAMPLES = 32768
+SEG_SECONDS = SEG_SAMPLES / 16000.0
+BATCH_PER_GPU = 64
+
+
+def synth_audio(n, seed0):
+    """SURVEY 8d sine-mix, numpy default_rng seeded per segment (vectorised; the product never
+    imports oracle/, so this is bench's own generator)."""
+    out = np.zeros((n, SEG_SAMPLES), np.float32)
+    t = np.arange(SEG_SAMPLES, dtype=np.float64) / 16000.0
+    for i in range(n):
+        rng = np.random.default_rng(seed0 + i)
+        x = np.zeros(SEG_SAMPLES)
+        for _ in range(int(rng.integers(3, 9))):
+            pitch = int(rng.integers(36, 97))
+            f = 440.0 * 2.0 ** ((pitch - 69) / 12.0)
+            x += rng.uniform(0.05, 0.3) * np.sin(2 * np.pi * f * t + rng.uniform(0, 2 * np.pi))
+        out[i] = (x * (0.9 / max(1e-12, np.abs(x).max()))).astype(np.float32)
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.p, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference arm: the CPU restatement (torch-CPU port of the oracle) on the host cores.
+    Each step = one bounded sample of the workload: REF_BATCH segments x REF_STEPS decode steps
+    of the same pipeline; the value is scaled to full-length (1024-step) transcription by the
+    measured per-step cost, and `sample` says exactly what ran."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+    from oracle import mt3_oracle as O
+    from oracle import torch_cpu as TC
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    cfg = O.T5Config()
+    params = O.init_params(cfg, seed=0)
+    model = TC.TorchCpuModel(params, cfg)
+    nb, nsteps = args.ref_batch, args.ref_dec_steps
+    audio = torch.from_numpy(synth_audio(nb, 1234))
+    times = []
+    with torch.no_grad():
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            model.transcribe_segments(audio, num_steps=nsteps)
+            dt = time.perf_counter() - t0
+            if i >= args.warmup:
+                times.append(dt)
+    ms = 1000.0 * float(np.mean(times))
+    # scale the decode part to args.dec_steps: time a short decode to separate the fixed part
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        spec = TC.compute_logmel(audio)
+        enc = model.encode(spec)
+        t_fixed = time.perf_counter() - t0
+    per_step = (ms / 1000.0 - t_fixed) / max(1, nsteps)
+    # decode cost grows with cache length; measured prefix under-estimates the tail, so this
+    # extrapolation FAVOURS the CPU (conservative for the GPU/CPU ratio)
+    full = t_fixed + per_step * args.dec_steps
+    value = nb * SEG_SECONDS / full
+    sample = (f"{nb} segments x {nsteps} of {args.dec_steps} greedy steps (log-mel+encoder+decoder, hoisted cross-K/V), "
+              f"decode extrapolated linearly to {args.dec_steps} steps; torch-CPU fp32 port of the reference semantics "
+              f"(JAX/T5X not installable here)")
+    line = {
+        "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "mt3 config, batch=64 x 2.048 s segments, log-mel + encoder + greedy decode "
+                               f"({args.dec_steps} steps)", "sample_batch": nb, "sample_dec_steps": nsteps},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mt3_b200 import _lib, inference, spectrograms, weights
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch N>1 with torch.distributed.run)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = BATCH_PER_GPU
+    # ---- weights: rank 0 draws them, ONE NCCL broadcast at load (north_star) -------------------
+    im = None
+    from mt3_b200 import network, vocabularies
+    codec = vocabularies.build_codec(vocabularies.VocabularyConfig(num_velocity_bins=1))
+    vocab = vocabularies.vocabulary_from_codec(codec)
+    cfg = network.T5Config(vocab_size=vocabularies.num_embeddings(vocab), emb_dim=512, num_heads=6,
+                           num_encoder_layers=8, num_decoder_layers=8, head_dim=64, mlp_dim=1024,
+                           mlp_activations=('gelu', 'linear'))
+    if rank == 0:
+        blob = torch.from_numpy(weights.flatten(weights.synthetic_params(cfg, 0), cfg)).to(dev)
+    else:
+        blob = torch.empty(weights.num_params(cfg), dtype=torch.float32, device=dev)
+    if world > 1:
+        dist.broadcast(blob, src=0)
+    flat = blob.cpu().numpy()
+    params, off = {}, 0
+    for name, shape in weights.param_shapes(cfg).items():
+        n = int(np.prod(shape))
+        params[name] = flat[off:off + n].reshape(shape)
+        off += n
+    del blob
+    im = inference.InferenceModel(params, 'mt3', device=dev, batch_size=B, use_graph=True)
+
+    # ---- inputs: contiguous shard of the global segment list ---------------------------------
+    audio_host = torch.from_numpy(synth_audio(B, 1234 + rank * B)).pin_memory()
+    audio_dev = audio_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    tokens = torch.empty((B, 1024), dtype=torch.int32, device=dev)
+    dec_steps = args.dec_steps
+
+    def one_pass():
+        spec = spectrograms.compute_spectrogram(audio_dev, im.spectrogram_config)
+        im.model.generate(spec, num_steps=dec_steps, stop_at_eos=False, use_graph=True, out=tokens)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        one_pass()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_pass()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = _lib.launch_count() - launches0
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e: public API with HOST buffers (H2D + D2H inside the timed region) ----------------
+    im.transcribe_segments(audio_host, num_steps=dec_steps, stop_at_eos=False)   # warm
+    barrier()
+    e2e_times = []
+    for _ in range(max(1, min(args.steps, 3))):
+        flush.fill_(1)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        out_host = im.transcribe_segments(audio_host, num_steps=dec_steps, stop_at_eos=False)
+        e2e_times.append(time.perf_counter() - t0)
+    e2e_ms = 1000.0 * float(np.mean(e2e_times))
+
+    # ---- all-gather of the decoded token streams at the end (north_star) -----------------------
+    if world > 1:
+        gathered = [torch.empty_like(tokens) for _ in range(world)]
+        dist.all_gather(gathered, tokens)
+        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+        ln = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(ln)
+        launches = int(ln[0])
+
+    ms_per_step = total_ms / args.steps
+    value = world * B * SEG_SECONDS / (ms_per_step / 1000.0)
+    e2e_value = world * B * SEG_SECONDS / (e2e_ms / 1000.0)
+
+    # ---- roofline of the dominant kernel: decode self-attention over the KV cache --------------
+    roofline = None
+    cpu_baseline = None
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        lib = _lib.load()
+        h = im.model._h
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        pos = 511                                   # mean cache length of a 1024-step decode
+        H, D = 6, 64
+        alg_bytes = B * H * (pos + 1) * D * 4 * 2 + B * H * D * 4 * 2     # K and V rows read once + q in, o out
+        iters = 64
+        for _ in range(2):
+            _lib.check(lib.mt3_debug_launch(h, _lib.K_DEC_SELF_ATTN, pos, 8, stream))
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.mt3_debug_launch(h, _lib.K_DEC_SELF_ATTN, pos, iters, stream))   # cycles over 8 layers' caches (805 MB > L2)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        us = 1000.0 * e0.elapsed_time(e1) / iters
+        ach = alg_bytes / (us * 1e-6) / 1e9
+        roofline = {"kernel": "dec_attention_kernel (self-attention, cache length 512)", "bound": "hbm",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "us_per_launch": us, "algorithmic_bytes_per_launch": alg_bytes}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import mt3_oracle as O
+            from oracle import torch_cpu as TC
+            torch.set_num_threads(os.cpu_count() or 1)
+            ocfg = O.T5Config()
+            cm = TC.TorchCpuModel(params, ocfg)
+            nb, nsteps = args.ref_batch, args.ref_dec_steps
+            a = audio_host[:nb].clone()
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                spec = TC.compute_logmel(a)
+                enc = cm.encode(spec)
+                t_fixed = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                cm.greedy_decode(enc, nsteps)
+                t_dec = time.perf_counter() - t0
+            full = t_fixed + t_dec / nsteps * dec_steps
+            cpu_baseline = {"value": nb * SEG_SECONDS / full, "unit": "audio-s/s", "cores": torch.get_num_threads(),
+                            "kind": "port",
+                            "sample": f"{nb} segments x {nsteps} of {dec_steps} greedy steps, decode extrapolated linearly "
+                                      f"(favours the CPU); torch-CPU fp32 port of the reference semantics, hoisted cross-K/V; "
+                                      f"measured {t_fixed:.2f} s log-mel+encoder, {t_dec:.2f} s decode"}
+
+    if rank == 0:
+        line = {
+            "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "mt3 config (BASELINE configs[1]): batch=64 x 2.048 s synthetic sine-mix segments per GPU, "
+                                   f"log-mel + 8-layer encoder + greedy decode, {dec_steps} decode steps, EOS never stops the loop",
+                       "segments_per_gpu": B, "dec_steps": dec_steps, "gemm_mode": "fp32_simt", "l2": "flushed between steps (256 MB write)",
+                       "parallelism": f"dp{world} (segments sharded, 1 weight broadcast, 1 token all-gather)"},
+            "segments_per_second": value / SEG_SECONDS,
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(B * SEG_SAMPLES * 4),
+                    "d2h_bytes_per_step": int(B * 1024 * 4), "ms_per_step": e2e_ms,
+                    "api": "InferenceModel.transcribe_segments (pinned host audio -> host tokens)"},
+            "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
+            "clocks": clocks, "roofline": roofline,
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dec-steps", type=int, default=1024)
+    ap.add_argument("--ref-batch", type=int, default=8, help="CPU sample: segments (the notebook's batch size)")
+    ap.add_argument("--ref-dec-steps", type=int, default=96, help="CPU sample: decode steps actually run")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,57 @@
+// Shared helpers for the mt3_b200 CUDA library (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/mt3_b200.h"
+
+namespace mt3 {
+
+// thread-local last-error text behind mt3_last_error()
+std::string& last_error();
+int fail(int code, const char* fmt, ...);
+
+extern std::atomic<uint64_t> g_launch_count;
+inline void count_launch(uint64_t n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
+
+#define MT3_CUDA_CHECK(expr)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return ::mt3::fail(MT3_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr,            \
+                         cudaGetErrorString(_e));                                              \
+  } while (0)
+
+#define MT3_LAUNCH_CHECK()                                                                     \
+  do {                                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess)                                                                     \
+      return ::mt3::fail(MT3_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__,        \
+                         cudaGetErrorString(_e));                                              \
+    ::mt3::count_launch();                                                                     \
+  } while (0)
+
+#define MT3_REQUIRE(cond, code, ...)                                                           \
+  do {                                                                                         \
+    if (!(cond)) return ::mt3::fail(code, __VA_ARGS__);                                        \
+  } while (0)
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace mt3

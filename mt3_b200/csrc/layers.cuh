@@ -1,0 +1,348 @@
+// Non-GEMM kernels of the MT3 encoder/decoder blocks (sm_100a): RMSNorm statistics,
+// attention (encoder, and the Tq = 1 decode form over the KV cache), token embedding,
+// greedy argmax with EOS bookkeeping, vocabulary decode, weight re-layout.
+#pragma once
+
+#include "common.cuh"
+
+namespace mt3 {
+
+// ---------------------------------------------------------------------------------
+// RMSNorm (layers.py:604-621): rstd[m] = 1/sqrt(mean(x[m,:]^2) + eps).  One warp per row.
+// ---------------------------------------------------------------------------------
+__global__ void row_rstd_kernel(const float* __restrict__ x, int ld, int M, int D, float eps,
+                                float* __restrict__ rstd) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float4* p = reinterpret_cast<const float4*>(x + (long long)row * ld);
+  float s = 0.f;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 v = p[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s = warp_sum(s);
+  if (lane == 0) rstd[row] = 1.0f / sqrtf(s / (float)D + eps);
+}
+
+// y = x * rstd * g  (materialised only where the reference's API returns the normed
+// tensor itself: `encoded`, network.py:192).
+__global__ void rmsnorm_kernel(const float* __restrict__ x, int ldx, int M, int D, float eps,
+                               const float* __restrict__ g, float* __restrict__ y, int ldy) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float4* p = reinterpret_cast<const float4*>(x + (long long)row * ldx);
+  float s = 0.f;
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 v = p[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  s = warp_sum(s);
+  const float r = 1.0f / sqrtf(s / (float)D + eps);
+  float4* q = reinterpret_cast<float4*>(y + (long long)row * ldy);
+  const float4* gg = reinterpret_cast<const float4*>(g);
+  for (int i = lane; i < D / 4; i += 32) {
+    const float4 v = p[i];
+    const float4 w = __ldg(gg + i);
+    q[i] = make_float4(v.x * r * w.x, v.y * r * w.y, v.z * r * w.z, v.w * r * w.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Encoder self-attention, exact fp32 (layers.py:85-157): softmax(q k^T) v, no 1/sqrt(d)
+// scaling (layers.py:230-234), mask all ones (network.py:283-289).
+// qkv [B*T, 3*H*64] rows = (b,t), columns = [q | k | v] each (h, d).  out [B*T, H*64].
+// One CTA = 32 query rows of one (b, h); scores for all T keys live in shared memory.
+// ---------------------------------------------------------------------------------
+constexpr int kHD = 64;   // head_dim the kernels are specialised for (gin/model.gin:54)
+
+__global__ void __launch_bounds__(256)
+enc_attention_kernel(const float* __restrict__ qkv, int ld, int T, int H, float* __restrict__ out, int ldo) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int QT = 32, KT = 64;
+  const int SP = T + 4;
+  float* sQ = sm;                 // [QT][64]
+  float* sS = sQ + QT * kHD;      // [QT][T+4]
+  float* sT = sS + QT * SP;       // [64][KT+4]  K tile transposed ([d][k]) / V tile [k][d+4]
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * QT;
+  const int tid = threadIdx.x;
+  const int qoff = h * kHD, koff = H * kHD + h * kHD, voff = 2 * H * kHD + h * kHD;
+  const float* base = qkv + (long long)b * T * ld;
+
+  for (int i = tid; i < QT * kHD / 4; i += 256) {
+    const int r = i / (kHD / 4), c4 = i % (kHD / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < T) v = *reinterpret_cast<const float4*>(base + (long long)(q0 + r) * ld + qoff + c4 * 4);
+    *reinterpret_cast<float4*>(sQ + r * kHD + c4 * 4) = v;
+  }
+  // S = Q K^T : thread -> 2 query rows x 4 keys
+  const int tq = tid / 16, tk = tid % 16;     // tq in [0,16): rows tq, tq+16 ; tk: keys tk*4..+3
+  for (int k0 = 0; k0 < T; k0 += KT) {
+    __syncthreads();
+    for (int i = tid; i < KT * kHD / 4; i += 256) {
+      const int r = i / (kHD / 4), c4 = i % (kHD / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + r < T) v = *reinterpret_cast<const float4*>(base + (long long)(k0 + r) * ld + koff + c4 * 4);
+      sT[(c4 * 4 + 0) * (KT + 4) + r] = v.x;
+      sT[(c4 * 4 + 1) * (KT + 4) + r] = v.y;
+      sT[(c4 * 4 + 2) * (KT + 4) + r] = v.z;
+      sT[(c4 * 4 + 3) * (KT + 4) + r] = v.w;
+    }
+    __syncthreads();
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int d = 0; d < kHD; ++d) {
+      const float q_0 = sQ[tq * kHD + d], q_1 = sQ[(tq + 16) * kHD + d];
+      const float4 kv = *reinterpret_cast<const float4*>(sT + d * (KT + 4) + tk * 4);
+      a0[0] = fmaf(q_0, kv.x, a0[0]); a0[1] = fmaf(q_0, kv.y, a0[1]);
+      a0[2] = fmaf(q_0, kv.z, a0[2]); a0[3] = fmaf(q_0, kv.w, a0[3]);
+      a1[0] = fmaf(q_1, kv.x, a1[0]); a1[1] = fmaf(q_1, kv.y, a1[1]);
+      a1[2] = fmaf(q_1, kv.z, a1[2]); a1[3] = fmaf(q_1, kv.w, a1[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + tk * 4 + j;
+      if (k < T) {
+        sS[tq * SP + k] = a0[j];
+        sS[(tq + 16) * SP + k] = a1[j];
+      }
+    }
+  }
+  __syncthreads();
+  // softmax over keys: warp w handles rows w*4 .. w*4+3
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int r = warp * 4; r < warp * 4 + 4; ++r) {
+      float* row = sS + r * SP;
+      float mx = -INFINITY;
+      for (int k = lane; k < T; k += 32) mx = fmaxf(mx, row[k]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int k = lane; k < T; k += 32) {
+        const float e = expf(row[k] - mx);
+        row[k] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+      for (int k = lane; k < T; k += 32) row[k] *= inv;
+    }
+  }
+  // O = P V : thread -> 2 query rows x 4 dims
+  float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+  const int td = tid % 16;   // dims td*4..+3
+  for (int k0 = 0; k0 < T; k0 += KT) {
+    __syncthreads();
+    for (int i = tid; i < KT * kHD / 4; i += 256) {
+      const int r = i / (kHD / 4), c4 = i % (kHD / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + r < T) v = *reinterpret_cast<const float4*>(base + (long long)(k0 + r) * ld + voff + c4 * 4);
+      *reinterpret_cast<float4*>(sT + r * (kHD + 4) + c4 * 4) = v;
+    }
+    __syncthreads();
+    const int kmax = min(KT, T - k0);
+    for (int k = 0; k < kmax; ++k) {
+      const float p0 = sS[tq * SP + k0 + k], p1 = sS[(tq + 16) * SP + k0 + k];
+      const float4 vv = *reinterpret_cast<const float4*>(sT + k * (kHD + 4) + td * 4);
+      o0[0] = fmaf(p0, vv.x, o0[0]); o0[1] = fmaf(p0, vv.y, o0[1]);
+      o0[2] = fmaf(p0, vv.z, o0[2]); o0[3] = fmaf(p0, vv.w, o0[3]);
+      o1[0] = fmaf(p1, vv.x, o1[0]); o1[1] = fmaf(p1, vv.y, o1[1]);
+      o1[2] = fmaf(p1, vv.z, o1[2]); o1[3] = fmaf(p1, vv.w, o1[3]);
+    }
+  }
+  float* ob = out + (long long)b * T * ldo + h * kHD + td * 4;
+  if (q0 + tq < T) *reinterpret_cast<float4*>(ob + (long long)(q0 + tq) * ldo) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+  if (q0 + tq + 16 < T)
+    *reinterpret_cast<float4*>(ob + (long long)(q0 + tq + 16) * ldo) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+}
+
+// ---------------------------------------------------------------------------------
+// Decode attention, one query position per sequence (layers.py:246-314 for the cached
+// self-attention, network.py:126-139 for cross-attention over the hoisted K/V).
+// q [B, ldq] (head h at column q_off + h*64); kv rows: kv + b*kv_b_stride + t*kv_t_stride,
+// K at column h*64, V at column v_off + h*64.  len = *len_ptr + len_add (self: pos+1) or
+// len_add alone when len_ptr is null (cross: T).  Slots >= len are never read, which
+// equals the reference's -1e10 bias (exp underflows to exactly 0 in fp32).
+// One CTA per (b, h), 128 threads; 8 lanes share a key row (coalesced 256-byte reads).
+// ---------------------------------------------------------------------------------
+constexpr int kDecAttnThreads = 128;
+
+__global__ void __launch_bounds__(kDecAttnThreads)
+dec_attention_kernel(const float* __restrict__ q, int ldq, int q_off, const float* __restrict__ kv,
+                     long long kv_b_stride, long long kv_t_stride, int v_off, const int* __restrict__ len_ptr,
+                     int len_add, int max_len, float* __restrict__ out, int ldo) {
+  extern __shared__ __align__(16) float sm[];
+  float* sP = sm;                    // [max_len]
+  float* sRed = sP + max_len;        // [8 groups][64] + scratch
+  __shared__ float s_stat[8];
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int len = (len_ptr ? *len_ptr : 0) + len_add;
+  const float* kb = kv + (long long)b * kv_b_stride + h * kHD;
+  const float* vb = kb + v_off;
+
+  // phase 1: scores
+  const int sub = lane & 7, kin = lane >> 3;          // 8 lanes per key, 4 keys per warp
+  const float4 q0 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + q_off + h * kHD + sub * 8);
+  const float4 q1 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + q_off + h * kHD + sub * 8 + 4);
+  float lmax = -INFINITY;
+  for (int k0 = warp * 4; k0 < len; k0 += 16) {
+    const int k = k0 + kin;
+    float s = 0.f;
+    if (k < len) {
+      const float* kr = kb + (long long)k * kv_t_stride + sub * 8;
+      const float4 a = *reinterpret_cast<const float4*>(kr);
+      const float4 c = *reinterpret_cast<const float4*>(kr + 4);
+      s = q0.x * a.x + q0.y * a.y + q0.z * a.z + q0.w * a.w + q1.x * c.x + q1.y * c.y + q1.z * c.z + q1.w * c.w;
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (k < len) {
+      if (sub == 0) sP[k] = s;
+      lmax = fmaxf(lmax, s);
+    }
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) s_stat[warp] = lmax;
+  __syncthreads();
+  const float mx = fmaxf(fmaxf(s_stat[0], s_stat[1]), fmaxf(s_stat[2], s_stat[3]));
+  // phase 2: exp + sum
+  float lsum = 0.f;
+  for (int k = tid; k < len; k += kDecAttnThreads) {
+    const float e = expf(sP[k] - mx);
+    sP[k] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) s_stat[4 + warp] = lsum;
+  __syncthreads();
+  const float inv = 1.0f / (s_stat[4] + s_stat[5] + s_stat[6] + s_stat[7]);
+  // phase 3: O = P V ; thread -> key group (tid/16) x 4 dims (tid%16)
+  const int kg = tid >> 4, d4 = tid & 15;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = kg; k < len; k += 8) {
+    const float p = sP[k];
+    const float4 v = *reinterpret_cast<const float4*>(vb + (long long)k * kv_t_stride + d4 * 4);
+    acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y);
+    acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(sRed + kg * kHD + d4 * 4) = acc;
+  __syncthreads();
+  if (tid < kHD) {
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += sRed[g * kHD + tid];
+    out[(long long)b * ldo + h * kHD + tid] = s * inv;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Decoder input: y[b,:] = E[tok[b],:] + PE[pos,:]  (Embed one-hot == row gather,
+// layers.py:516-537; FixedEmbed decode branch, layers.py:589-596).
+// ---------------------------------------------------------------------------------
+__global__ void embed_kernel(const int* __restrict__ tok, const float* __restrict__ emb, int D, int vocab,
+                             const float* __restrict__ pe, const int* __restrict__ pos_ptr, float* __restrict__ y) {
+  const int b = blockIdx.x;
+  int t = tok[b];
+  t = min(max(t, 0), vocab - 1);
+  const int pos = *pos_ptr;
+  const float4* e = reinterpret_cast<const float4*>(emb + (long long)t * D);
+  const float4* p = reinterpret_cast<const float4*>(pe + (long long)pos * D);
+  float4* o = reinterpret_cast<float4*>(y + (long long)b * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    const float4 a = __ldg(e + i), c = __ldg(p + i);
+    o[i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// Greedy pick + loop bookkeeping (stands in for t5x's decode loop at num_decodes=1,
+// models.py:127): next = argmax(logits) (first maximum wins, like np/jnp.argmax);
+// finished sequences emit PAD; EOS (id 1, vocabularies.py:157-159) marks finished.
+// The last CTA to arrive advances the shared position and publishes all_finished.
+// state: [0] pos, [1] arrival counter, [2] all_finished
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+argmax_step_kernel(const float* __restrict__ logits, int V, int B, int* __restrict__ tok_cur,
+                   int* __restrict__ finished, int* __restrict__ tokens_out, int out_ld, int* __restrict__ tok_out_user,
+                   int* __restrict__ state, int advance) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* l = logits + (long long)b * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = tid; i < V; i += 256) {
+    const float v = l[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) { sv[warp] = best; si[warp] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+    const int pos = state[0];
+    int nxt = bi;
+    if (finished) {
+      if (finished[b]) nxt = 0;
+      if (nxt == 1) finished[b] = 1;
+    }
+    if (tok_cur) tok_cur[b] = nxt;
+    if (tokens_out) tokens_out[(long long)b * out_ld + pos] = nxt;
+    if (tok_out_user) tok_out_user[b] = nxt;
+    if (advance) {
+      __threadfence();
+      const int done = atomicAdd(&state[1], 1);
+      if (done == B - 1) {
+        __threadfence();
+        int all = 1;
+        if (finished) {
+          for (int i = 0; i < B; ++i) all &= (*(volatile int*)&finished[i]) != 0;
+        } else {
+          all = 0;
+        }
+        state[2] = all;
+        state[1] = 0;
+        state[0] = pos + 1;
+      }
+    }
+  }
+}
+
+// advance the position without an argmax (decode_step called with tok_out == NULL)
+__global__ void advance_pos_kernel(int* state) { state[0] += 1; }
+
+// GenericTokenVocabulary._decode_tf (vocabularies.py:241-271).
+__global__ void vocab_decode_kernel(const int* __restrict__ ids, int B, int L, int num_regular, int* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  bool eos = false;
+  for (int i = 0; i < L; ++i) {
+    const int id = ids[(long long)b * L + i];
+    eos = eos || (id == 1);
+    int o;
+    if (eos) o = -1;
+    else if (id >= 3 && id < 3 + num_regular) o = id - 3;
+    else o = -2;
+    out[(long long)b * L + i] = o;
+  }
+}
+
+// dst[k, col_off + n*col_stride] = src[k, n] * (g ? g[k] : 1)   -- weight re-layout at model creation
+__global__ void scale_copy_cols_kernel(const float* __restrict__ src, int K, int N, const float* __restrict__ g,
+                                       float* __restrict__ dst, int ldd, int col_off, int col_stride) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)K * N) return;
+  const int k = (int)(i / N), n = (int)(i % N);
+  dst[(long long)k * ldd + col_off + (long long)n * col_stride] = src[i] * (g ? g[k] : 1.f);
+}
+
+}  // namespace mt3

@@ -1,0 +1,329 @@
+// K1: fused log-mel frontend for sm_100a.
+//
+// Replaces spectrograms.compute_spectrogram (spectrograms.py:64-73) ->
+// spectral_ops.compute_logmel/compute_mel/compute_mag/stft/safe_log
+// (spectral_ops.py:29-88): frame (hop 128, pad_end) -> periodic Hann -> rFFT-2048 ->
+// |.| -> mel filterbank (on magnitude) -> log(where(x<=0, eps, x)).
+//
+// Design (one warp per frame, nothing but the audio is read and only the log-mel
+// frames are written -- the reference materialises a [B,256,1025] complex64
+// spectrum, 134 MB at B=64):
+//   * the CTA stages the audio span of its frames in shared memory (each sample is
+//     shared by 16 overlapping frames) together with the Hann window;
+//   * a 2048-point real FFT is a 1024-point complex FFT of z[n] = x[2n] + i x[2n+1]
+//     plus an untangling pass.  1024 = 32 x 32: lane n2 holds z[32 n1 + n2] and
+//     runs a radix-2 DIF 32-point FFT entirely in registers (twiddles are
+//     compile-time constants), multiplies by W_1024^(n2 k1), the 32x32 block is
+//     transposed through padded shared memory, and a second in-register 32-point
+//     FFT yields Z[k1 + 32 k2] in lane k1;
+//   * the untangle step X[k] = E[k] + W_2048^k O[k] needs Z[1024-k], which lives
+//     in lane (32 - k1) mod 32: fetched with warp shuffles;
+//   * magnitudes go to shared memory; the mel "matmul" (99.6 % zeros: <= 2 non-zeros
+//     per FFT bin, <= 10 per mel bin) is a banded gather-FMA, lane m handles mel bins
+//     m, m+32, ..., so the final store is coalesced.
+// Roofline: 655 360 algorithmic bytes and ~14.4 MFLOP of butterflies per mt3
+// segment; with hop 128 every sample feeds 16 frames, so the kernel is bound by
+// fp32 issue / shared memory, not HBM ("K1").
+#include <math.h>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mt3 {
+
+struct Frontend {
+  mt3_frontend_config cfg;
+  int n_bins;              // fft/2 + 1
+  float* d_window;         // [fft]
+  float2* d_tw1024;        // [32 k1][32 lane]  W_1024^(lane*k1)
+  float2* d_rtw;           // [1024]            W_2048^k
+  int* d_mel_start;        // [n_mel + 1]
+  int* d_mel_bin0;         // [n_mel]
+  float* d_mel_w;          // [nnz]
+  int nnz;
+};
+
+namespace {
+
+__host__ __device__ constexpr int brev5(int r) {
+  return ((r & 1) << 4) | ((r & 2) << 2) | (r & 4) | ((r & 8) >> 2) | ((r & 16) >> 4);
+}
+
+// W_32^m = (cos(2 pi m/32), -sin(2 pi m/32)); returns c = cos, s = sin.
+__device__ __forceinline__ void tw32(int m, float& c, float& s) {
+  switch (m) {
+    case 1: c = 0.98078528040323043f; s = 0.19509032201612825f; break;
+    case 2: c = 0.92387953251128674f; s = 0.38268343236508978f; break;
+    case 3: c = 0.83146961230254524f; s = 0.55557023301960218f; break;
+    case 4: c = 0.70710678118654757f; s = 0.70710678118654757f; break;
+    case 5: c = 0.55557023301960218f; s = 0.83146961230254524f; break;
+    case 6: c = 0.38268343236508978f; s = 0.92387953251128674f; break;
+    case 7: c = 0.19509032201612825f; s = 0.98078528040323043f; break;
+    case 9: c = -0.19509032201612825f; s = 0.98078528040323043f; break;
+    case 10: c = -0.38268343236508978f; s = 0.92387953251128674f; break;
+    case 11: c = -0.55557023301960218f; s = 0.83146961230254524f; break;
+    case 12: c = -0.70710678118654757f; s = 0.70710678118654757f; break;
+    case 13: c = -0.83146961230254524f; s = 0.55557023301960218f; break;
+    case 14: c = -0.92387953251128674f; s = 0.38268343236508978f; break;
+    case 15: c = -0.98078528040323043f; s = 0.19509032201612825f; break;
+    default: c = 1.f; s = 0.f; break;
+  }
+}
+
+// In-register 32-point forward FFT, radix-2 decimation in frequency.
+// Output is bit-reversed: x[r] holds X[brev5(r)].
+__device__ __forceinline__ void fft32(float (&xr)[32], float (&xi)[32]) {
+#pragma unroll
+  for (int stage = 0; stage < 5; ++stage) {
+    const int span = 16 >> stage;
+#pragma unroll
+    for (int a = 0; a < 32; ++a) {
+      if ((a & span) == 0) {
+        const int b = a + span;
+        const int m = (a & (span - 1)) * (16 / span);
+        const float tr = xr[a] - xr[b];
+        const float ti = xi[a] - xi[b];
+        xr[a] += xr[b];
+        xi[a] += xi[b];
+        if (m == 0) {
+          xr[b] = tr;
+          xi[b] = ti;
+        } else if (m == 8) {  // * (-i)
+          xr[b] = ti;
+          xi[b] = -tr;
+        } else {
+          float c, s;
+          tw32(m, c, s);
+          xr[b] = tr * c + ti * s;
+          xi[b] = ti * c - tr * s;
+        }
+      }
+    }
+  }
+}
+
+constexpr int kFft = 2048;
+constexpr int kHalf = 1024;
+constexpr int kScratchF2 = 32 * 33;  // padded 32x32 complex transpose buffer per warp
+
+template <int FRAMES_PER_CTA, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+logmel2048_kernel(const float* __restrict__ audio, long long audio_stride, int n_samples, int hop,
+                  const int* __restrict__ n_valid_frames, int T, const float* __restrict__ window,
+                  const float2* __restrict__ tw1024, const float2* __restrict__ rtw,
+                  const int* __restrict__ mel_start, const int* __restrict__ mel_bin0,
+                  const float* __restrict__ mel_w, int n_mel, float log_eps, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const int chunk = (FRAMES_PER_CTA - 1) * hop + kFft;     // samples staged per CTA
+  const int chunk_pad = (chunk + 3) & ~3;
+  float* s_audio = smem;                                   // [chunk_pad]
+  float* s_win = s_audio + chunk_pad;                      // [2048]
+  float2* s_scratch = reinterpret_cast<float2*>(s_win + kFft);  // [WARPS][32*33]
+
+  const int seg = blockIdx.y;
+  const int t0 = blockIdx.x * FRAMES_PER_CTA;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  const float* a = audio + (long long)seg * audio_stride;
+  const long long s0 = (long long)t0 * hop;
+  for (int i = tid; i < chunk; i += WARPS * 32) {
+    const long long g = s0 + i;
+    s_audio[i] = (g < n_samples) ? __ldg(a + g) : 0.f;   // pad_end=True zeros
+  }
+  for (int i = tid; i < kFft; i += WARPS * 32) s_win[i] = __ldg(window + i);
+  __syncthreads();
+
+  const int n_valid = n_valid_frames ? n_valid_frames[seg] : T;
+  float2* scratch = s_scratch + warp * kScratchF2;
+  float* mag = reinterpret_cast<float*>(scratch);          // reused: [1025] magnitudes
+
+  for (int f = warp; f < FRAMES_PER_CTA; f += WARPS) {
+    const int t = t0 + f;
+    if (t >= T) break;
+    float* orow = out + ((long long)seg * T + t) * n_mel;
+    if (t >= n_valid) {                                    // feature-converter zero padding
+      for (int m = lane; m < n_mel; m += 32) orow[m] = 0.f;
+      continue;
+    }
+    float xr[32], xi[32];
+    {
+      const float2* fa = reinterpret_cast<const float2*>(s_audio + f * hop);
+      const float2* fw = reinterpret_cast<const float2*>(s_win);
+#pragma unroll
+      for (int n1 = 0; n1 < 32; ++n1) {
+        const float2 v = fa[32 * n1 + lane];
+        const float2 w = fw[32 * n1 + lane];
+        xr[n1] = v.x * w.x;
+        xi[n1] = v.y * w.y;
+      }
+    }
+    fft32(xr, xi);   // over n1: x[r] = A[k1 = brev5(r)] for n2 = lane
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const int k1 = brev5(r);
+      float vr = xr[r], vi = xi[r];
+      if (k1 != 0) {
+        const float2 w = __ldg(tw1024 + k1 * 32 + lane);
+        const float nr = vr * w.x - vi * w.y;
+        vi = vr * w.y + vi * w.x;
+        vr = nr;
+      }
+      scratch[k1 * 33 + lane] = make_float2(vr, vi);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 32; ++n2) {
+      const float2 v = scratch[lane * 33 + n2];
+      xr[n2] = v.x;
+      xi[n2] = v.y;
+    }
+    __syncwarp();
+    fft32(xr, xi);   // over n2: x[r] = Z[lane + 32 * brev5(r)]
+
+    // untangle: X[k] = E[k] + W_2048^k O[k], E = (Z[k] + conj Z[N-k]) / 2, O = (Z[k] - conj Z[N-k]) / (2i)
+    const int partner = (32 - lane) & 31;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+      const int k2 = brev5(r);
+      const int r0 = brev5((32 - k2) & 31);   // what lane 0 must publish (Z[32 (32-k2)])
+      const float pr = (lane == 0) ? xr[r0] : xr[31 - r];
+      const float pi = (lane == 0) ? xi[r0] : xi[31 - r];
+      const float qr = __shfl_sync(0xffffffffu, pr, partner);
+      const float qi = __shfl_sync(0xffffffffu, pi, partner);
+      const float zr = xr[r], zi = xi[r];
+      const int k = lane + 32 * k2;
+      const float er = 0.5f * (zr + qr), ei = 0.5f * (zi - qi);
+      const float orr = 0.5f * (zi + qi), oi = -0.5f * (zr - qr);
+      const float2 w = __ldg(rtw + k);
+      const float Xr = er + (w.x * orr - w.y * oi);
+      const float Xi = ei + (w.x * oi + w.y * orr);
+      mag[k] = sqrtf(Xr * Xr + Xi * Xi);
+      if (r == 0 && lane == 0) mag[kHalf] = fabsf(zr - zi);   // Nyquist bin
+    }
+    __syncwarp();
+    for (int m = lane; m < n_mel; m += 32) {
+      const int b = mel_start[m], e = mel_start[m + 1];
+      const float* mg = mag + mel_bin0[m];
+      float acc = 0.f;
+      for (int i = b; i < e; ++i) acc = fmaf(mg[i - b], __ldg(mel_w + i), acc);
+      orow[m] = logf(acc <= 0.f ? log_eps : acc);      // safe_log: replace, not add
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+}  // namespace mt3
+
+using namespace mt3;
+
+extern "C" int mt3_frontend_create(const mt3_frontend_config* cfg, const float* mel_matrix, mt3_frontend** out) {
+  MT3_REQUIRE(cfg && mel_matrix && out, MT3_ERR_BAD_ARG, "mt3_frontend_create: null argument");
+  MT3_REQUIRE(cfg->fft_size == kFft, MT3_ERR_UNSUPPORTED,
+              "mt3_frontend_create: fft_size %d unsupported (the reference fixes FFT_SIZE=2048, spectrograms.py:27-28)",
+              cfg->fft_size);
+  MT3_REQUIRE(cfg->hop_width > 0 && cfg->hop_width % 2 == 0 && cfg->hop_width <= kFft, MT3_ERR_BAD_ARG,
+              "mt3_frontend_create: hop_width %d must be even and in (0, %d]", cfg->hop_width, kFft);
+  MT3_REQUIRE(cfg->num_mel_bins > 0 && cfg->sample_rate > 0, MT3_ERR_BAD_ARG, "mt3_frontend_create: bad sizes");
+  Frontend* fe = new Frontend();
+  fe->cfg = *cfg;
+  fe->n_bins = cfg->fft_size / 2 + 1;
+  const int n_mel = cfg->num_mel_bins;
+
+  std::vector<float> win(kFft);
+  for (int i = 0; i < kFft; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / kFft));  // periodic Hann
+  std::vector<float2> tw(32 * 32), rt(kHalf);
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int l = 0; l < 32; ++l) {
+      const double th = -2.0 * M_PI * (double)(k1 * l) / 1024.0;
+      tw[k1 * 32 + l] = make_float2((float)cos(th), (float)sin(th));
+    }
+  for (int k = 0; k < kHalf; ++k) {
+    const double th = -2.0 * M_PI * (double)k / 2048.0;
+    rt[k] = make_float2((float)cos(th), (float)sin(th));
+  }
+  // banded form of the [n_bins, n_mel] matrix: per mel bin the contiguous span of non-zero FFT bins
+  std::vector<int> start(n_mel + 1, 0), bin0(n_mel, 0);
+  std::vector<float> w;
+  for (int m = 0; m < n_mel; ++m) {
+    int lo = -1, hi = -1;
+    for (int b = 0; b < fe->n_bins; ++b)
+      if (mel_matrix[(size_t)b * n_mel + m] != 0.f) {
+        if (lo < 0) lo = b;
+        hi = b;
+      }
+    start[m] = (int)w.size();
+    if (lo >= 0) {
+      bin0[m] = lo;
+      for (int b = lo; b <= hi; ++b) w.push_back(mel_matrix[(size_t)b * n_mel + m]);
+    }
+  }
+  start[n_mel] = (int)w.size();
+  fe->nnz = (int)w.size();
+  if (w.empty()) w.push_back(0.f);
+
+#define FE_ALLOC_COPY(dst, vec)                                                            \
+  MT3_CUDA_CHECK(cudaMalloc((void**)&(dst), (vec).size() * sizeof((vec)[0])));            \
+  MT3_CUDA_CHECK(cudaMemcpy((dst), (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice))
+  FE_ALLOC_COPY(fe->d_window, win);
+  FE_ALLOC_COPY(fe->d_tw1024, tw);
+  FE_ALLOC_COPY(fe->d_rtw, rt);
+  FE_ALLOC_COPY(fe->d_mel_start, start);
+  FE_ALLOC_COPY(fe->d_mel_bin0, bin0);
+  FE_ALLOC_COPY(fe->d_mel_w, w);
+#undef FE_ALLOC_COPY
+  *out = reinterpret_cast<mt3_frontend*>(fe);
+  return MT3_OK;
+}
+
+extern "C" int mt3_frontend_destroy(mt3_frontend* h) {
+  if (!h) return MT3_OK;
+  Frontend* fe = reinterpret_cast<Frontend*>(h);
+  cudaFree(fe->d_window);
+  cudaFree(fe->d_tw1024);
+  cudaFree(fe->d_rtw);
+  cudaFree(fe->d_mel_start);
+  cudaFree(fe->d_mel_bin0);
+  cudaFree(fe->d_mel_w);
+  delete fe;
+  return MT3_OK;
+}
+
+extern "C" int mt3_frontend_num_frames(const mt3_frontend* h, int64_t n_samples) {
+  if (!h || n_samples < 0) return fail(MT3_ERR_BAD_ARG, "mt3_frontend_num_frames: bad argument");
+  const Frontend* fe = reinterpret_cast<const Frontend*>(h);
+  return (int)((n_samples + fe->cfg.hop_width - 1) / fe->cfg.hop_width);
+}
+
+extern "C" int mt3_logmel_f32(const mt3_frontend* h, const float* audio, int64_t audio_stride, int32_t num_segments,
+                              int32_t n_samples, const int32_t* n_valid_frames, float* out, void* stream) {
+  MT3_REQUIRE(h && out, MT3_ERR_BAD_ARG, "mt3_logmel_f32: null handle/output");
+  MT3_REQUIRE(num_segments >= 0 && n_samples >= 0, MT3_ERR_BAD_ARG, "mt3_logmel_f32: negative size");
+  if (num_segments == 0 || n_samples == 0) return MT3_OK;  // empty input -> zero frames (tf.signal.frame)
+  MT3_REQUIRE(audio, MT3_ERR_BAD_ARG, "mt3_logmel_f32: null audio");
+  MT3_REQUIRE(audio_stride >= n_samples, MT3_ERR_SHAPE, "mt3_logmel_f32: audio_stride %lld < n_samples %d",
+              (long long)audio_stride, n_samples);
+  MT3_REQUIRE(num_segments <= 65535, MT3_ERR_SHAPE, "mt3_logmel_f32: more than 65535 segments per call");
+  const Frontend* fe = reinterpret_cast<const Frontend*>(h);
+  const int hop = fe->cfg.hop_width;
+  const int T = (n_samples + hop - 1) / hop;
+  constexpr int F = 16, W = 8;
+  const int chunk = (F - 1) * hop + kFft;
+  const size_t smem = (size_t)(((chunk + 3) & ~3) + kFft) * sizeof(float) + (size_t)W * kScratchF2 * sizeof(float2);
+  MT3_REQUIRE(smem <= 227 * 1024, MT3_ERR_UNSUPPORTED, "mt3_logmel_f32: hop %d needs %zu B of shared memory", hop, smem);
+  auto kern = logmel2048_kernel<F, W>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((T + F - 1) / F, num_segments);
+  kern<<<grid, W * 32, smem, (cudaStream_t)stream>>>(audio, audio_stride, n_samples, hop, n_valid_frames, T,
+                                                     fe->d_window, fe->d_tw1024, fe->d_rtw, fe->d_mel_start,
+                                                     fe->d_mel_bin0, fe->d_mel_w, fe->cfg.num_mel_bins,
+                                                     fe->cfg.log_eps, out);
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}

@@ -1,0 +1,640 @@
+// Host orchestration of the MT3 encoder / decoder on sm_100a behind the C ABI.
+//
+// Reference semantics: network.py:44-85 (EncoderLayer), :88-155 (DecoderLayer), :158-193
+// (Encoder), :196-262 (Decoder), :275-361 (Transformer.encode/decode); layers.py for the ops.
+// Data layout in HBM (all fp32, row-major):
+//   hidden h        [B*T, D]
+//   qkv             [B*T, 3Q]   columns [q | k | v], each (head, 64)
+//   cross K/V       [Ld][B*T, 2Q]  columns [k | v]          (hoisted: computed once per batch)
+//   self K/V cache  [Ld][B][L][2Q] columns [k | v]          (append = one contiguous row write)
+// The reference's [B,H,D,L] cache layout (layers.py:249-260) is a TPU scatter trick; the
+// ABI exposes tokens and logits, not the cache, so the layout is ours.
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "layers.cuh"
+
+namespace mt3 {
+
+struct ParamEntry { std::string name; int64_t rows, cols, offset; };
+
+static std::vector<ParamEntry> param_table(const mt3_model_config& c) {
+  std::vector<ParamEntry> t;
+  int64_t off = 0;
+  auto add = [&](const std::string& n, int64_t r, int64_t co) {
+    t.push_back({n, r, co, off});
+    off += r * co;
+  };
+  const int64_t D = c.emb_dim, Q = (int64_t)c.num_heads * c.head_dim, F = c.mlp_dim, V = c.vocab_size;
+  add("encoder/continuous_inputs_projection/kernel", c.input_depth, D);
+  for (int i = 0; i < c.num_encoder_layers; ++i) {
+    const std::string p = "encoder/layers_" + std::to_string(i) + "/";
+    add(p + "pre_attention_layer_norm/scale", 1, D);
+    add(p + "attention/query/kernel", D, Q);
+    add(p + "attention/key/kernel", D, Q);
+    add(p + "attention/value/kernel", D, Q);
+    add(p + "attention/out/kernel", Q, D);
+    add(p + "pre_mlp_layer_norm/scale", 1, D);
+    add(p + "mlp/wi_0/kernel", D, F);
+    add(p + "mlp/wi_1/kernel", D, F);
+    add(p + "mlp/wo/kernel", F, D);
+  }
+  add("encoder/encoder_norm/scale", 1, D);
+  add("decoder/token_embedder/embedding", V, D);
+  for (int i = 0; i < c.num_decoder_layers; ++i) {
+    const std::string p = "decoder/layers_" + std::to_string(i) + "/";
+    add(p + "pre_self_attention_layer_norm/scale", 1, D);
+    add(p + "self_attention/query/kernel", D, Q);
+    add(p + "self_attention/key/kernel", D, Q);
+    add(p + "self_attention/value/kernel", D, Q);
+    add(p + "self_attention/out/kernel", Q, D);
+    add(p + "pre_cross_attention_layer_norm/scale", 1, D);
+    add(p + "encoder_decoder_attention/query/kernel", D, Q);
+    add(p + "encoder_decoder_attention/key/kernel", D, Q);
+    add(p + "encoder_decoder_attention/value/kernel", D, Q);
+    add(p + "encoder_decoder_attention/out/kernel", Q, D);
+    add(p + "pre_mlp_layer_norm/scale", 1, D);
+    add(p + "mlp/wi_0/kernel", D, F);
+    add(p + "mlp/wi_1/kernel", D, F);
+    add(p + "mlp/wo/kernel", F, D);
+  }
+  add("decoder/decoder_norm/scale", 1, D);
+  add("decoder/logits_dense/kernel", D, V);
+  return t;
+}
+
+struct EncLayer { float *wqkv, *wo, *wi, *wo2; };
+struct DecLayer { float *wqkv, *wo, *wq_c, *wkv_c, *wo_c, *wi, *wo2; };
+
+struct Model {
+  mt3_model_config cfg;
+  int D, H, Q, F, V, Le, Ld, L;
+  float* slab = nullptr;          // all prepared weights
+  float* w_in = nullptr;
+  std::vector<EncLayer> enc;
+  float* enc_norm_g = nullptr;
+  float* emb = nullptr;
+  std::vector<DecLayer> dec;
+  float* w_logits = nullptr;
+  float* pe = nullptr;            // [2048, D] sinusoid table (FixedEmbed.max_length, layers.py:565)
+  int pe_rows = 2048;
+
+  // workspace (caller-owned)
+  char* ws = nullptr;
+  int64_t ws_bytes = 0;
+  int B = 0, T = 0;
+  float *h = nullptr, *rstd = nullptr, *qkv = nullptr, *ao = nullptr, *g = nullptr, *encoded = nullptr;
+  float *ckv = nullptr, *skv = nullptr;
+  float *dy = nullptr, *drstd = nullptr, *dq = nullptr, *dao = nullptr, *dg = nullptr, *dlogits = nullptr;
+  int *tok_cur = nullptr, *finished = nullptr, *tokens = nullptr, *state = nullptr;
+  bool have_cross = false;
+  int host_pos = 0;               // host mirror of the device position (cache overflow guard)
+
+  // CUDA graph of one greedy step
+  cudaStream_t cap_stream = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_kernels = 0;
+  int* h_flag = nullptr;          // pinned
+};
+
+static int64_t prepared_floats(const mt3_model_config& c) {
+  const int64_t D = c.emb_dim, Q = (int64_t)c.num_heads * c.head_dim, F = c.mlp_dim, V = c.vocab_size;
+  int64_t n = (int64_t)c.input_depth * D;
+  n += (int64_t)c.num_encoder_layers * (D * 3 * Q + Q * D + D * 2 * F + F * D);
+  n += D;          // encoder_norm
+  n += V * D;      // embedding
+  n += (int64_t)c.num_decoder_layers * (D * 3 * Q + Q * D + D * Q + D * 2 * Q + Q * D + D * 2 * F + F * D);
+  n += D * V;      // logits
+  n += 2048 * D;   // PE
+  return n;
+}
+
+static int prep_copy(cudaStream_t s, const float* src, int K, int N, const float* g, float* dst, int ldd, int col_off,
+                     int col_stride) {
+  const long long n = (long long)K * N;
+  scale_copy_cols_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, K, N, g, dst, ldd, col_off, col_stride);
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+#define MT3_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != MT3_OK) return _r; \
+  } while (0)
+
+static int gemm(Model* m, const GemmArgs& a, cudaStream_t s) {
+  (void)m;
+  return launch_sgemm(a, s);
+}
+
+static GemmArgs gemm_args(const float* A, int lda, const float* B, int ldb, int M, int N, int K, float* C, int ldc) {
+  GemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.M = M; a.N = N; a.K = K;
+  a.C = C; a.ldc = ldc; a.n_split = N; a.epi = EPI_STORE;
+  return a;
+}
+
+static int launch_rstd(const float* x, int ld, int M, int D, float* rstd, cudaStream_t s) {
+  row_rstd_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, ld, M, D, 1e-6f, rstd);
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
+static int set_attr_once() {
+  static bool done = false;
+  if (done) return MT3_OK;
+  MT3_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  done = true;
+  return MT3_OK;
+}
+
+static int encode_impl(Model* m, const float* x, float* encoded, cudaStream_t s) {
+  const int M = m->B * m->T, D = m->D, Q = m->Q, F = m->F;
+  MT3_TRY(set_attr_once());
+  {
+    GemmArgs a = gemm_args(x, m->cfg.input_depth, m->w_in, D, M, D, m->cfg.input_depth, m->h, D);
+    a.epi = EPI_ADD_PE; a.pe = m->pe; a.pe_T = m->T; a.pe_ld = D;
+    MT3_TRY(gemm(m, a, s));
+  }
+  const size_t attn_smem = (size_t)(32 * kHD + 32 * (m->T + 4) + 64 * 68) * sizeof(float);
+  MT3_REQUIRE(attn_smem <= 200 * 1024, MT3_ERR_UNSUPPORTED, "encode: input_length %d too long for the attention kernel", m->T);
+  for (int l = 0; l < m->Le; ++l) {
+    const EncLayer& w = m->enc[l];
+    MT3_TRY(launch_rstd(m->h, D, M, D, m->rstd, s));
+    {
+      GemmArgs a = gemm_args(m->h, D, w.wqkv, 3 * Q, M, 3 * Q, D, m->qkv, 3 * Q);
+      a.row_scale = m->rstd;
+      MT3_TRY(gemm(m, a, s));
+    }
+    {
+      dim3 grid(cdiv(m->T, 32), m->H, m->B);
+      enc_attention_kernel<<<grid, 256, attn_smem, s>>>(m->qkv, 3 * Q, m->T, m->H, m->ao, Q);
+      MT3_LAUNCH_CHECK();
+    }
+    {
+      GemmArgs a = gemm_args(m->ao, Q, w.wo, D, M, D, Q, m->h, D);
+      a.epi = EPI_RESIDUAL; a.R = m->h; a.ldr = D;
+      MT3_TRY(gemm(m, a, s));
+    }
+    MT3_TRY(launch_rstd(m->h, D, M, D, m->rstd, s));
+    {
+      GemmArgs a = gemm_args(m->h, D, w.wi, 2 * F, M, 2 * F, D, m->g, F);
+      a.row_scale = m->rstd; a.epi = EPI_GATED_GELU;
+      MT3_TRY(gemm(m, a, s));
+    }
+    {
+      GemmArgs a = gemm_args(m->g, F, w.wo2, D, M, D, F, m->h, D);
+      a.epi = EPI_RESIDUAL; a.R = m->h; a.ldr = D;
+      MT3_TRY(gemm(m, a, s));
+    }
+  }
+  rmsnorm_kernel<<<cdiv(M, 8), 256, 0, s>>>(m->h, D, M, D, 1e-6f, m->enc_norm_g, encoded, D);
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
+static int cross_kv_impl(Model* m, const float* encoded, cudaStream_t s) {
+  const int M = m->B * m->T, D = m->D, Q = m->Q;
+  for (int l = 0; l < m->Ld; ++l) {
+    GemmArgs a = gemm_args(encoded, D, m->dec[l].wkv_c, 2 * Q, M, 2 * Q, D, m->ckv + (int64_t)l * M * 2 * Q, 2 * Q);
+    MT3_TRY(gemm(m, a, s));
+  }
+  MT3_CUDA_CHECK(cudaMemsetAsync(m->state, 0, 4 * sizeof(int), s));
+  MT3_CUDA_CHECK(cudaMemsetAsync(m->finished, 0, (size_t)m->B * sizeof(int), s));
+  MT3_CUDA_CHECK(cudaMemsetAsync(m->tok_cur, 0, (size_t)m->B * sizeof(int), s));
+  m->have_cross = true;
+  m->host_pos = 0;
+  return MT3_OK;
+}
+
+// One decode step.  tok_in DEV [B]; logits DEV [B,V]; greedy != 0 runs the argmax/bookkeeping
+// kernel (tok_user optional), else only the position is advanced.
+static int decode_step_impl(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
+                            int* tokens_ws, cudaStream_t s) {
+  const int B = m->B, D = m->D, Q = m->Q, F = m->F, V = m->V, L = m->L, T = m->T;
+  int* pos = m->state;
+  embed_kernel<<<B, 128, 0, s>>>(tok_in, m->emb, D, V, m->pe, pos, m->dy);
+  MT3_LAUNCH_CHECK();
+  const int max_len_sm = (std::max(L, T) + 3) & ~3;
+  const size_t dsm = (size_t)(max_len_sm + 8 * kHD) * sizeof(float);
+  for (int l = 0; l < m->Ld; ++l) {
+    const DecLayer& w = m->dec[l];
+    float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
+    const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
+    MT3_TRY(launch_rstd(m->dy, D, B, D, m->drstd, s));
+    {  // fused RMSNorm + QKV projection + K/V cache append (layers.py:238-240, :272-289)
+      GemmArgs a = gemm_args(m->dy, D, w.wqkv, 3 * Q, B, 3 * Q, D, m->dq, Q);
+      a.row_scale = m->drstd;
+      a.n_split = Q; a.C1 = skv; a.c1_row_stride = (long long)L * 2 * Q; a.c1_pos = pos; a.c1_pos_stride = 2 * Q;
+      MT3_TRY(gemm(m, a, s));
+    }
+    dec_attention_kernel<<<dim3(m->H, B), kDecAttnThreads, dsm, s>>>(m->dq, Q, 0, skv, (long long)L * 2 * Q, 2 * Q, Q, pos,
+                                                                      1, max_len_sm, m->dao, Q);
+    MT3_LAUNCH_CHECK();
+    {
+      GemmArgs a = gemm_args(m->dao, Q, w.wo, D, B, D, Q, m->dy, D);
+      a.epi = EPI_RESIDUAL; a.R = m->dy; a.ldr = D;
+      MT3_TRY(gemm(m, a, s));
+    }
+    MT3_TRY(launch_rstd(m->dy, D, B, D, m->drstd, s));
+    {
+      GemmArgs a = gemm_args(m->dy, D, w.wq_c, Q, B, Q, D, m->dq, Q);
+      a.row_scale = m->drstd;
+      MT3_TRY(gemm(m, a, s));
+    }
+    dec_attention_kernel<<<dim3(m->H, B), kDecAttnThreads, dsm, s>>>(m->dq, Q, 0, ckv, (long long)T * 2 * Q, 2 * Q, Q,
+                                                                      nullptr, T, max_len_sm, m->dao, Q);
+    MT3_LAUNCH_CHECK();
+    {
+      GemmArgs a = gemm_args(m->dao, Q, w.wo_c, D, B, D, Q, m->dy, D);
+      a.epi = EPI_RESIDUAL; a.R = m->dy; a.ldr = D;
+      MT3_TRY(gemm(m, a, s));
+    }
+    MT3_TRY(launch_rstd(m->dy, D, B, D, m->drstd, s));
+    {
+      GemmArgs a = gemm_args(m->dy, D, w.wi, 2 * F, B, 2 * F, D, m->dg, F);
+      a.row_scale = m->drstd; a.epi = EPI_GATED_GELU;
+      MT3_TRY(gemm(m, a, s));
+    }
+    {
+      GemmArgs a = gemm_args(m->dg, F, w.wo2, D, B, D, F, m->dy, D);
+      a.epi = EPI_RESIDUAL; a.R = m->dy; a.ldr = D;
+      MT3_TRY(gemm(m, a, s));
+    }
+  }
+  MT3_TRY(launch_rstd(m->dy, D, B, D, m->drstd, s));
+  {
+    GemmArgs a = gemm_args(m->dy, D, m->w_logits, V, B, V, D, logits, V);
+    a.row_scale = m->drstd;
+    MT3_TRY(gemm(m, a, s));
+  }
+  if (greedy) {
+    argmax_step_kernel<<<B, 256, 0, s>>>(logits, V, B, use_finished ? m->tok_cur : nullptr,
+                                         use_finished ? m->finished : nullptr, tokens_ws, L, tok_user, m->state, 1);
+    MT3_LAUNCH_CHECK();
+  } else {
+    advance_pos_kernel<<<1, 1, 0, s>>>(m->state);
+    MT3_LAUNCH_CHECK();
+  }
+  return MT3_OK;
+}
+
+static void drop_graph(Model* m) {
+  if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
+  if (m->graph) cudaGraphDestroy(m->graph);
+  m->graph_exec = nullptr;
+  m->graph = nullptr;
+}
+
+static int ensure_graph(Model* m) {
+  if (m->graph_exec) return MT3_OK;
+  if (!m->cap_stream) MT3_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+  const uint64_t before = g_launch_count.load();
+  MT3_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+  int r = decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, m->cap_stream);
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
+  if (r != MT3_OK) {
+    if (g) cudaGraphDestroy(g);
+    return r;
+  }
+  if (e != cudaSuccess) return fail(MT3_ERR_CUDA, "cudaStreamEndCapture -> %s", cudaGetErrorString(e));
+  m->graph = g;
+  m->graph_kernels = g_launch_count.load() - before;
+  g_launch_count.fetch_sub(m->graph_kernels);   // capture does not execute
+  MT3_CUDA_CHECK(cudaGraphInstantiate(&m->graph_exec, m->graph, 0));
+  return MT3_OK;
+}
+
+}  // namespace mt3
+
+using namespace mt3;
+
+extern "C" int64_t mt3_model_num_params(const mt3_model_config* cfg) {
+  if (!cfg) return -1;
+  auto t = param_table(*cfg);
+  return t.back().offset + t.back().rows * t.back().cols;
+}
+
+extern "C" int64_t mt3_model_param_offset(const mt3_model_config* cfg, const char* name, int64_t* numel) {
+  if (!cfg || !name) return -1;
+  for (const auto& e : param_table(*cfg))
+    if (e.name == name) {
+      if (numel) *numel = e.rows * e.cols;
+      return e.offset;
+    }
+  return -1;
+}
+
+extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weights, mt3_model** out, void* stream) {
+  MT3_REQUIRE(cfg && weights && out, MT3_ERR_BAD_ARG, "mt3_model_create: null argument");
+  MT3_REQUIRE(cfg->head_dim == kHD, MT3_ERR_UNSUPPORTED, "mt3_model_create: head_dim %d (kernels are built for 64)", cfg->head_dim);
+  MT3_REQUIRE(cfg->emb_dim % 16 == 0 && cfg->mlp_dim % 16 == 0 && cfg->input_depth % 16 == 0 && cfg->vocab_size % 4 == 0,
+              MT3_ERR_UNSUPPORTED, "mt3_model_create: emb/mlp/input dims must be multiples of 16, vocab of 4");
+  MT3_REQUIRE(cfg->num_heads > 0 && cfg->num_encoder_layers >= 0 && cfg->num_decoder_layers > 0 && cfg->max_batch > 0 &&
+                  cfg->max_input_length > 0 && cfg->max_decode_length > 0,
+              MT3_ERR_BAD_ARG, "mt3_model_create: non-positive size");
+  MT3_REQUIRE(cfg->max_decode_length <= 2048 && cfg->max_input_length <= 2048, MT3_ERR_UNSUPPORTED,
+              "mt3_model_create: lengths above FixedEmbed.max_length=2048 (layers.py:565)");
+  MT3_REQUIRE(cfg->gemm_mode == MT3_GEMM_FP32_SIMT, MT3_ERR_UNSUPPORTED,
+              "mt3_model_create: gemm_mode %d not built in this version (only MT3_GEMM_FP32_SIMT)", cfg->gemm_mode);
+  cudaStream_t s = (cudaStream_t)stream;
+  Model* m = new Model();
+  m->cfg = *cfg;
+  m->D = cfg->emb_dim; m->H = cfg->num_heads; m->Q = cfg->num_heads * cfg->head_dim; m->F = cfg->mlp_dim;
+  m->V = cfg->vocab_size; m->Le = cfg->num_encoder_layers; m->Ld = cfg->num_decoder_layers; m->L = cfg->max_decode_length;
+  const int D = m->D, Q = m->Q, F = m->F, V = m->V;
+  cudaError_t e = cudaMalloc((void**)&m->slab, (size_t)prepared_floats(*cfg) * sizeof(float));
+  if (e != cudaSuccess) {
+    delete m;
+    return fail(MT3_ERR_CUDA, "mt3_model_create: cudaMalloc -> %s", cudaGetErrorString(e));
+  }
+  float* p = m->slab;
+  auto take = [&](int64_t n) { float* r = p; p += n; return r; };
+  auto t = param_table(*cfg);
+  auto W = [&](const std::string& n) -> const float* {
+    for (const auto& en : t) if (en.name == n) return weights + en.offset;
+    return nullptr;
+  };
+  int rc = MT3_OK;
+#define PREP(...) do { if (rc == MT3_OK) rc = prep_copy(s, __VA_ARGS__); } while (0)
+  m->w_in = take((int64_t)cfg->input_depth * D);
+  PREP(W("encoder/continuous_inputs_projection/kernel"), cfg->input_depth, D, nullptr, m->w_in, D, 0, 1);
+  m->enc.resize(m->Le);
+  for (int i = 0; i < m->Le; ++i) {
+    const std::string pre = "encoder/layers_" + std::to_string(i) + "/";
+    EncLayer& L = m->enc[i];
+    const float* g1 = W(pre + "pre_attention_layer_norm/scale");
+    const float* g2 = W(pre + "pre_mlp_layer_norm/scale");
+    L.wqkv = take((int64_t)D * 3 * Q);
+    PREP(W(pre + "attention/query/kernel"), D, Q, g1, L.wqkv, 3 * Q, 0, 1);
+    PREP(W(pre + "attention/key/kernel"), D, Q, g1, L.wqkv, 3 * Q, Q, 1);
+    PREP(W(pre + "attention/value/kernel"), D, Q, g1, L.wqkv, 3 * Q, 2 * Q, 1);
+    L.wo = take((int64_t)Q * D);
+    PREP(W(pre + "attention/out/kernel"), Q, D, nullptr, L.wo, D, 0, 1);
+    L.wi = take((int64_t)D * 2 * F);
+    PREP(W(pre + "mlp/wi_0/kernel"), D, F, g2, L.wi, 2 * F, 0, 2);
+    PREP(W(pre + "mlp/wi_1/kernel"), D, F, g2, L.wi, 2 * F, 1, 2);
+    L.wo2 = take((int64_t)F * D);
+    PREP(W(pre + "mlp/wo/kernel"), F, D, nullptr, L.wo2, D, 0, 1);
+  }
+  m->enc_norm_g = take(D);
+  PREP(W("encoder/encoder_norm/scale"), 1, D, nullptr, m->enc_norm_g, D, 0, 1);
+  m->emb = take((int64_t)V * D);
+  PREP(W("decoder/token_embedder/embedding"), V, D, nullptr, m->emb, D, 0, 1);
+  m->dec.resize(m->Ld);
+  for (int i = 0; i < m->Ld; ++i) {
+    const std::string pre = "decoder/layers_" + std::to_string(i) + "/";
+    DecLayer& L = m->dec[i];
+    const float* g1 = W(pre + "pre_self_attention_layer_norm/scale");
+    const float* g2 = W(pre + "pre_cross_attention_layer_norm/scale");
+    const float* g3 = W(pre + "pre_mlp_layer_norm/scale");
+    L.wqkv = take((int64_t)D * 3 * Q);
+    PREP(W(pre + "self_attention/query/kernel"), D, Q, g1, L.wqkv, 3 * Q, 0, 1);
+    PREP(W(pre + "self_attention/key/kernel"), D, Q, g1, L.wqkv, 3 * Q, Q, 1);
+    PREP(W(pre + "self_attention/value/kernel"), D, Q, g1, L.wqkv, 3 * Q, 2 * Q, 1);
+    L.wo = take((int64_t)Q * D);
+    PREP(W(pre + "self_attention/out/kernel"), Q, D, nullptr, L.wo, D, 0, 1);
+    L.wq_c = take((int64_t)D * Q);
+    PREP(W(pre + "encoder_decoder_attention/query/kernel"), D, Q, g2, L.wq_c, Q, 0, 1);
+    L.wkv_c = take((int64_t)D * 2 * Q);   // applied to `encoded`, which is already normed: no fold
+    PREP(W(pre + "encoder_decoder_attention/key/kernel"), D, Q, nullptr, L.wkv_c, 2 * Q, 0, 1);
+    PREP(W(pre + "encoder_decoder_attention/value/kernel"), D, Q, nullptr, L.wkv_c, 2 * Q, Q, 1);
+    L.wo_c = take((int64_t)Q * D);
+    PREP(W(pre + "encoder_decoder_attention/out/kernel"), Q, D, nullptr, L.wo_c, D, 0, 1);
+    L.wi = take((int64_t)D * 2 * F);
+    PREP(W(pre + "mlp/wi_0/kernel"), D, F, g3, L.wi, 2 * F, 0, 2);
+    PREP(W(pre + "mlp/wi_1/kernel"), D, F, g3, L.wi, 2 * F, 1, 2);
+    L.wo2 = take((int64_t)F * D);
+    PREP(W(pre + "mlp/wo/kernel"), F, D, nullptr, L.wo2, D, 0, 1);
+  }
+  m->w_logits = take((int64_t)D * V);
+  PREP(W("decoder/logits_dense/kernel"), D, V, W("decoder/decoder_norm/scale"), m->w_logits, V, 0, 1);
+#undef PREP
+  m->pe = take((int64_t)2048 * D);
+  if (rc == MT3_OK) {
+    // layers.py:51-82 (float64 on the host, rounded to float32 like the reference's numpy code)
+    std::vector<float> pe((size_t)2048 * D, 0.f);
+    const int half = D / 2;
+    const double scale_factor = -log(10000.0 / 1.0) / (double)(half - 1);
+    for (int pos = 0; pos < 2048; ++pos)
+      for (int i = 0; i < half; ++i) {
+        const double div = 1.0 * exp((double)i * scale_factor);
+        pe[(size_t)pos * D + i] = (float)sin((double)pos * div);
+        pe[(size_t)pos * D + half + i] = (float)cos((double)pos * div);
+      }
+    e = cudaMemcpyAsync(m->pe, pe.data(), pe.size() * sizeof(float), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: PE upload -> %s", cudaGetErrorString(e));
+  }
+  if (rc == MT3_OK) {
+    e = cudaMallocHost((void**)&m->h_flag, 4 * sizeof(int));
+    if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: cudaMallocHost -> %s", cudaGetErrorString(e));
+  }
+  if (rc != MT3_OK) {
+    cudaFree(m->slab);
+    delete m;
+    return rc;
+  }
+  *out = reinterpret_cast<mt3_model*>(m);
+  return MT3_OK;
+}
+
+extern "C" int mt3_model_destroy(mt3_model* h) {
+  if (!h) return MT3_OK;
+  Model* m = reinterpret_cast<Model*>(h);
+  drop_graph(m);
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  if (m->h_flag) cudaFreeHost(m->h_flag);
+  cudaFree(m->slab);
+  delete m;
+  return MT3_OK;
+}
+
+namespace {
+struct WsLayout {
+  int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, total;
+};
+WsLayout ws_layout(const Model* m, int B, int T) {
+  WsLayout w;
+  int64_t off = 0;
+  auto take = [&](int64_t bytes) { int64_t r = off; off += align_up(bytes, 256); return r; };
+  const int64_t M = (int64_t)B * T, D = m->D, Q = m->Q, F = m->F, V = m->V, L = m->L;
+  w.h = take(M * D * 4);
+  w.rstd = take(M * 4);
+  w.qkv = take(M * 3 * Q * 4);
+  w.ao = take(M * Q * 4);
+  w.g = take(M * F * 4);
+  w.encoded = take(M * D * 4);
+  w.ckv = take((int64_t)m->Ld * M * 2 * Q * 4);
+  w.skv = take((int64_t)m->Ld * B * L * 2 * Q * 4);
+  w.dy = take((int64_t)B * D * 4);
+  w.drstd = take((int64_t)B * 4);
+  w.dq = take((int64_t)B * Q * 4);
+  w.dao = take((int64_t)B * Q * 4);
+  w.dg = take((int64_t)B * F * 4);
+  w.dlogits = take((int64_t)B * V * 4);
+  w.tok_cur = take((int64_t)B * 4);
+  w.finished = take((int64_t)B * 4);
+  w.tokens = take((int64_t)B * L * 4);
+  w.state = take(64);
+  w.total = off;
+  return w;
+}
+}  // namespace
+
+extern "C" int64_t mt3_workspace_bytes(const mt3_model* h, int32_t batch, int32_t input_length) {
+  if (!h || batch <= 0 || input_length <= 0) return -1;
+  return ws_layout(reinterpret_cast<const Model*>(h), batch, input_length).total;
+}
+
+extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t bytes, int32_t batch, int32_t input_length) {
+  MT3_REQUIRE(h && workspace, MT3_ERR_BAD_ARG, "mt3_model_set_workspace: null argument");
+  Model* m = reinterpret_cast<Model*>(h);
+  MT3_REQUIRE(batch > 0 && batch <= m->cfg.max_batch, MT3_ERR_SHAPE, "batch %d outside (0, max_batch=%d]", batch, m->cfg.max_batch);
+  MT3_REQUIRE(input_length > 0 && input_length <= m->cfg.max_input_length, MT3_ERR_SHAPE,
+              "input_length %d outside (0, max_input_length=%d]", input_length, m->cfg.max_input_length);
+  MT3_REQUIRE(((uintptr_t)workspace & 255) == 0, MT3_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  const WsLayout w = ws_layout(m, batch, input_length);
+  MT3_REQUIRE(bytes >= w.total, MT3_ERR_WORKSPACE, "workspace has %lld bytes, %lld needed", (long long)bytes, (long long)w.total);
+  drop_graph(m);
+  char* b = (char*)workspace;
+  m->ws = b; m->ws_bytes = bytes; m->B = batch; m->T = input_length;
+  m->h = (float*)(b + w.h); m->rstd = (float*)(b + w.rstd); m->qkv = (float*)(b + w.qkv); m->ao = (float*)(b + w.ao);
+  m->g = (float*)(b + w.g); m->encoded = (float*)(b + w.encoded); m->ckv = (float*)(b + w.ckv); m->skv = (float*)(b + w.skv);
+  m->dy = (float*)(b + w.dy); m->drstd = (float*)(b + w.drstd); m->dq = (float*)(b + w.dq); m->dao = (float*)(b + w.dao);
+  m->dg = (float*)(b + w.dg); m->dlogits = (float*)(b + w.dlogits); m->tok_cur = (int*)(b + w.tok_cur);
+  m->finished = (int*)(b + w.finished); m->tokens = (int*)(b + w.tokens); m->state = (int*)(b + w.state);
+  m->have_cross = false;
+  return MT3_OK;
+}
+
+#define MT3_NEED_WS(m) MT3_REQUIRE((m)->ws, MT3_ERR_STATE, "no workspace set (call mt3_model_set_workspace first)")
+
+extern "C" int mt3_encode(mt3_model* h, const float* x, float* encoded, void* stream) {
+  MT3_REQUIRE(h && x && encoded, MT3_ERR_BAD_ARG, "mt3_encode: null argument");
+  Model* m = reinterpret_cast<Model*>(h);
+  MT3_NEED_WS(m);
+  return encode_impl(m, x, encoded, (cudaStream_t)stream);
+}
+
+extern "C" int mt3_cross_kv(mt3_model* h, const float* encoded, void* stream) {
+  MT3_REQUIRE(h && encoded, MT3_ERR_BAD_ARG, "mt3_cross_kv: null argument");
+  Model* m = reinterpret_cast<Model*>(h);
+  MT3_NEED_WS(m);
+  return cross_kv_impl(m, encoded, (cudaStream_t)stream);
+}
+
+extern "C" int mt3_decode_step(mt3_model* h, const int32_t* tok_in, float* logits, int32_t* tok_out, void* stream) {
+  MT3_REQUIRE(h && tok_in, MT3_ERR_BAD_ARG, "mt3_decode_step: null argument");
+  Model* m = reinterpret_cast<Model*>(h);
+  MT3_NEED_WS(m);
+  MT3_REQUIRE(m->have_cross, MT3_ERR_STATE, "mt3_decode_step before mt3_cross_kv");
+  MT3_REQUIRE(m->host_pos < m->L, MT3_ERR_STATE, "mt3_decode_step: cache full (%d steps = max_decode_length)", m->L);
+  m->host_pos += 1;
+  return decode_step_impl(m, tok_in, logits ? logits : m->dlogits, tok_out != nullptr, tok_out, 0, nullptr,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int mt3_generate(mt3_model* h, const float* x, int32_t num_steps, int32_t flags, int32_t* tokens_out,
+                            int32_t* steps_run, void* stream) {
+  MT3_REQUIRE(h && x && tokens_out, MT3_ERR_BAD_ARG, "mt3_generate: null argument");
+  Model* m = reinterpret_cast<Model*>(h);
+  MT3_NEED_WS(m);
+  MT3_REQUIRE(num_steps >= 0 && num_steps <= m->L, MT3_ERR_SHAPE, "num_steps %d outside [0, max_decode_length=%d]", num_steps, m->L);
+  MT3_REQUIRE((flags & ~(MT3_GEN_STOP_AT_EOS | MT3_GEN_USE_GRAPH)) == 0, MT3_ERR_BAD_ARG, "mt3_generate: unknown flag bits 0x%x", flags);
+  cudaStream_t s = (cudaStream_t)stream;
+  MT3_TRY(encode_impl(m, x, m->encoded, s));
+  MT3_TRY(cross_kv_impl(m, m->encoded, s));
+  MT3_CUDA_CHECK(cudaMemsetAsync(m->tokens, 0, (size_t)m->B * m->L * sizeof(int), s));
+  const bool use_graph = (flags & MT3_GEN_USE_GRAPH) != 0;
+  const bool stop = (flags & MT3_GEN_STOP_AT_EOS) != 0;
+  if (use_graph) MT3_TRY(ensure_graph(m));
+  int ran = 0;
+  for (int step = 0; step < num_steps; ++step) {
+    if (use_graph) {
+      MT3_CUDA_CHECK(cudaGraphLaunch(m->graph_exec, s));
+      count_launch(m->graph_kernels);
+    } else {
+      MT3_TRY(decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, s));
+    }
+    ++ran;
+    m->host_pos += 1;
+    if (stop && ((step & 15) == 15 || step == num_steps - 1)) {
+      MT3_CUDA_CHECK(cudaMemcpyAsync(m->h_flag, m->state + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+      MT3_CUDA_CHECK(cudaStreamSynchronize(s));
+      if (m->h_flag[0]) break;
+    }
+  }
+  MT3_CUDA_CHECK(cudaMemcpyAsync(tokens_out, m->tokens, (size_t)m->B * m->L * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (steps_run) *steps_run = ran;
+  return MT3_OK;
+}
+
+extern "C" int mt3_vocab_decode(const int32_t* ids, int32_t batch, int32_t length, int32_t num_regular_tokens, int32_t* out,
+                                void* stream) {
+  MT3_REQUIRE(ids && out, MT3_ERR_BAD_ARG, "mt3_vocab_decode: null argument");
+  MT3_REQUIRE(batch >= 0 && length >= 0 && num_regular_tokens >= 0, MT3_ERR_BAD_ARG, "mt3_vocab_decode: negative size");
+  if (batch == 0 || length == 0) return MT3_OK;
+  vocab_decode_kernel<<<cdiv(batch, 64), 64, 0, (cudaStream_t)stream>>>(ids, batch, length, num_regular_tokens, out);
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
+extern "C" int mt3_debug_launch(mt3_model* h, int32_t kind, int32_t pos, int32_t iters, void* stream) {
+  MT3_REQUIRE(h, MT3_ERR_BAD_ARG, "mt3_debug_launch: null model");
+  Model* m = reinterpret_cast<Model*>(h);
+  MT3_NEED_WS(m);
+  MT3_REQUIRE(pos >= 0 && pos < m->L && iters > 0, MT3_ERR_BAD_ARG, "mt3_debug_launch: bad pos/iters");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int B = m->B, D = m->D, Q = m->Q, L = m->L, T = m->T, M = B * T;
+  const int max_len_sm = (std::max(L, T) + 3) & ~3;
+  const size_t dsm = (size_t)(max_len_sm + 8 * kHD) * sizeof(float);
+  for (int it = 0; it < iters; ++it) {
+    const int l = it % m->Ld;
+    switch (kind) {
+      case MT3_K_DEC_SELF_ATTN: {
+        float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
+        dec_attention_kernel<<<dim3(m->H, B), kDecAttnThreads, dsm, s>>>(m->dq, Q, 0, skv, (long long)L * 2 * Q, 2 * Q, Q,
+                                                                          nullptr, pos + 1, max_len_sm, m->dao, Q);
+        MT3_LAUNCH_CHECK();
+        break;
+      }
+      case MT3_K_DEC_CROSS_ATTN: {
+        const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
+        dec_attention_kernel<<<dim3(m->H, B), kDecAttnThreads, dsm, s>>>(m->dq, Q, 0, ckv, (long long)T * 2 * Q, 2 * Q, Q,
+                                                                          nullptr, T, max_len_sm, m->dao, Q);
+        MT3_LAUNCH_CHECK();
+        break;
+      }
+      case MT3_K_DEC_QKV_GEMM: {
+        // scratch output: the encoder qkv buffer (B*T rows >= B)
+        GemmArgs a = gemm_args(m->dy, D, m->dec[l].wqkv, 3 * Q, B, 3 * Q, D, m->qkv, 3 * Q);
+        MT3_TRY(gemm(m, a, s));
+        break;
+      }
+      case MT3_K_ENC_QKV_GEMM: {
+        GemmArgs a = gemm_args(m->h, D, m->enc[it % std::max(1, m->Le)].wqkv, 3 * Q, M, 3 * Q, D, m->qkv, 3 * Q);
+        a.row_scale = m->rstd;
+        MT3_TRY(gemm(m, a, s));
+        break;
+      }
+      case MT3_K_ENC_ATTN: {
+        MT3_TRY(set_attr_once());
+        const size_t attn_smem = (size_t)(32 * kHD + 32 * (T + 4) + 64 * 68) * sizeof(float);
+        enc_attention_kernel<<<dim3(cdiv(T, 32), m->H, B), 256, attn_smem, s>>>(m->qkv, 3 * Q, T, m->H, m->ao, Q);
+        MT3_LAUNCH_CHECK();
+        break;
+      }
+      default:
+        return fail(MT3_ERR_BAD_ARG, "mt3_debug_launch: unknown kind %d", kind);
+    }
+  }
+  return MT3_OK;
+}

@@ -264,7 +264,9 @@ def init_params(cfg: T5Config, seed: int = 0, norm_scale_jitter: float = 0.0) ->
     out: Dict[str, np.ndarray] = {}
     for name, shape in param_shapes(cfg).items():
         if name.endswith("/scale"):
-            w = np.ones(shape) + norm_scale_jitter * rng.standard_normal(shape)
+            w = np.ones(shape)
+            if norm_scale_jitter > 0.0:
+                w = w + norm_scale_jitter * rng.standard_normal(shape)
         elif name.endswith("/embedding"):
             w = rng.standard_normal(shape)
         else:

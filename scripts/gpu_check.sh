@@ -1,0 +1,13 @@
+#!/bin/bash
+# One gpurun call: parity tests, smoke, bench line, ncu launch list.  Everything lands in gpurun_out/.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -x -q -m gpu -s 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.log
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
+echo "== bench"; timeout 900 python bench.py --steps 3 --warmup 3 2>&1 | tail -3 | tee gpurun_out/bench.json
+echo "== ncu launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+   python bench.py --steps 1 --warmup 3 --dec-steps 4 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+tail -2 gpurun_out/ncu_bench.log
+python scripts/summarize_launches.py gpurun_out/launches.csv 2>&1 | tail -30

@@ -1,0 +1,318 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's
+full batch -- through size-independent properties.
+
+Tolerances (north_star: "decoded event-token ids matching the reference within fp32 logit
+tolerance (mel frames within 1e-4 rel)"):
+  mel frames   |mel - mel64| <= 1e-4 * mel64 + 1e-6 * max_bin(mel64[frame])   in the linear mel
+               domain, i.e. 1e-4 relative plus the fp32 noise floor of the frame (leakage bins
+               100+ dB below the partials carry the FFT's own fp32 rounding noise);
+  logits       |l - l64| <= LOGIT_TOL * max|l64| with LOGIT_TOL = 5e-4, and never worse than
+               4x what the fp32 *oracle* itself deviates from the fp64 oracle on that input;
+  tokens       identical to the fp64 oracle's greedy tokens wherever its top-2 logit margin
+               exceeds 2x the measured logit error.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mt3_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+LOGIT_TOL = 5e-4
+DEV = "cuda:0"
+
+
+def _mel_close(lm_gpu: np.ndarray, lm64: np.ndarray):
+    mel, mel64 = np.exp(lm_gpu.astype(np.float64)), np.exp(lm64)
+    tol = 1e-4 * mel64 + 1e-6 * mel64.max(axis=-1, keepdims=True)
+    err = np.abs(mel - mel64)
+    worst = float((err / tol).max())
+    assert worst <= 1.0, f"mel frames outside tolerance: worst err/tol = {worst:.3f}"
+    return worst
+
+
+@pytest.fixture(scope="module")
+def spec_cfg():
+    from mt3_b200 import spectrograms
+    return spectrograms.SpectrogramConfig()
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 log-mel
+# ------------------------------------------------------------------------------------------------
+def test_logmel_vs_oracle_and_golden(spec_cfg):
+    from mt3_b200 import spectrograms
+    audio = np.stack([O.sine_mix(32768, seed=1234 + i) for i in range(6)] +
+                     [O.sine_mix(32768, seed=7)])
+    lm = spectrograms.compute_spectrogram(torch.from_numpy(audio).to(DEV), spec_cfg).cpu().numpy()
+    assert lm.shape == (7, 256, 512) and lm.dtype == np.float32
+    lm64 = O.compute_spectrogram(audio.astype(np.float64), np.float64)
+    _mel_close(lm, lm64)
+    g = np.load(os.path.join(GOLD, "logmel_sine_seed7.npz"))
+    _mel_close(lm[6][g["rows"]], g["logmel"])
+
+
+def test_logmel_edge_cases(spec_cfg):
+    from mt3_b200 import spectrograms
+    rng = np.random.default_rng(3)
+    # all-zero audio: safe_log's replace branch -> exactly log(1e-5)
+    z = spectrograms.compute_spectrogram(torch.zeros(32768, device=DEV), spec_cfg).cpu().numpy()
+    assert z.shape == (256, 512)
+    np.testing.assert_allclose(z, np.log(np.float32(1e-5)), rtol=1e-6)
+    # full-scale white noise
+    noise = rng.uniform(-1, 1, 32768).astype(np.float32)
+    ln = spectrograms.compute_spectrogram(torch.from_numpy(noise).to(DEV), spec_cfg).cpu().numpy()
+    _mel_close(ln, O.compute_spectrogram(noise.astype(np.float64), np.float64))
+    # ragged length (not a multiple of hop) against the committed fixture
+    g = np.load(os.path.join(GOLD, "logmel_noise_5000.npz"))
+    lr = spectrograms.compute_spectrogram(torch.from_numpy(g["audio"]).to(DEV), spec_cfg).cpu().numpy()
+    assert lr.shape == (40, 512)
+    _mel_close(lr, g["logmel"])
+    # 1 sample, and empty input (tf.signal.frame gives 1 frame / 0 frames)
+    one = spectrograms.compute_spectrogram(torch.full((1,), 0.5, device=DEV), spec_cfg).cpu().numpy()
+    assert one.shape == (1, 512)
+    _mel_close(one, O.compute_spectrogram(np.full((1,), 0.5), np.float64))
+    empty = spectrograms.compute_spectrogram(torch.zeros((3, 0), device=DEV), spec_cfg)
+    assert tuple(empty.shape) == (3, 0, 512)
+    # short last segment: rows past n_valid are the feature converter's 0.0 padding (models.py:96)
+    a = torch.from_numpy(np.stack([O.sine_mix(32768, 1), O.sine_mix(32768, 2)])).to(DEV)
+    a[1, 229 * 128:] = 0
+    nv = torch.tensor([256, 229], dtype=torch.int32, device=DEV)
+    lv = spectrograms.compute_spectrogram(a, spec_cfg, n_valid_frames=nv).cpu().numpy()
+    assert (lv[1, 229:] == 0).all() and (lv[0] != 0).any()
+    short = O.compute_spectrogram(a[1, :229 * 128].cpu().numpy().astype(np.float64), np.float64)
+    _mel_close(lv[1, :229], short)
+    # strided rows
+    big = torch.zeros((4, 40000), device=DEV)
+    big[:, :32768] = a[0]
+    ls = spectrograms.compute_spectrogram(big[:, :32768], spec_cfg).cpu().numpy()
+    np.testing.assert_array_equal(ls[2], lv[0])
+
+
+def test_logmel_shift_property_full_batch(spec_cfg):
+    """Size-independent property at the full B=64: a frame's output depends only on its own 2048
+    samples, so shifting a segment by k hops shifts the frames bit-exactly."""
+    from mt3_b200 import spectrograms
+    audio = np.stack([O.sine_mix(32768 + 5 * 128, seed=100 + i) for i in range(64)])
+    a = torch.from_numpy(audio).to(DEV)
+    base = spectrograms.compute_spectrogram(a[:, :32768], spec_cfg)
+    shifted = spectrograms.compute_spectrogram(a[:, 5 * 128:], spec_cfg)
+    # frames whose 2048-sample window lies inside both views
+    n_ok = 256 - 16 - 5
+    assert torch.equal(base[:, 5:5 + n_ok], shifted[:, :n_ok])
+
+
+# ------------------------------------------------------------------------------------------------
+# Encoder / decoder
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def mt3_model():
+    from mt3_b200 import network
+    cfg = network.T5Config(vocab_size=1536, emb_dim=512, num_heads=6, num_encoder_layers=8, num_decoder_layers=8,
+                           head_dim=64, mlp_dim=1024, mlp_activations=('gelu', 'linear'))
+    ocfg = O.T5Config()
+    params = O.init_params(ocfg, seed=0, norm_scale_jitter=0.05)
+    model = network.Transformer(cfg, params, device=DEV, max_batch=64, max_input_length=256, max_decode_length=1024)
+    return model, ocfg, params
+
+
+def _inputs(b, t=256, seed=0):
+    audio = np.stack([O.sine_mix(t * 128, seed=1234 + seed + i) for i in range(b)])
+    return O.compute_spectrogram(audio, np.float32)
+
+
+def test_encoder_parity(mt3_model):
+    model, ocfg, params = mt3_model
+    x = _inputs(2)
+    enc = model.encode(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    enc64 = O.encode(params, ocfg, x, np.float64)
+    enc32 = O.encode(params, ocfg, x, np.float32)
+    scale = np.abs(enc64).max()
+    e_gpu, e_f32 = np.abs(enc - enc64).max() / scale, np.abs(enc32 - enc64).max() / scale
+    print(f"encoder: gpu vs fp64 {e_gpu:.3e}   fp32-oracle vs fp64 {e_f32:.3e}")
+    assert e_gpu <= max(LOGIT_TOL, 4 * e_f32)
+    assert e_gpu <= 4 * e_f32 + 1e-5, "CUDA encoder is much less accurate than the reference's fp32 arithmetic"
+
+
+def test_decoder_teacher_forced_logits_and_tokens(mt3_model):
+    model, ocfg, params = mt3_model
+    x = _inputs(2, seed=10)
+    enc64 = O.encode(params, ocfg, x, np.float64)
+    steps = 12
+    toks64, logits64 = O.greedy_decode(params, ocfg, enc64, steps, np.float64, stop_at_eos=False, return_logits=True)
+    dec_in = np.concatenate([np.zeros((2, 1), np.int64), toks64[:, :steps - 1]], axis=1)
+    _, logits32 = O.greedy_decode(params, ocfg, enc64.astype(np.float32), steps, np.float32, stop_at_eos=False,
+                                  return_logits=True, forced_tokens=dec_in)
+    enc_gpu = model.encode(torch.from_numpy(x).to(DEV))
+    lg = model.teacher_forced_logits(enc_gpu, torch.from_numpy(dec_in).to(DEV).to(torch.int32)).cpu().numpy()
+    scale = np.abs(logits64).max()
+    e_gpu, e_f32 = np.abs(lg - logits64).max() / scale, np.abs(logits32 - logits64).max() / scale
+    print(f"logits: gpu vs fp64 {e_gpu:.3e}   fp32-oracle vs fp64 {e_f32:.3e}")
+    assert e_gpu <= max(LOGIT_TOL, 4 * e_f32)
+    # free-running greedy tokens where the margin allows
+    out = model.generate(torch.from_numpy(x).to(DEV), num_steps=steps, stop_at_eos=False, use_graph=False).cpu().numpy()
+    srt = np.sort(logits64, axis=-1)
+    margin = srt[..., -1] - srt[..., -2]
+    safe = np.cumprod(margin > 2 * e_gpu * scale, axis=1).astype(bool)     # only up to the first risky step
+    np.testing.assert_array_equal(out[:, :steps][safe], toks64[:, :steps][safe])
+    assert (out[:, steps:] == 0).all()
+
+
+def test_model_tiny_golden_fixture():
+    """Committed oracle fixture (mt3 layer sizes, 1+1 layers, T=32)."""
+    from mt3_b200 import network
+    g = np.load(os.path.join(GOLD, "model_tiny.npz"))
+    ocfg = O.T5Config(vocab_size=1536, num_encoder_layers=1, num_decoder_layers=1)
+    params = O.init_params(ocfg, seed=int(g["weight_seed"]), norm_scale_jitter=float(g["jitter"]))
+    cfg = network.T5Config(vocab_size=1536, emb_dim=512, num_heads=6, num_encoder_layers=1, num_decoder_layers=1,
+                           head_dim=64, mlp_dim=1024, mlp_activations=('gelu', 'linear'))
+    m = network.Transformer(cfg, params, device=DEV, max_batch=2, max_input_length=32, max_decode_length=16)
+    x = torch.from_numpy(g["x"]).to(DEV)
+    enc = m.encode(x)
+    np.testing.assert_allclose(enc.cpu().numpy()[:, ::8, ::16], g["encoded"], rtol=1e-3, atol=2e-4)
+    dec_in = np.concatenate([np.zeros((2, 1), np.int64), g["tokens"][:, :5]], axis=1)
+    lg = m.teacher_forced_logits(enc, torch.from_numpy(dec_in).to(DEV).to(torch.int32)).cpu().numpy()
+    assert np.abs(lg[:, :, ::16] - g["logits"]).max() <= LOGIT_TOL * np.abs(g["logits"]).max()
+    toks = m.generate(x, num_steps=6, stop_at_eos=False, use_graph=True).cpu().numpy()
+    np.testing.assert_array_equal(toks[:, :6], g["tokens"])
+
+
+def _eos_params(ocfg, seed, boost):
+    """Random weights never emit EOS at a useful rate; scaling the EOS column of logits_dense
+    makes EOS win whenever its projection is positive, so sequences end at scattered steps."""
+    p = O.init_params(ocfg, seed=seed)
+    w = p["decoder/logits_dense/kernel"].copy()
+    w[:, O.EOS_ID] *= boost
+    p["decoder/logits_dense/kernel"] = w
+    return p
+
+
+def test_generate_eos_semantics_and_graph_equivalence():
+    from mt3_b200 import network
+    ocfg = O.T5Config(vocab_size=1536, num_encoder_layers=2, num_decoder_layers=2)
+    params = _eos_params(ocfg, seed=9, boost=6.0)
+    cfg = network.T5Config(vocab_size=1536, emb_dim=512, num_heads=6, num_encoder_layers=2, num_decoder_layers=2,
+                           head_dim=64, mlp_dim=1024, mlp_activations=('gelu', 'linear'))
+    L = 48
+    m = network.Transformer(cfg, params, device=DEV, max_batch=4, max_input_length=64, max_decode_length=L)
+    x = _inputs(4, t=64, seed=50)
+    enc64 = O.encode(params, ocfg, x, np.float64)
+    ref = O.greedy_decode(params, ocfg, enc64, L, np.float64, stop_at_eos=True)
+    has_eos = (ref == O.EOS_ID).any(axis=1)
+    assert has_eos.any(), "test weights did not produce any EOS; raise the boost"
+    xg = torch.from_numpy(x).to(DEV)
+    t_plain = m.generate(xg, stop_at_eos=True, use_graph=False).cpu().numpy()
+    steps_plain = m.last_steps_run
+    t_graph = m.generate(xg, stop_at_eos=True, use_graph=True).cpu().numpy()
+    t_full = m.generate(xg, stop_at_eos=False, use_graph=True).cpu().numpy()
+    np.testing.assert_array_equal(t_plain, t_graph)
+    np.testing.assert_array_equal(t_plain, t_full)          # finished sequences keep emitting PAD
+    if has_eos.all():
+        assert steps_plain < L                               # the loop really stopped early
+    # zeros after the first EOS, identical prefix to the oracle where margins are safe
+    for b in range(4):
+        row = t_plain[b]
+        if (row == 1).any():
+            first = int(np.argmax(row == 1))
+            assert (row[first + 1:] == 0).all()
+    _, logits64 = O.greedy_decode(params, ocfg, enc64, L, np.float64, stop_at_eos=False, return_logits=True)
+    srt = np.sort(logits64, axis=-1)
+    safe = np.cumprod((srt[..., -1] - srt[..., -2]) > 1e-3 * np.abs(logits64).max(), axis=1).astype(bool)
+    ref_full = O.greedy_decode(params, ocfg, enc64, L, np.float64, stop_at_eos=False)
+    alive = np.cumsum(ref_full == 1, axis=1) - (ref_full == 1) == 0   # up to and including first EOS
+    sel = safe & alive
+    np.testing.assert_array_equal(t_plain[sel], ref_full[sel])
+    # vocabulary decode kernel == oracle (vocabularies.py:241-271)
+    from mt3_b200 import vocabularies
+    vocab = vocabularies.GenericTokenVocabulary(1388, extra_ids=100)
+    dec = vocab.decode_tf(torch.from_numpy(t_plain).to(DEV)).cpu().numpy()
+    np.testing.assert_array_equal(dec, O.vocab_decode(t_plain, 1388))
+
+
+def test_vocab_decode_kernel_random():
+    from mt3_b200 import vocabularies
+    rng = np.random.default_rng(0)
+    ids = rng.integers(0, 1536, size=(64, 1024)).astype(np.int32)
+    ids[rng.random(ids.shape) < 0.002] = 1
+    ids[5] = 7            # no EOS at all
+    vocab = vocabularies.GenericTokenVocabulary(1388, extra_ids=100)
+    got = vocab.decode_tf(torch.from_numpy(ids).to(DEV)).cpu().numpy()
+    np.testing.assert_array_equal(got, O.vocab_decode(ids, 1388))
+
+
+def test_batch_invariance_full_batch(mt3_model):
+    """Size-independent property at the full B=64: segments are independent (data-parallel unit),
+    so a segment's tokens do not depend on which batch it was decoded in."""
+    model, _, _ = mt3_model
+    x = torch.from_numpy(_inputs(64, seed=200)).to(DEV)
+    steps = 24
+    full = model.generate(x, num_steps=steps, stop_at_eos=False, use_graph=True)
+    sub = model.generate(x[8:16].contiguous(), num_steps=steps, stop_at_eos=False, use_graph=True)
+    assert torch.equal(full[8:16], sub)
+    enc_full = model.encode(x)
+    enc_sub = model.encode(x[40:44].contiguous())
+    assert torch.equal(enc_full[40:44], enc_sub)
+
+
+def test_error_paths(mt3_model):
+    from mt3_b200 import _lib
+    model, _, _ = mt3_model
+    with pytest.raises(TypeError):
+        model.encode(torch.zeros(1, 256, 512))                       # CPU tensor
+    with pytest.raises(ValueError):
+        model.encode(torch.zeros(1, 256, 100, device=DEV))           # wrong depth
+    with pytest.raises(_lib.Mt3Error):
+        model.encode(torch.zeros(65, 256, 512, device=DEV))          # batch > max_batch
+    with pytest.raises(_lib.Mt3Error):
+        model.generate(torch.zeros(1, 256, 512, device=DEV), num_steps=2000)
+    enc = model.encode(torch.zeros(1, 256, 512, device=DEV))
+    model.init_cache(enc)
+    with pytest.raises(ValueError):
+        model.decode(enc, None, torch.zeros(1, 2, dtype=torch.int32, device=DEV))   # layers.py:266-270
+    with pytest.raises(ValueError):
+        model.decode(enc, None, torch.zeros(1, 1, device=DEV))                      # layers.py:528-529
+
+
+def test_inference_model_api_end_to_end():
+    from mt3_b200 import inference
+    im = inference.InferenceModel('synthetic:0', 'mt3', device=DEV, batch_size=8)
+    assert (im.inputs_length, im.outputs_length, im.batch_size) == (256, 1024, 8)
+    assert im.sequence_length == {'inputs': 256, 'targets': 1024}
+    assert im.input_shapes['encoder_input_tokens'] == (8, 256)
+    assert im.model.config.vocab_size == 1536
+    audio = np.concatenate([O.sine_mix(32768, 1), O.sine_mix(32768, 2), O.sine_mix(20000, 3)])   # 2.6 segments
+    ds = im.preprocess(im.audio_to_dataset(audio))
+    assert len(ds) == 3 and ds[2]['inputs'].shape[0] == (len(audio) + 128 - len(audio) % 128) // 128 - 512
+    # predict_tokens on a hand-made batch == oracle pipeline semantics (decoded ids)
+    spec = O.compute_spectrogram(np.stack([audio[:32768], audio[32768:65536]]), np.float32)
+    toks = im.model.generate(torch.from_numpy(spec).to(DEV), num_steps=8, stop_at_eos=False).cpu().numpy()
+    dec = im.vocabulary.decode_tf(toks)
+    np.testing.assert_array_equal(dec, O.vocab_decode(toks, 1388))
+    with pytest.raises(ValueError):
+        inference.InferenceModel('synthetic', 'bogus')
+    ism = inference.InferenceModel('synthetic:1', 'ismir2021', device=DEV, batch_size=1)
+    assert ism.inputs_length == 512 and ism.model.config.vocab_size == 1664
+    clip = O.sine_mix(32000, 5)                                   # BASELINE config 1: single 2 s clip
+    frames, times = ism._audio_to_frames(clip)
+    assert frames.shape == (251, 128)
+    seg = np.zeros((1, 512 * 128), np.float32)
+    seg[0, :251 * 128] = frames.reshape(-1)
+    out = ism.transcribe_segments(seg, n_valid_frames=np.array([251], np.int32), num_steps=6, stop_at_eos=False)
+    assert out.shape == (1, 1024) and out.dtype == np.int32
+    # against the oracle on the same padded spectrogram
+    ocfg = O.T5Config(vocab_size=1664)
+    from mt3_b200 import weights
+    params = weights.synthetic_params(ism.model.config, 1)
+    spec = O.pad_inputs(O.compute_spectrogram(frames.reshape(-1), np.float32), 512)[None]
+    enc64 = O.encode(params, ocfg, spec, np.float64)
+    ref, lg = O.greedy_decode(params, ocfg, enc64, 6, np.float64, stop_at_eos=False, return_logits=True)
+    srt = np.sort(lg, -1)
+    safe = np.cumprod((srt[..., -1] - srt[..., -2]) > 1e-3 * np.abs(lg).max(), axis=1).astype(bool)
+    np.testing.assert_array_equal(out[:, :6][safe], O.vocab_decode(ref[:, :6], 1514)[safe])
