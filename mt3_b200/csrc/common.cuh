@@ -54,4 +54,10 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// x = hi + lo with hi = x truncated to tf32 (what kind::tf32 reads), lo = x - hi (exact in fp32).
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
 }  // namespace mt3

@@ -10,15 +10,21 @@ namespace mt3 {
 // ---------------------------------------------------------------------------------
 // RMSNorm (layers.py:604-621): rstd[m] = 1/sqrt(mean(x[m,:]^2) + eps).  One warp per row.
 // ---------------------------------------------------------------------------------
-__global__ void row_rstd_kernel(const float* __restrict__ x, int ld, int M, int D, float eps,
-                                float* __restrict__ rstd) {
+// x_lo != null: the row is stored as a tf32 hi/lo pair (x = x_hi + x_lo exactly).
+__global__ void row_rstd_kernel(const float* __restrict__ x, const float* __restrict__ x_lo, int ld, int M, int D,
+                                float eps, float* __restrict__ rstd) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const float4* p = reinterpret_cast<const float4*>(x + (long long)row * ld);
+  const float4* pl = x_lo ? reinterpret_cast<const float4*>(x_lo + (long long)row * ld) : nullptr;
   float s = 0.f;
   for (int i = lane; i < D / 4; i += 32) {
-    const float4 v = p[i];
+    float4 v = p[i];
+    if (pl) {
+      const float4 w = pl[i];
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
     s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   s = warp_sum(s);
@@ -27,15 +33,24 @@ __global__ void row_rstd_kernel(const float* __restrict__ x, int ld, int M, int 
 
 // y = x * rstd * g  (materialised only where the reference's API returns the normed
 // tensor itself: `encoded`, network.py:192).
-__global__ void rmsnorm_kernel(const float* __restrict__ x, int ldx, int M, int D, float eps,
-                               const float* __restrict__ g, float* __restrict__ y, int ldy) {
+__global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ x_lo, int ldx, int M, int D,
+                               float eps, const float* __restrict__ g, float* __restrict__ y, int ldy) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   const float4* p = reinterpret_cast<const float4*>(x + (long long)row * ldx);
+  const float4* pl = x_lo ? reinterpret_cast<const float4*>(x_lo + (long long)row * ldx) : nullptr;
+  auto ld4 = [&](int i) {
+    float4 v = p[i];
+    if (pl) {
+      const float4 w = pl[i];
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    return v;
+  };
   float s = 0.f;
   for (int i = lane; i < D / 4; i += 32) {
-    const float4 v = p[i];
+    const float4 v = ld4(i);
     s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
   s = warp_sum(s);
@@ -43,7 +58,7 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, int ldx, int M, int 
   float4* q = reinterpret_cast<float4*>(y + (long long)row * ldy);
   const float4* gg = reinterpret_cast<const float4*>(g);
   for (int i = lane; i < D / 4; i += 32) {
-    const float4 v = p[i];
+    const float4 v = ld4(i);
     const float4 w = __ldg(gg + i);
     q[i] = make_float4(v.x * r * w.x, v.y * r * w.y, v.z * r * w.z, v.w * r * w.w);
   }
@@ -58,7 +73,8 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, int ldx, int M, int 
 constexpr int kHD = 64;   // head_dim the kernels are specialised for (gin/model.gin:54)
 
 __global__ void __launch_bounds__(256)
-enc_attention_kernel(const float* __restrict__ qkv, int ld, int T, int H, float* __restrict__ out, int ldo) {
+enc_attention_kernel(const float* __restrict__ qkv, int ld, int T, int H, float* __restrict__ out,
+                     float* __restrict__ out_lo, int ldo) {
   extern __shared__ __align__(16) float sm[];
   constexpr int QT = 32, KT = 64;
   const int SP = T + 4;
@@ -151,10 +167,22 @@ enc_attention_kernel(const float* __restrict__ qkv, int ld, int T, int H, float*
       o1[2] = fmaf(p1, vv.z, o1[2]); o1[3] = fmaf(p1, vv.w, o1[3]);
     }
   }
-  float* ob = out + (long long)b * T * ldo + h * kHD + td * 4;
-  if (q0 + tq < T) *reinterpret_cast<float4*>(ob + (long long)(q0 + tq) * ldo) = make_float4(o0[0], o0[1], o0[2], o0[3]);
-  if (q0 + tq + 16 < T)
-    *reinterpret_cast<float4*>(ob + (long long)(q0 + tq + 16) * ldo) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+  const long long obase = (long long)b * T * ldo + h * kHD + td * 4;
+  auto store = [&](int row, const float (&o)[4]) {
+    if (row >= T) return;
+    const long long off = obase + (long long)row * ldo;
+    if (out_lo) {
+      float hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_tf32(o[j], hi[j], lo[j]);
+      *reinterpret_cast<float4*>(out + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(out_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    } else {
+      *reinterpret_cast<float4*>(out + off) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  };
+  store(q0 + tq, o0);
+  store(q0 + tq + 16, o1);
 }
 
 // ---------------------------------------------------------------------------------
@@ -343,6 +371,43 @@ __global__ void scale_copy_cols_kernel(const float* __restrict__ src, int K, int
   if (i >= (long long)K * N) return;
   const int k = (int)(i / N), n = (int)(i % N);
   dst[(long long)k * ldd + col_off + (long long)n * col_stride] = src[i] * (g ? g[k] : 1.f);
+}
+
+// hi/lo split of a dense fp32 array (tf32x3 operands)
+__global__ void split_pair_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  float4 h, l;
+  split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+  reinterpret_cast<float4*>(hi)[i] = h;
+  reinterpret_cast<float4*>(lo)[i] = l;
+}
+
+// src [K, N] row-major -> dst_hi (/dst_lo) [N, K]: the K-major ("transposed") weight layout the UMMA B operand reads.
+__global__ void transpose_split_kernel(const float* __restrict__ src, int K, int N, float* __restrict__ dst_hi,
+                                       float* __restrict__ dst_lo) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? src[(long long)k * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N && k < K) {
+      const float v = tile[threadIdx.x][i];
+      if (dst_lo) {
+        float h, l;
+        split_tf32(v, h, l);
+        dst_hi[(long long)n * K + k] = h;
+        dst_lo[(long long)n * K + k] = l;
+      } else {
+        dst_hi[(long long)n * K + k] = v;
+      }
+    }
+  }
 }
 
 }  // namespace mt3

@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 #include "layers.cuh"
 
 namespace mt3 {
@@ -67,13 +68,22 @@ static std::vector<ParamEntry> param_table(const mt3_model_config& c) {
   return t;
 }
 
-struct EncLayer { float *wqkv, *wo, *wi, *wo2; };
-struct DecLayer { float *wqkv, *wo, *wq_c, *wkv_c, *wo_c, *wi, *wo2; };
+// K-major ("transposed", [N,K]) copy of a prepared weight for the tcgen05 path, optionally tf32 hi/lo split.
+struct TcW { float* hi = nullptr; float* lo = nullptr; TcOperand op; int K = 0, N = 0; };
+// An activation buffer [rows, ld]; lo != null when it is carried as a tf32 hi/lo pair.
+struct Act { float* hi = nullptr; float* lo = nullptr; TcOperand op; };
+
+struct EncLayer { float *wqkv, *wo, *wi, *wo2; TcW t_wqkv, t_wo, t_wi, t_wo2; };
+struct DecLayer { float *wqkv, *wo, *wq_c, *wkv_c, *wo_c, *wi, *wo2; TcW t_wkv_c; };
 
 struct Model {
   mt3_model_config cfg;
   int D, H, Q, F, V, Le, Ld, L;
   float* slab = nullptr;          // all prepared weights
+  float* slab_tc = nullptr;       // K-major (and hi/lo) copies for the tcgen05 path
+  bool tc = false, split3 = false;
+  TcW t_w_in;
+  Act a_x, a_h, a_ao, a_g, a_enc; // tcgen05-path activation buffers (workspace)
   float* w_in = nullptr;
   std::vector<EncLayer> enc;
   float* enc_norm_g = nullptr;
@@ -141,7 +151,7 @@ static GemmArgs gemm_args(const float* A, int lda, const float* B, int ldb, int 
 }
 
 static int launch_rstd(const float* x, int ld, int M, int D, float* rstd, cudaStream_t s) {
-  row_rstd_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, ld, M, D, 1e-6f, rstd);
+  row_rstd_kernel<<<cdiv(M, 8), 256, 0, s>>>(x, nullptr, ld, M, D, 1e-6f, rstd);
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }
@@ -154,7 +164,105 @@ static int set_attr_once() {
   return MT3_OK;
 }
 
+static int prep_tc_weight(Model* m, cudaStream_t s, const float* w, int K, int N, float*& cursor, TcW* out) {
+  out->K = K; out->N = N;
+  out->hi = cursor; cursor += (int64_t)K * N;
+  if (m->split3) { out->lo = cursor; cursor += (int64_t)K * N; }
+  transpose_split_kernel<<<dim3(cdiv(N, 32), cdiv(K, 32)), dim3(32, 8), 0, s>>>(w, K, N, out->hi, out->lo);
+  MT3_LAUNCH_CHECK();
+  return make_operand(&out->op, out->hi, out->lo, N, K, K);
+}
+
+static int64_t tc_weight_floats(const mt3_model_config& c) {
+  const int64_t D = c.emb_dim, Q = (int64_t)c.num_heads * c.head_dim, F = c.mlp_dim;
+  int64_t n = (int64_t)c.input_depth * D;
+  n += (int64_t)c.num_encoder_layers * (D * 3 * Q + Q * D + D * 2 * F + F * D);
+  n += (int64_t)c.num_decoder_layers * (D * 2 * Q);
+  return n * (c.gemm_mode == MT3_GEMM_TF32X3 ? 2 : 1);
+}
+
+static TcGemmArgs tc_args(int M, int N, int K, float* C_hi, float* C_lo, int ldc) {
+  TcGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.M = M; a.N = N; a.K = K; a.C_hi = C_hi; a.C_lo = C_lo; a.ldc = ldc; a.n_split = N; a.epi = EPI_STORE;
+  return a;
+}
+
+// Encoder on the tcgen05 path.  Activations that feed a GEMM are kept as tf32 hi/lo pairs in TF32X3 mode.
+static int encode_tc_impl(Model* m, const float* x, float* encoded, cudaStream_t s) {
+  const int M = m->B * m->T, D = m->D, Q = m->Q, F = m->F, depth = m->cfg.input_depth;
+  MT3_TRY(set_attr_once());
+  TcOperand opx;
+  if (m->split3) {
+    const long long n4 = (long long)M * depth / 4;
+    split_pair_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(x, m->a_x.hi, m->a_x.lo, n4);
+    MT3_LAUNCH_CHECK();
+    opx = m->a_x.op;
+  } else {
+    MT3_TRY(make_operand(&opx, x, nullptr, M, depth, depth));
+  }
+  {
+    TcGemmArgs a = tc_args(M, D, depth, m->a_h.hi, m->a_h.lo, D);
+    a.epi = EPI_ADD_PE; a.pe = m->pe; a.pe_T = m->T; a.pe_ld = D;
+    MT3_TRY(launch_tc_gemm(opx, m->t_w_in.op, a, m->split3, s));
+  }
+  const size_t attn_smem = (size_t)(32 * kHD + 32 * (m->T + 4) + 64 * 68) * sizeof(float);
+  MT3_REQUIRE(attn_smem <= 200 * 1024, MT3_ERR_UNSUPPORTED, "encode: input_length %d too long for the attention kernel", m->T);
+  for (int l = 0; l < m->Le; ++l) {
+    const EncLayer& w = m->enc[l];
+    row_rstd_kernel<<<cdiv(M, 8), 256, 0, s>>>(m->a_h.hi, m->a_h.lo, D, M, D, 1e-6f, m->rstd);
+    MT3_LAUNCH_CHECK();
+    {
+      TcGemmArgs a = tc_args(M, 3 * Q, D, m->qkv, nullptr, 3 * Q);
+      a.row_scale = m->rstd;
+      MT3_TRY(launch_tc_gemm(m->a_h.op, w.t_wqkv.op, a, m->split3, s));
+    }
+    enc_attention_kernel<<<dim3(cdiv(m->T, 32), m->H, m->B), 256, attn_smem, s>>>(m->qkv, 3 * Q, m->T, m->H, m->a_ao.hi,
+                                                                                   m->a_ao.lo, Q);
+    MT3_LAUNCH_CHECK();
+    {
+      TcGemmArgs a = tc_args(M, D, Q, m->a_h.hi, m->a_h.lo, D);
+      a.epi = EPI_RESIDUAL; a.R_hi = m->a_h.hi; a.R_lo = m->a_h.lo; a.ldr = D;
+      MT3_TRY(launch_tc_gemm(m->a_ao.op, w.t_wo.op, a, m->split3, s));
+    }
+    row_rstd_kernel<<<cdiv(M, 8), 256, 0, s>>>(m->a_h.hi, m->a_h.lo, D, M, D, 1e-6f, m->rstd);
+    MT3_LAUNCH_CHECK();
+    {
+      TcGemmArgs a = tc_args(M, 2 * F, D, m->a_g.hi, m->a_g.lo, F);
+      a.row_scale = m->rstd; a.epi = EPI_GATED_GELU;
+      MT3_TRY(launch_tc_gemm(m->a_h.op, w.t_wi.op, a, m->split3, s));
+    }
+    {
+      TcGemmArgs a = tc_args(M, D, F, m->a_h.hi, m->a_h.lo, D);
+      a.epi = EPI_RESIDUAL; a.R_hi = m->a_h.hi; a.R_lo = m->a_h.lo; a.ldr = D;
+      MT3_TRY(launch_tc_gemm(m->a_g.op, w.t_wo2.op, a, m->split3, s));
+    }
+  }
+  rmsnorm_kernel<<<cdiv(M, 8), 256, 0, s>>>(m->a_h.hi, m->a_h.lo, D, M, D, 1e-6f, m->enc_norm_g, encoded, D);
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
+static int cross_kv_tc_impl(Model* m, const float* encoded, cudaStream_t s) {
+  const int M = m->B * m->T, D = m->D, Q = m->Q;
+  TcOperand ope;
+  if (m->split3) {
+    const long long n4 = (long long)M * D / 4;
+    split_pair_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(encoded, m->a_enc.hi, m->a_enc.lo, n4);
+    MT3_LAUNCH_CHECK();
+    ope = m->a_enc.op;
+  } else {
+    MT3_TRY(make_operand(&ope, encoded, nullptr, M, D, D));
+  }
+  for (int l = 0; l < m->Ld; ++l) {
+    TcGemmArgs a = tc_args(M, 2 * Q, D, m->ckv + (int64_t)l * M * 2 * Q, nullptr, 2 * Q);
+    MT3_TRY(launch_tc_gemm(ope, m->dec[l].t_wkv_c.op, a, m->split3, s));
+  }
+  return MT3_OK;
+}
+
 static int encode_impl(Model* m, const float* x, float* encoded, cudaStream_t s) {
+  if (m->tc) return encode_tc_impl(m, x, encoded, s);
   const int M = m->B * m->T, D = m->D, Q = m->Q, F = m->F;
   MT3_TRY(set_attr_once());
   {
@@ -174,7 +282,7 @@ static int encode_impl(Model* m, const float* x, float* encoded, cudaStream_t s)
     }
     {
       dim3 grid(cdiv(m->T, 32), m->H, m->B);
-      enc_attention_kernel<<<grid, 256, attn_smem, s>>>(m->qkv, 3 * Q, m->T, m->H, m->ao, Q);
+      enc_attention_kernel<<<grid, 256, attn_smem, s>>>(m->qkv, 3 * Q, m->T, m->H, m->ao, nullptr, Q);
       MT3_LAUNCH_CHECK();
     }
     {
@@ -194,16 +302,20 @@ static int encode_impl(Model* m, const float* x, float* encoded, cudaStream_t s)
       MT3_TRY(gemm(m, a, s));
     }
   }
-  rmsnorm_kernel<<<cdiv(M, 8), 256, 0, s>>>(m->h, D, M, D, 1e-6f, m->enc_norm_g, encoded, D);
+  rmsnorm_kernel<<<cdiv(M, 8), 256, 0, s>>>(m->h, nullptr, D, M, D, 1e-6f, m->enc_norm_g, encoded, D);
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }
 
 static int cross_kv_impl(Model* m, const float* encoded, cudaStream_t s) {
   const int M = m->B * m->T, D = m->D, Q = m->Q;
-  for (int l = 0; l < m->Ld; ++l) {
-    GemmArgs a = gemm_args(encoded, D, m->dec[l].wkv_c, 2 * Q, M, 2 * Q, D, m->ckv + (int64_t)l * M * 2 * Q, 2 * Q);
-    MT3_TRY(gemm(m, a, s));
+  if (m->tc) {
+    MT3_TRY(cross_kv_tc_impl(m, encoded, s));
+  } else {
+    for (int l = 0; l < m->Ld; ++l) {
+      GemmArgs a = gemm_args(encoded, D, m->dec[l].wkv_c, 2 * Q, M, 2 * Q, D, m->ckv + (int64_t)l * M * 2 * Q, 2 * Q);
+      MT3_TRY(gemm(m, a, s));
+    }
   }
   MT3_CUDA_CHECK(cudaMemsetAsync(m->state, 0, 4 * sizeof(int), s));
   MT3_CUDA_CHECK(cudaMemsetAsync(m->finished, 0, (size_t)m->B * sizeof(int), s));
@@ -342,8 +454,11 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
               MT3_ERR_BAD_ARG, "mt3_model_create: non-positive size");
   MT3_REQUIRE(cfg->max_decode_length <= 2048 && cfg->max_input_length <= 2048, MT3_ERR_UNSUPPORTED,
               "mt3_model_create: lengths above FixedEmbed.max_length=2048 (layers.py:565)");
-  MT3_REQUIRE(cfg->gemm_mode == MT3_GEMM_FP32_SIMT, MT3_ERR_UNSUPPORTED,
-              "mt3_model_create: gemm_mode %d not built in this version (only MT3_GEMM_FP32_SIMT)", cfg->gemm_mode);
+  MT3_REQUIRE(cfg->gemm_mode == MT3_GEMM_FP32_SIMT || cfg->gemm_mode == MT3_GEMM_TF32X3 || cfg->gemm_mode == MT3_GEMM_TF32,
+              MT3_ERR_BAD_ARG, "mt3_model_create: unknown gemm_mode %d", cfg->gemm_mode);
+  if (cfg->gemm_mode != MT3_GEMM_FP32_SIMT)
+    MT3_REQUIRE(cfg->emb_dim % 32 == 0 && cfg->mlp_dim % 32 == 0 && cfg->input_depth % 32 == 0, MT3_ERR_UNSUPPORTED,
+                "mt3_model_create: the tcgen05 path needs emb/mlp/input dims that are multiples of 32");
   cudaStream_t s = (cudaStream_t)stream;
   Model* m = new Model();
   m->cfg = *cfg;
@@ -433,12 +548,35 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: PE upload -> %s", cudaGetErrorString(e));
   }
+  m->tc = cfg->gemm_mode != MT3_GEMM_FP32_SIMT;
+  m->split3 = cfg->gemm_mode == MT3_GEMM_TF32X3;
+  if (rc == MT3_OK && m->tc) {
+    e = cudaMalloc((void**)&m->slab_tc, (size_t)tc_weight_floats(*cfg) * sizeof(float));
+    if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: cudaMalloc(tc weights) -> %s", cudaGetErrorString(e));
+    float* cur = m->slab_tc;
+#define TCPREP(src, K, N, dst) do { if (rc == MT3_OK) rc = prep_tc_weight(m, s, src, K, N, cur, dst); } while (0)
+    TCPREP(m->w_in, cfg->input_depth, D, &m->t_w_in);
+    for (int i = 0; i < m->Le; ++i) {
+      EncLayer& L = m->enc[i];
+      TCPREP(L.wqkv, D, 3 * Q, &L.t_wqkv);
+      TCPREP(L.wo, Q, D, &L.t_wo);
+      TCPREP(L.wi, D, 2 * F, &L.t_wi);
+      TCPREP(L.wo2, F, D, &L.t_wo2);
+    }
+    for (int i = 0; i < m->Ld; ++i) TCPREP(m->dec[i].wkv_c, D, 2 * Q, &m->dec[i].t_wkv_c);
+#undef TCPREP
+    if (rc == MT3_OK) {
+      e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: tc weight prep -> %s", cudaGetErrorString(e));
+    }
+  }
   if (rc == MT3_OK) {
     e = cudaMallocHost((void**)&m->h_flag, 4 * sizeof(int));
     if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: cudaMallocHost -> %s", cudaGetErrorString(e));
   }
   if (rc != MT3_OK) {
     cudaFree(m->slab);
+    cudaFree(m->slab_tc);
     delete m;
     return rc;
   }
@@ -453,12 +591,14 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   if (m->h_flag) cudaFreeHost(m->h_flag);
   cudaFree(m->slab);
+  cudaFree(m->slab_tc);
   delete m;
   return MT3_OK;
 }
 
 namespace {
 struct WsLayout {
+  int64_t x_hi, x_lo, h_lo, ao_lo, g_lo, enc_hi, enc_lo;
   int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, total;
 };
 WsLayout ws_layout(const Model* m, int B, int T) {
@@ -466,6 +606,14 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   int64_t off = 0;
   auto take = [&](int64_t bytes) { int64_t r = off; off += align_up(bytes, 256); return r; };
   const int64_t M = (int64_t)B * T, D = m->D, Q = m->Q, F = m->F, V = m->V, L = m->L;
+  const bool s3 = m->split3;
+  w.x_hi = take(s3 ? M * m->cfg.input_depth * 4 : 0);
+  w.x_lo = take(s3 ? M * m->cfg.input_depth * 4 : 0);
+  w.h_lo = take(s3 ? M * D * 4 : 0);
+  w.ao_lo = take(s3 ? M * Q * 4 : 0);
+  w.g_lo = take(s3 ? M * F * 4 : 0);
+  w.enc_hi = take(s3 ? M * D * 4 : 0);
+  w.enc_lo = take(s3 ? M * D * 4 : 0);
   w.h = take(M * D * 4);
   w.rstd = take(M * 4);
   w.qkv = take(M * 3 * Q * 4);
@@ -512,6 +660,22 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
   m->dg = (float*)(b + w.dg); m->dlogits = (float*)(b + w.dlogits); m->tok_cur = (int*)(b + w.tok_cur);
   m->finished = (int*)(b + w.finished); m->tokens = (int*)(b + w.tokens); m->state = (int*)(b + w.state);
   m->have_cross = false;
+  if (m->tc) {
+    const int64_t M = (int64_t)batch * input_length;
+    const bool s3 = m->split3;
+    m->a_x.hi = s3 ? (float*)(b + w.x_hi) : nullptr; m->a_x.lo = s3 ? (float*)(b + w.x_lo) : nullptr;
+    m->a_h.hi = m->h; m->a_h.lo = s3 ? (float*)(b + w.h_lo) : nullptr;
+    m->a_ao.hi = m->ao; m->a_ao.lo = s3 ? (float*)(b + w.ao_lo) : nullptr;
+    m->a_g.hi = m->g; m->a_g.lo = s3 ? (float*)(b + w.g_lo) : nullptr;
+    m->a_enc.hi = s3 ? (float*)(b + w.enc_hi) : nullptr; m->a_enc.lo = s3 ? (float*)(b + w.enc_lo) : nullptr;
+    if (s3) {
+      MT3_TRY(make_operand(&m->a_x.op, m->a_x.hi, m->a_x.lo, M, m->cfg.input_depth, m->cfg.input_depth));
+      MT3_TRY(make_operand(&m->a_enc.op, m->a_enc.hi, m->a_enc.lo, M, m->D, m->D));
+    }
+    MT3_TRY(make_operand(&m->a_h.op, m->a_h.hi, m->a_h.lo, M, m->D, m->D));
+    MT3_TRY(make_operand(&m->a_ao.op, m->a_ao.hi, m->a_ao.lo, M, m->Q, m->Q));
+    MT3_TRY(make_operand(&m->a_g.op, m->a_g.hi, m->a_g.lo, M, m->F, m->F));
+  }
   return MT3_OK;
 }
 
@@ -620,6 +784,12 @@ extern "C" int mt3_debug_launch(mt3_model* h, int32_t kind, int32_t pos, int32_t
         break;
       }
       case MT3_K_ENC_QKV_GEMM: {
+        if (m->tc) {
+          TcGemmArgs t = tc_args(M, 3 * Q, D, m->qkv, nullptr, 3 * Q);
+          t.row_scale = m->rstd;
+          MT3_TRY(launch_tc_gemm(m->a_h.op, m->enc[it % std::max(1, m->Le)].t_wqkv.op, t, m->split3, s));
+          break;
+        }
         GemmArgs a = gemm_args(m->h, D, m->enc[it % std::max(1, m->Le)].wqkv, 3 * Q, M, 3 * Q, D, m->qkv, 3 * Q);
         a.row_scale = m->rstd;
         MT3_TRY(gemm(m, a, s));
@@ -628,7 +798,7 @@ extern "C" int mt3_debug_launch(mt3_model* h, int32_t kind, int32_t pos, int32_t
       case MT3_K_ENC_ATTN: {
         MT3_TRY(set_attr_once());
         const size_t attn_smem = (size_t)(32 * kHD + 32 * (T + 4) + 64 * 68) * sizeof(float);
-        enc_attention_kernel<<<dim3(cdiv(T, 32), m->H, B), 256, attn_smem, s>>>(m->qkv, 3 * Q, T, m->H, m->ao, Q);
+        enc_attention_kernel<<<dim3(cdiv(T, 32), m->H, B), 256, attn_smem, s>>>(m->qkv, 3 * Q, T, m->H, m->ao, nullptr, Q);
         MT3_LAUNCH_CHECK();
         break;
       }

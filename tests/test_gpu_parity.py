@@ -316,3 +316,39 @@ def test_inference_model_api_end_to_end():
     srt = np.sort(lg, -1)
     safe = np.cumprod((srt[..., -1] - srt[..., -2]) > 1e-3 * np.abs(lg).max(), axis=1).astype(bool)
     np.testing.assert_array_equal(out[:, :6][safe], O.vocab_decode(ref[:, :6], 1514)[safe])
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 GEMM modes (encoder + cross-K/V on the tensor cores)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,tol", [("tf32x3", None), ("tf32", 3e-2)])
+def test_tensor_core_encoder_parity(mode, tol):
+    """MT3_GEMM_TF32X3 must meet the same fp32 bar as the exact-fp32 SIMT path; single-pass TF32
+    is reported with its own (10-bit mantissa) tolerance and is not the default."""
+    from mt3_b200 import _lib, network
+    cfg = network.T5Config(vocab_size=1536, emb_dim=512, num_heads=6, num_encoder_layers=8, num_decoder_layers=8,
+                           head_dim=64, mlp_dim=1024, mlp_activations=('gelu', 'linear'))
+    ocfg = O.T5Config()
+    params = O.init_params(ocfg, seed=0, norm_scale_jitter=0.05)
+    gm = _lib.GEMM_TF32X3 if mode == "tf32x3" else _lib.GEMM_TF32
+    model = network.Transformer(cfg, params, device=DEV, max_batch=4, max_input_length=256, max_decode_length=64, gemm_mode=gm)
+    x = _inputs(3, seed=77)        # M = 768 rows: 6 row tiles
+    enc = model.encode(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    enc64 = O.encode(params, ocfg, x, np.float64)
+    enc32 = O.encode(params, ocfg, x, np.float32)
+    scale = np.abs(enc64).max()
+    e_gpu, e_f32 = np.abs(enc - enc64).max() / scale, np.abs(enc32 - enc64).max() / scale
+    print(f"encoder[{mode}]: gpu vs fp64 {e_gpu:.3e}   fp32-oracle vs fp64 {e_f32:.3e}")
+    if tol is None:
+        assert e_gpu <= max(LOGIT_TOL, 4 * e_f32)
+    else:
+        assert e_gpu <= tol
+    # decode on top of the tensor-core encoder / cross-K/V: teacher-forced logits
+    steps = 6
+    toks64, logits64 = O.greedy_decode(params, ocfg, enc64, steps, np.float64, stop_at_eos=False, return_logits=True)
+    dec_in = np.concatenate([np.zeros((3, 1), np.int64), toks64[:, :steps - 1]], axis=1)
+    enc_gpu = model.encode(torch.from_numpy(x).to(DEV))
+    lg = model.teacher_forced_logits(enc_gpu, torch.from_numpy(dec_in).to(DEV).to(torch.int32)).cpu().numpy()
+    e_l = np.abs(lg - logits64).max() / np.abs(logits64).max()
+    print(f"logits[{mode}]: gpu vs fp64 {e_l:.3e}")
+    assert e_l <= (LOGIT_TOL if tol is None else tol)
