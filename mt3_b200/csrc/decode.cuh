@@ -1,0 +1,358 @@
+// Decode-step kernels (one new token per sequence, M = batch rows), sm_100a.
+//
+// The decode step is bandwidth/latency bound (DESIGN.md "decode step"): per layer it streams
+// 11.8 MB of fp32 weights and, per sequence, the self-attention K/V rows written so far plus
+// the 256 hoisted cross-attention K/V rows.  Two kernels carry it:
+//
+//  sgemm_dec_kernel    exact-fp32 GEMM for M <= 64 rows.  A 64 x 32 output tile per CTA gives only
+//                      N/32 CTAs, so K is split across gridDim.y CTAs; each writes its partial tile
+//                      to an L2-resident scratch and the LAST CTA to arrive for that tile (atomic
+//                      ticket) sums the partials IN FIXED ORDER (deterministic) and runs the fused
+//                      epilogue.  The RMSNorm statistic of the input rows (layers.py:613-616) is
+//                      computed from the A tiles the GEMM loads anyway (no separate pass), and the
+//                      epilogues are those of gemm_simt.cuh incl. the head-major KV-cache append.
+//
+//  dec_attention_bulk_kernel  one query per (sequence, head) over contiguous head-major K/V rows
+//                      (kv[b][K|V][head][cap][64]).  A producer warp streams 32-key tiles (8 KB) with
+//                      cp.async.bulk (TMA 1-D) into a 6-stage shared-memory ring, signalled through
+//                      mbarriers; four consumer warps compute scores (pass 1: K tiles), the softmax,
+//                      and P.V (pass 2: V tiles).  Slots >= len are never read -- identical to the
+//                      reference's -1e10 mask bias (layers.py:297-322: exp underflows to exactly 0).
+#pragma once
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "tc.cuh"
+
+namespace mt3 {
+
+struct DecGemmArgs {
+  const float* A; int lda;        // [M, K]
+  const float* W; int ldw;        // [K, N] row-major
+  int M, N, K;
+  int norm;                       // 1: scale row m by rsqrt(mean(A[m,:]^2) + eps); needs K == row length
+  float eps;
+  int epi;
+  const float* R; int ldr;
+  float* C; int ldc;
+  int n_split; float* C1; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;
+  float* partial;                 // [splits][n_tiles][64*32 + 64] scratch
+  int* counters;                  // [n_tiles], zero on entry, left zero on exit
+};
+
+constexpr int kDecBM = 64, kDecBN = 32, kDecBK = 16;
+constexpr int kDecTileFloats = kDecBM * kDecBN + kDecBM;   // partial tile + per-row sum of squares
+
+__global__ void __launch_bounds__(128)
+sgemm_dec_kernel(const DecGemmArgs p) {
+  constexpr int BM = kDecBM, BN = kDecBN, BK = kDecBK, NT = 128, APAD = 4;
+  __shared__ __align__(16) float As[2][BK][BM + APAD];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  __shared__ float s_ss[BM];
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x;
+  const int tx = tid % 8, ty = tid / 8;                  // thread tile: rows ty*4.., cols tx*4..
+  const int n0 = blockIdx.x * BN;
+  const int splits = gridDim.y, ks = blockIdx.y;
+  const int kc = p.K / splits;                           // host guarantees kc % BK == 0
+  const int kbeg = ks * kc;
+
+  float4 ra[2], rb;
+  float ss[2] = {0.f, 0.f};                              // sum of squares of rows tid/4 and tid/4 + 32
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * NT;
+      const int row = idx >> 2, kq = idx & 3;
+      ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < p.M) ra[i] = *reinterpret_cast<const float4*>(p.A + (long long)row * p.lda + k0 + kq * 4);
+      ss[i] += ra[i].x * ra[i].x + ra[i].y * ra[i].y + ra[i].z * ra[i].z + ra[i].w * ra[i].w;
+    }
+    {
+      const int kr = tid >> 3, nq = tid & 7;
+      rb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + nq * 4 < p.N) rb = __ldg(reinterpret_cast<const float4*>(p.W + (long long)(k0 + kr) * p.ldw + n0 + nq * 4));
+    }
+  };
+  auto store_tiles = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * NT;
+      const int row = idx >> 2, kq = idx & 3;
+      As[buf][kq * 4 + 0][row] = ra[i].x;
+      As[buf][kq * 4 + 1][row] = ra[i].y;
+      As[buf][kq * 4 + 2][row] = ra[i].z;
+      As[buf][kq * 4 + 3][row] = ra[i].w;
+    }
+    *reinterpret_cast<float4*>(&Bs[buf][tid >> 3][(tid & 7) * 4]) = rb;
+  };
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int nk = kc / BK;
+  load_tiles(kbeg);
+  store_tiles(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) load_tiles(kbeg + (kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      store_tiles(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  // per-row sum of squares over this CTA's K range: the 4 threads sharing a row are adjacent lanes
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 1);
+    ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 2);
+  }
+
+  const int n_tiles = gridDim.x;
+  if (splits > 1) {
+    float* mine = p.partial + ((long long)ks * n_tiles + blockIdx.x) * kDecTileFloats;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(mine + (ty * 4 + i) * BN + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if ((tid & 3) == 0) {
+      mine[BM * BN + (tid >> 2)] = ss[0];
+      mine[BM * BN + (tid >> 2) + 32] = ss[1];
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int ticket = atomicAdd(&p.counters[blockIdx.x], 1);
+      s_last = (ticket == splits - 1);
+      if (s_last) p.counters[blockIdx.x] = 0;            // re-arm for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // fixed-order reduction of all partials (including our own) -> bit-reproducible
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    float sst = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const float* src = p.partial + ((long long)s * n_tiles + blockIdx.x) * kDecTileFloats;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (ty * 4 + i) * BN + tx * 4));
+        acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+      }
+      if (tid < BM) sst += __ldcg(src + BM * BN + tid);
+    }
+    if (tid < BM) s_ss[tid] = sst;
+  } else {
+    if ((tid & 3) == 0) {
+      s_ss[tid >> 2] = ss[0];
+      s_ss[(tid >> 2) + 32] = ss[1];
+    }
+  }
+  __syncthreads();
+
+  // ---- fused epilogue (same set as gemm_simt.cuh) ----
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = ty * 4 + i;
+    if (m >= p.M) continue;
+    const int n = n0 + tx * 4;
+    if (n >= p.N) continue;
+    const float rs = p.norm ? 1.0f / sqrtf(s_ss[m] / (float)p.K + p.eps) : 1.f;
+    float4 v = make_float4(acc[i][0] * rs, acc[i][1] * rs, acc[i][2] * rs, acc[i][3] * rs);
+    if (p.epi == EPI_GATED_GELU) {
+      *reinterpret_cast<float2*>(p.C + (long long)m * p.ldc + (n >> 1)) = make_float2(gelu_tanh(v.x) * v.y, gelu_tanh(v.z) * v.w);
+      continue;
+    }
+    if (p.epi == EPI_RESIDUAL) {
+      const float4 q = *reinterpret_cast<const float4*>(p.R + (long long)m * p.ldr + n);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    if (n < p.n_split) {
+      *reinterpret_cast<float4*>(p.C + (long long)m * p.ldc + n) = v;
+    } else {
+      const int pos = p.hm_pos ? *p.hm_pos : 0;
+      *reinterpret_cast<float4*>(p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos)) = v;
+    }
+  }
+}
+
+// K split so that about one wave of CTAs streams the weight matrix.
+inline int dec_gemm_splits(int N, int K, int sm_count) {
+  const int n_tiles = cdiv(N, kDecBN);
+  int best = 1;
+  for (int s = 2; s <= 16; s *= 2) {
+    if (K % s != 0 || (K / s) % kDecBK != 0 || K / s < 32) break;
+    if (n_tiles * s <= sm_count + sm_count / 8) best = s;
+  }
+  return best;
+}
+
+inline int launch_dec_gemm(const DecGemmArgs& a, int splits, cudaStream_t s) {
+  MT3_REQUIRE(a.M <= kDecBM, MT3_ERR_UNSUPPORTED, "decode gemm: M=%d > %d rows", a.M, kDecBM);
+  MT3_REQUIRE(a.K % (splits * kDecBK) == 0 && a.N % 4 == 0 && a.lda % 4 == 0 && a.ldw % 4 == 0 && a.n_split % 4 == 0,
+              MT3_ERR_UNSUPPORTED, "decode gemm: K=%d splits=%d N=%d not tileable", a.K, splits, a.N);
+  sgemm_dec_kernel<<<dim3(cdiv(a.N, kDecBN), splits), 128, 0, s>>>(a);
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decode attention over head-major K/V, bulk-copy pipelined.
+// ---------------------------------------------------------------------------------------------
+constexpr int kAttKT = 32;                       // keys per tile (8 KB)
+constexpr int kAttStages = 6;
+constexpr int kAttTileFloats = kAttKT * 64;
+constexpr int kAttThreads = 160;                 // 4 consumer warps + 1 producer warp
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :
+               : "r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+
+inline size_t dec_attention_smem(int max_len) {
+  return (size_t)(kAttStages * kAttTileFloats + ((max_len + 3) & ~3) + 8 * 64) * sizeof(float) + 2 * kAttStages * 8 + 64;
+}
+
+// q [B, ldq], head h at column q_off + h*64.  kv: head-major [b][2][H][cap][64].  out [B, ldo].
+// len = (len_ptr ? *len_ptr : 0) + len_add.
+__global__ void __launch_bounds__(kAttThreads)
+dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const float* __restrict__ kv, int H, int cap,
+                          const int* __restrict__ len_ptr, int len_add, int max_len, float* __restrict__ out, int ldo) {
+  extern __shared__ __align__(128) float sm[];
+  float* ring = sm;                                              // [stages][32*64]
+  float* sP = ring + kAttStages * kAttTileFloats;                // [max_len4]
+  float* sRed = sP + ((max_len + 3) & ~3);                       // [8][64]
+  uint64_t* full = reinterpret_cast<uint64_t*>(sRed + 8 * 64);   // [stages]
+  uint64_t* empty = full + kAttStages;
+  __shared__ float s_stat[8];
+
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int len = (len_ptr ? *len_ptr : 0) + len_add;
+  const int nt = (len + kAttKT - 1) / kAttKT;
+  const float* kbase = kv + (((long long)b * 2 + 0) * H + h) * (long long)cap * 64;
+  const float* vbase = kv + (((long long)b * 2 + 1) * H + h) * (long long)cap * 64;
+
+  if (tid == 0) {
+    for (int s = 0; s < kAttStages; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 4);
+    }
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == 4) {
+    // ---- producer: K tiles 0..nt-1, then V tiles 0..nt-1 ----
+    if (lane == 0) {
+      for (int j = 0; j < 2 * nt; ++j) {
+        const int s = j % kAttStages;
+        const uint32_t ph = (j / kAttStages) & 1;
+        tc::mbar_wait(&empty[s], ph ^ 1);
+        const int t = j < nt ? j : j - nt;
+        const int keys = min(kAttKT, len - t * kAttKT);
+        const uint32_t bytes = (uint32_t)keys * 64 * 4;
+        const float* src = (j < nt ? kbase : vbase) + (long long)t * kAttTileFloats;
+        tc::mbar_arrive_expect_tx(&full[s], bytes);
+        bulk_g2s(ring + s * kAttTileFloats, src, bytes, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ---- consumers (128 threads) ----
+  // pass 1: scores.  16 lanes cover one key row (conflict-free 256-byte read), 2 keys per warp instruction.
+  const int c = lane & 15, half = lane >> 4;
+  const float4 q4 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + q_off + h * 64 + c * 4);
+  float lmax = -INFINITY;
+  for (int j = 0; j < nt; ++j) {
+    const int s = j % kAttStages;
+    tc::mbar_wait(&full[s], (j / kAttStages) & 1);
+    const float* tile = ring + s * kAttTileFloats;
+    const int k0 = j * kAttKT;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = warp * 8 + i * 2 + half;                    // key inside the tile
+      float d = 0.f;
+      if (k0 + kk < len) {
+        const float4 kx = *reinterpret_cast<const float4*>(tile + kk * 64 + c * 4);
+        d = q4.x * kx.x + q4.y * kx.y + q4.z * kx.z + q4.w * kx.w;
+      }
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      d += __shfl_xor_sync(0xffffffffu, d, 8);
+      if (k0 + kk < len) {
+        if (c == 0) sP[k0 + kk] = d;
+        lmax = fmaxf(lmax, d);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&empty[s]);
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0) s_stat[warp] = lmax;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const float mx = fmaxf(fmaxf(s_stat[0], s_stat[1]), fmaxf(s_stat[2], s_stat[3]));
+  float lsum = 0.f;
+  for (int k = tid; k < len; k += 128) {
+    const float e = expf(sP[k] - mx);
+    sP[k] = e;
+    lsum += e;
+  }
+  lsum = warp_sum(lsum);
+  if (lane == 0) s_stat[4 + warp] = lsum;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const float inv = 1.0f / (s_stat[4] + s_stat[5] + s_stat[6] + s_stat[7]);
+
+  // pass 2: O = P V.  thread -> key group (tid / 16: 8 groups) x 4 dims (tid % 16)
+  const int kg = tid >> 4, d4 = tid & 15;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = nt; j < 2 * nt; ++j) {
+    const int s = j % kAttStages;
+    tc::mbar_wait(&full[s], (j / kAttStages) & 1);
+    const float* tile = ring + s * kAttTileFloats;
+    const int k0 = (j - nt) * kAttKT;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = kg + i * 8;
+      if (k0 + kk < len) {
+        const float pk = sP[k0 + kk];
+        const float4 v = *reinterpret_cast<const float4*>(tile + kk * 64 + d4 * 4);
+        acc.x = fmaf(pk, v.x, acc.x); acc.y = fmaf(pk, v.y, acc.y);
+        acc.z = fmaf(pk, v.z, acc.z); acc.w = fmaf(pk, v.w, acc.w);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) tc::mbar_arrive(&empty[s]);
+  }
+  *reinterpret_cast<float4*>(sRed + kg * 64 + d4 * 4) = acc;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  if (tid < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s += sRed[g * 64 + tid];
+    out[(long long)b * ldo + h * 64 + tid] = s * inv;
+  }
+}
+
+}  // namespace mt3

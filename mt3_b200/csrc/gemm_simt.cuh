@@ -32,9 +32,20 @@ struct GemmArgs {
   const float* R; int ldr;     // EPI_RESIDUAL
   const float* pe; int pe_T; int pe_ld;  // EPI_ADD_PE
   float* C; int ldc;
-  int n_split;                 // columns >= n_split -> C1 (N if unused)
-  float* C1; long long c1_row_stride; const int* c1_pos; long long c1_pos_stride;
+  int n_split;                 // columns >= n_split -> head-major K/V store at C1 (N if unused)
+  float* C1; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // head-major K/V store, see kv_dest()
 };
+
+// Head-major K/V layout shared by the self-attention cache and the hoisted cross K/V:
+//   kv[b][which(0=K,1=V)][head][cap][64]
+// Row m of the GEMM is (b, t) = (m / rows_per_b, m % rows_per_b + pos); column c (relative to n_split) is
+// (which, head, d) = (c / (H*64), (c % (H*64)) / 64, c % 64).  Decode: rows_per_b = 1, pos = cache index
+// (the fused KV-cache append, layers.py:272-289); cross K/V: rows_per_b = T, pos = 0.
+__device__ __forceinline__ long long kv_dest(int m, int c, int rows_per_b, int cap, int H, int pos) {
+  const int b = m / rows_per_b, t = m % rows_per_b + pos;
+  const int which = c / (H * 64), h = (c % (H * 64)) >> 6, d = c & 63;
+  return ((((long long)b * 2 + which) * H + h) * cap + t) * 64 + d;
+}
 
 __device__ __forceinline__ float gelu_tanh(float x) {
   // flax.linen.gelu(approximate=True): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
@@ -169,8 +180,8 @@ sgemm_kernel(const GemmArgs p) {
         if (n < p.n_split) {
           *reinterpret_cast<float4*>(p.C + (long long)m * p.ldc + n) = v;
         } else {
-          const long long pos = p.c1_pos ? (long long)(*p.c1_pos) : 0;
-          *reinterpret_cast<float4*>(p.C1 + (long long)m * p.c1_row_stride + pos * p.c1_pos_stride + (n - p.n_split)) = v;
+          const int pos = p.hm_pos ? *p.hm_pos : 0;
+          *reinterpret_cast<float4*>(p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos)) = v;
         }
       }
     }

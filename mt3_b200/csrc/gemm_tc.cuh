@@ -34,7 +34,7 @@ struct TcGemmArgs {
   const float* R_hi; const float* R_lo; int ldr;
   const float* pe; int pe_T; int pe_ld;
   float* C_hi; float* C_lo; int ldc;       // C_lo != null: write hi/lo split of the result
-  int n_split; float* C1; long long c1_row_stride; const int* c1_pos; long long c1_pos_stride;
+  int n_split; float* C1; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // head-major K/V store, see kv_dest()
 };
 
 constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 32;
@@ -198,8 +198,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         ch = p.C_hi + (long long)m * p.ldc + n;
         if (p.C_lo) cl = p.C_lo + (long long)m * p.ldc + n;
       } else {
-        const long long pos = p.c1_pos ? (long long)(*p.c1_pos) : 0;
-        ch = p.C1 + (long long)m * p.c1_row_stride + pos * p.c1_pos_stride + (n - p.n_split);
+        const int pos = p.hm_pos ? *p.hm_pos : 0;
+        ch = p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos);
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {

@@ -186,87 +186,6 @@ enc_attention_kernel(const float* __restrict__ qkv, int ld, int T, int H, float*
 }
 
 // ---------------------------------------------------------------------------------
-// Decode attention, one query position per sequence (layers.py:246-314 for the cached
-// self-attention, network.py:126-139 for cross-attention over the hoisted K/V).
-// q [B, ldq] (head h at column q_off + h*64); kv rows: kv + b*kv_b_stride + t*kv_t_stride,
-// K at column h*64, V at column v_off + h*64.  len = *len_ptr + len_add (self: pos+1) or
-// len_add alone when len_ptr is null (cross: T).  Slots >= len are never read, which
-// equals the reference's -1e10 bias (exp underflows to exactly 0 in fp32).
-// One CTA per (b, h), 128 threads; 8 lanes share a key row (coalesced 256-byte reads).
-// ---------------------------------------------------------------------------------
-constexpr int kDecAttnThreads = 128;
-
-__global__ void __launch_bounds__(kDecAttnThreads)
-dec_attention_kernel(const float* __restrict__ q, int ldq, int q_off, const float* __restrict__ kv,
-                     long long kv_b_stride, long long kv_t_stride, int v_off, const int* __restrict__ len_ptr,
-                     int len_add, int max_len, float* __restrict__ out, int ldo) {
-  extern __shared__ __align__(16) float sm[];
-  float* sP = sm;                    // [max_len]
-  float* sRed = sP + max_len;        // [8 groups][64] + scratch
-  __shared__ float s_stat[8];
-  const int b = blockIdx.y, h = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int len = (len_ptr ? *len_ptr : 0) + len_add;
-  const float* kb = kv + (long long)b * kv_b_stride + h * kHD;
-  const float* vb = kb + v_off;
-
-  // phase 1: scores
-  const int sub = lane & 7, kin = lane >> 3;          // 8 lanes per key, 4 keys per warp
-  const float4 q0 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + q_off + h * kHD + sub * 8);
-  const float4 q1 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + q_off + h * kHD + sub * 8 + 4);
-  float lmax = -INFINITY;
-  for (int k0 = warp * 4; k0 < len; k0 += 16) {
-    const int k = k0 + kin;
-    float s = 0.f;
-    if (k < len) {
-      const float* kr = kb + (long long)k * kv_t_stride + sub * 8;
-      const float4 a = *reinterpret_cast<const float4*>(kr);
-      const float4 c = *reinterpret_cast<const float4*>(kr + 4);
-      s = q0.x * a.x + q0.y * a.y + q0.z * a.z + q0.w * a.w + q1.x * c.x + q1.y * c.y + q1.z * c.z + q1.w * c.w;
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (k < len) {
-      if (sub == 0) sP[k] = s;
-      lmax = fmaxf(lmax, s);
-    }
-  }
-  lmax = warp_max(lmax);
-  if (lane == 0) s_stat[warp] = lmax;
-  __syncthreads();
-  const float mx = fmaxf(fmaxf(s_stat[0], s_stat[1]), fmaxf(s_stat[2], s_stat[3]));
-  // phase 2: exp + sum
-  float lsum = 0.f;
-  for (int k = tid; k < len; k += kDecAttnThreads) {
-    const float e = expf(sP[k] - mx);
-    sP[k] = e;
-    lsum += e;
-  }
-  lsum = warp_sum(lsum);
-  if (lane == 0) s_stat[4 + warp] = lsum;
-  __syncthreads();
-  const float inv = 1.0f / (s_stat[4] + s_stat[5] + s_stat[6] + s_stat[7]);
-  // phase 3: O = P V ; thread -> key group (tid/16) x 4 dims (tid%16)
-  const int kg = tid >> 4, d4 = tid & 15;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int k = kg; k < len; k += 8) {
-    const float p = sP[k];
-    const float4 v = *reinterpret_cast<const float4*>(vb + (long long)k * kv_t_stride + d4 * 4);
-    acc.x = fmaf(p, v.x, acc.x); acc.y = fmaf(p, v.y, acc.y);
-    acc.z = fmaf(p, v.z, acc.z); acc.w = fmaf(p, v.w, acc.w);
-  }
-  *reinterpret_cast<float4*>(sRed + kg * kHD + d4 * 4) = acc;
-  __syncthreads();
-  if (tid < kHD) {
-    float s = 0.f;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) s += sRed[g * kHD + tid];
-    out[(long long)b * ldo + h * kHD + tid] = s * inv;
-  }
-}
-
-// ---------------------------------------------------------------------------------
 // Decoder input: y[b,:] = E[tok[b],:] + PE[pos,:]  (Embed one-hot == row gather,
 // layers.py:516-537; FixedEmbed decode branch, layers.py:589-596).
 // ---------------------------------------------------------------------------------

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "decode.cuh"
 #include "layers.cuh"
 
 namespace mt3 {
@@ -101,6 +102,9 @@ struct Model {
   float *ckv = nullptr, *skv = nullptr;
   float *dy = nullptr, *drstd = nullptr, *dq = nullptr, *dao = nullptr, *dg = nullptr, *dlogits = nullptr;
   int *tok_cur = nullptr, *finished = nullptr, *tokens = nullptr, *state = nullptr;
+  float* dpartial = nullptr;      // split-K scratch of the decode GEMM
+  int* dcounters = nullptr;
+  int sm_count = 148;
   bool have_cross = false;
   int host_pos = 0;               // host mirror of the device position (cache overflow guard)
 
@@ -255,7 +259,8 @@ static int cross_kv_tc_impl(Model* m, const float* encoded, cudaStream_t s) {
     MT3_TRY(make_operand(&ope, encoded, nullptr, M, D, D));
   }
   for (int l = 0; l < m->Ld; ++l) {
-    TcGemmArgs a = tc_args(M, 2 * Q, D, m->ckv + (int64_t)l * M * 2 * Q, nullptr, 2 * Q);
+    TcGemmArgs a = tc_args(M, 2 * Q, D, nullptr, nullptr, 2 * Q);
+    a.n_split = 0; a.C1 = m->ckv + (int64_t)l * M * 2 * Q; a.hm_rows_per_b = m->T; a.hm_cap = m->T; a.hm_H = m->H;
     MT3_TRY(launch_tc_gemm(ope, m->dec[l].t_wkv_c.op, a, m->split3, s));
   }
   return MT3_OK;
@@ -313,11 +318,13 @@ static int cross_kv_impl(Model* m, const float* encoded, cudaStream_t s) {
     MT3_TRY(cross_kv_tc_impl(m, encoded, s));
   } else {
     for (int l = 0; l < m->Ld; ++l) {
-      GemmArgs a = gemm_args(encoded, D, m->dec[l].wkv_c, 2 * Q, M, 2 * Q, D, m->ckv + (int64_t)l * M * 2 * Q, 2 * Q);
+      GemmArgs a = gemm_args(encoded, D, m->dec[l].wkv_c, 2 * Q, M, 2 * Q, D, nullptr, 2 * Q);
+      a.n_split = 0; a.C1 = m->ckv + (int64_t)l * M * 2 * Q; a.hm_rows_per_b = m->T; a.hm_cap = m->T; a.hm_H = m->H;
       MT3_TRY(gemm(m, a, s));
     }
   }
   MT3_CUDA_CHECK(cudaMemsetAsync(m->state, 0, 4 * sizeof(int), s));
+  MT3_CUDA_CHECK(cudaMemsetAsync(m->dcounters, 0, (size_t)cdiv(std::max(std::max(3 * Q, 2 * m->F), m->V), kDecBN) * sizeof(int), s));
   MT3_CUDA_CHECK(cudaMemsetAsync(m->finished, 0, (size_t)m->B * sizeof(int), s));
   MT3_CUDA_CHECK(cudaMemsetAsync(m->tok_cur, 0, (size_t)m->B * sizeof(int), s));
   m->have_cross = true;
@@ -325,67 +332,68 @@ static int cross_kv_impl(Model* m, const float* encoded, cudaStream_t s) {
   return MT3_OK;
 }
 
-// One decode step.  tok_in DEV [B]; logits DEV [B,V]; greedy != 0 runs the argmax/bookkeeping
-// kernel (tok_user optional), else only the position is advanced.
+// Decode-step GEMM on M = B rows: split-K exact-fp32 kernel with the RMSNorm statistic fused
+// (decode.cuh); batches above 64 rows run in 64-row blocks.
+static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, int K, int norm, int epi, float* C, int ldc,
+                    int n_split, float* kv, const int* pos, cudaStream_t s) {
+  const int splits = dec_gemm_splits(N, K, m->sm_count);
+  for (int r0 = 0; r0 < m->B; r0 += kDecBM) {
+    DecGemmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.A = A + (int64_t)r0 * lda; a.lda = lda; a.W = W; a.ldw = N; a.M = std::min(kDecBM, m->B - r0); a.N = N; a.K = K;
+    a.norm = norm; a.eps = 1e-6f; a.epi = epi;
+    a.R = C + (int64_t)r0 * ldc; a.ldr = ldc;                  // residual is always added in place
+    a.C = C + (int64_t)r0 * ldc; a.ldc = ldc; a.n_split = n_split;
+    if (kv) {  // rows_per_b = 1: skip r0 sequences, each 2*H*cap*64 floats
+      a.C1 = kv + (int64_t)r0 * 2 * m->H * m->L * 64; a.hm_rows_per_b = 1; a.hm_cap = m->L; a.hm_H = m->H; a.hm_pos = pos;
+    }
+    a.partial = m->dpartial; a.counters = m->dcounters;
+    MT3_TRY(launch_dec_gemm(a, splits, s));
+  }
+  return MT3_OK;
+}
+
+static int launch_dec_attention(Model* m, const float* q, const float* kv, int cap, const int* len_ptr, int len_add,
+                                float* out, cudaStream_t s) {
+  static bool attr_done = false;
+  const int max_len = std::max(m->L, m->T);
+  const size_t smem = dec_attention_smem(max_len);
+  if (!attr_done) {
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_done = true;
+  }
+  MT3_REQUIRE(smem <= 100 * 1024, MT3_ERR_UNSUPPORTED, "decode attention: length %d too long", max_len);
+  dec_attention_bulk_kernel<<<dim3(m->H, m->B), kAttThreads, smem, s>>>(q, m->Q, 0, kv, m->H, cap, len_ptr, len_add, max_len,
+                                                                         out, m->Q);
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
+// One decode step (network.py:303-361 -> :196-262 -> :88-155).  tok_in DEV [B]; logits DEV [B,V];
+// greedy != 0 runs the argmax/bookkeeping kernel (tok_user optional), else only the position advances.
+// 8 launches per layer: [norm+QKV+KV-append] [self-attn] [out+residual] [norm+q] [cross-attn]
+// [out+residual] [norm+gated-GELU MLP in] [MLP out+residual].
 static int decode_step_impl(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
                             int* tokens_ws, cudaStream_t s) {
   const int B = m->B, D = m->D, Q = m->Q, F = m->F, V = m->V, L = m->L, T = m->T;
   int* pos = m->state;
   embed_kernel<<<B, 128, 0, s>>>(tok_in, m->emb, D, V, m->pe, pos, m->dy);
   MT3_LAUNCH_CHECK();
-  const int max_len_sm = (std::max(L, T) + 3) & ~3;
-  const size_t dsm = (size_t)(max_len_sm + 8 * kHD) * sizeof(float);
   for (int l = 0; l < m->Ld; ++l) {
     const DecLayer& w = m->dec[l];
     float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
     const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
-    MT3_TRY(launch_rstd(m->dy, D, B, D, m->drstd, s));
-    {  // fused RMSNorm + QKV projection + K/V cache append (layers.py:238-240, :272-289)
-      GemmArgs a = gemm_args(m->dy, D, w.wqkv, 3 * Q, B, 3 * Q, D, m->dq, Q);
-      a.row_scale = m->drstd;
-      a.n_split = Q; a.C1 = skv; a.c1_row_stride = (long long)L * 2 * Q; a.c1_pos = pos; a.c1_pos_stride = 2 * Q;
-      MT3_TRY(gemm(m, a, s));
-    }
-    dec_attention_kernel<<<dim3(m->H, B), kDecAttnThreads, dsm, s>>>(m->dq, Q, 0, skv, (long long)L * 2 * Q, 2 * Q, Q, pos,
-                                                                      1, max_len_sm, m->dao, Q);
-    MT3_LAUNCH_CHECK();
-    {
-      GemmArgs a = gemm_args(m->dao, Q, w.wo, D, B, D, Q, m->dy, D);
-      a.epi = EPI_RESIDUAL; a.R = m->dy; a.ldr = D;
-      MT3_TRY(gemm(m, a, s));
-    }
-    MT3_TRY(launch_rstd(m->dy, D, B, D, m->drstd, s));
-    {
-      GemmArgs a = gemm_args(m->dy, D, w.wq_c, Q, B, Q, D, m->dq, Q);
-      a.row_scale = m->drstd;
-      MT3_TRY(gemm(m, a, s));
-    }
-    dec_attention_kernel<<<dim3(m->H, B), kDecAttnThreads, dsm, s>>>(m->dq, Q, 0, ckv, (long long)T * 2 * Q, 2 * Q, Q,
-                                                                      nullptr, T, max_len_sm, m->dao, Q);
-    MT3_LAUNCH_CHECK();
-    {
-      GemmArgs a = gemm_args(m->dao, Q, w.wo_c, D, B, D, Q, m->dy, D);
-      a.epi = EPI_RESIDUAL; a.R = m->dy; a.ldr = D;
-      MT3_TRY(gemm(m, a, s));
-    }
-    MT3_TRY(launch_rstd(m->dy, D, B, D, m->drstd, s));
-    {
-      GemmArgs a = gemm_args(m->dy, D, w.wi, 2 * F, B, 2 * F, D, m->dg, F);
-      a.row_scale = m->drstd; a.epi = EPI_GATED_GELU;
-      MT3_TRY(gemm(m, a, s));
-    }
-    {
-      GemmArgs a = gemm_args(m->dg, F, w.wo2, D, B, D, F, m->dy, D);
-      a.epi = EPI_RESIDUAL; a.R = m->dy; a.ldr = D;
-      MT3_TRY(gemm(m, a, s));
-    }
+    // fused RMSNorm + QKV projection + K/V cache append (layers.py:238-240, :272-289)
+    MT3_TRY(dec_gemm(m, m->dy, D, w.wqkv, 3 * Q, D, 1, EPI_STORE, m->dq, Q, Q, skv, pos, s));
+    MT3_TRY(launch_dec_attention(m, m->dq, skv, L, pos, 1, m->dao, s));
+    MT3_TRY(dec_gemm(m, m->dao, Q, w.wo, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, s));
+    MT3_TRY(dec_gemm(m, m->dy, D, w.wq_c, Q, D, 1, EPI_STORE, m->dq, Q, Q, nullptr, nullptr, s));
+    MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, s));
+    MT3_TRY(dec_gemm(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, s));
+    MT3_TRY(dec_gemm(m, m->dy, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr, nullptr, s));
+    MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, s));
   }
-  MT3_TRY(launch_rstd(m->dy, D, B, D, m->drstd, s));
-  {
-    GemmArgs a = gemm_args(m->dy, D, m->w_logits, V, B, V, D, logits, V);
-    a.row_scale = m->drstd;
-    MT3_TRY(gemm(m, a, s));
-  }
+  MT3_TRY(dec_gemm(m, m->dy, D, m->w_logits, V, D, 1, EPI_STORE, logits, V, V, nullptr, nullptr, s));
   if (greedy) {
     argmax_step_kernel<<<B, 256, 0, s>>>(logits, V, B, use_finished ? m->tok_cur : nullptr,
                                          use_finished ? m->finished : nullptr, tokens_ws, L, tok_user, m->state, 1);
@@ -548,6 +556,11 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: PE upload -> %s", cudaGetErrorString(e));
   }
+  {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      m->sm_count = sms;
+  }
   m->tc = cfg->gemm_mode != MT3_GEMM_FP32_SIMT;
   m->split3 = cfg->gemm_mode == MT3_GEMM_TF32X3;
   if (rc == MT3_OK && m->tc) {
@@ -599,7 +612,7 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
 namespace {
 struct WsLayout {
   int64_t x_hi, x_lo, h_lo, ao_lo, g_lo, enc_hi, enc_lo;
-  int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, total;
+  int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, total;
 };
 WsLayout ws_layout(const Model* m, int B, int T) {
   WsLayout w;
@@ -632,6 +645,8 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   w.finished = take((int64_t)B * 4);
   w.tokens = take((int64_t)B * L * 4);
   w.state = take(64);
+  w.dpartial = take((int64_t)16 * cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * kDecTileFloats * 4);
+  w.dcounters = take((int64_t)cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * 4);
   w.total = off;
   return w;
 }
@@ -659,6 +674,7 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
   m->dy = (float*)(b + w.dy); m->drstd = (float*)(b + w.drstd); m->dq = (float*)(b + w.dq); m->dao = (float*)(b + w.dao);
   m->dg = (float*)(b + w.dg); m->dlogits = (float*)(b + w.dlogits); m->tok_cur = (int*)(b + w.tok_cur);
   m->finished = (int*)(b + w.finished); m->tokens = (int*)(b + w.tokens); m->state = (int*)(b + w.state);
+  m->dpartial = (float*)(b + w.dpartial); m->dcounters = (int*)(b + w.dcounters);
   m->have_cross = false;
   if (m->tc) {
     const int64_t M = (int64_t)batch * input_length;
@@ -758,29 +774,22 @@ extern "C" int mt3_debug_launch(mt3_model* h, int32_t kind, int32_t pos, int32_t
   MT3_REQUIRE(pos >= 0 && pos < m->L && iters > 0, MT3_ERR_BAD_ARG, "mt3_debug_launch: bad pos/iters");
   cudaStream_t s = (cudaStream_t)stream;
   const int B = m->B, D = m->D, Q = m->Q, L = m->L, T = m->T, M = B * T;
-  const int max_len_sm = (std::max(L, T) + 3) & ~3;
-  const size_t dsm = (size_t)(max_len_sm + 8 * kHD) * sizeof(float);
   for (int it = 0; it < iters; ++it) {
     const int l = it % m->Ld;
     switch (kind) {
       case MT3_K_DEC_SELF_ATTN: {
         float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
-        dec_attention_kernel<<<dim3(m->H, B), kDecAttnThreads, dsm, s>>>(m->dq, Q, 0, skv, (long long)L * 2 * Q, 2 * Q, Q,
-                                                                          nullptr, pos + 1, max_len_sm, m->dao, Q);
-        MT3_LAUNCH_CHECK();
+        MT3_TRY(launch_dec_attention(m, m->dq, skv, L, nullptr, pos + 1, m->dao, s));
         break;
       }
       case MT3_K_DEC_CROSS_ATTN: {
         const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
-        dec_attention_kernel<<<dim3(m->H, B), kDecAttnThreads, dsm, s>>>(m->dq, Q, 0, ckv, (long long)T * 2 * Q, 2 * Q, Q,
-                                                                          nullptr, T, max_len_sm, m->dao, Q);
-        MT3_LAUNCH_CHECK();
+        MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, s));
         break;
       }
       case MT3_K_DEC_QKV_GEMM: {
         // scratch output: the encoder qkv buffer (B*T rows >= B)
-        GemmArgs a = gemm_args(m->dy, D, m->dec[l].wqkv, 3 * Q, B, 3 * Q, D, m->qkv, 3 * Q);
-        MT3_TRY(gemm(m, a, s));
+        MT3_TRY(dec_gemm(m, m->dy, D, m->dec[l].wqkv, 3 * Q, D, 1, EPI_STORE, m->qkv, 3 * Q, 3 * Q, nullptr, nullptr, s));
         break;
       }
       case MT3_K_ENC_QKV_GEMM: {

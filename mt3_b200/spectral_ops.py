@@ -87,6 +87,8 @@ def compute_logmel(audio: torch.Tensor, lo_hz=80.0, hi_hz=7600.0, bins=64, fft_s
         out = torch.empty((S, T, bins), dtype=torch.float32, device=a.device)
     else:
         assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.numel() == S * T * bins
+    if S == 0 or T == 0:          # empty input -> zero frames (tf.signal.frame), nothing to launch
+        return out[0] if squeeze else out
     nv = None
     if n_valid_frames is not None:
         assert n_valid_frames.is_cuda and n_valid_frames.dtype == torch.int32 and n_valid_frames.numel() == S

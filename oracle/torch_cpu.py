@@ -85,7 +85,12 @@ class TorchCpuModel:
 
     def greedy_decode(self, encoded: torch.Tensor, num_steps: int, max_decode_length: int = 1024,
                       stop_at_eos: bool = False, hoist_cross_kv: bool = True, return_logits: bool = False,
-                      forced_tokens: Optional[torch.Tensor] = None):
+                      forced_tokens: Optional[torch.Tensor] = None, time_budget_s: Optional[float] = None):
+        """`time_budget_s` bounds the wall time (bench's CPU legs): the loop stops after the first
+        step that exceeds it and `self.last_steps_run` says how many steps ran."""
+        import time as _time
+        _t0 = _time.perf_counter()
+        self.last_steps_run = 0
         p, c = self.p, self.cfg
         b, t, _ = encoded.shape
         H, Dh = c.num_heads, c.head_dim
@@ -134,7 +139,10 @@ class TorchCpuModel:
                     cur = forced_tokens[:, step + 1].long()
             else:
                 cur = nxt
+            self.last_steps_run = step + 1
             if stop_at_eos and bool(finished.all()):
+                break
+            if time_budget_s is not None and _time.perf_counter() - _t0 > time_budget_s:
                 break
         if return_logits:
             return out, torch.stack(logits_all, dim=1)
