@@ -9,7 +9,7 @@ echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 
 echo "== bench simt"; timeout 600 python bench.py --steps 3 --warmup 3 2> gpurun_out/bench_simt.err | tail -1 | tee gpurun_out/bench_simt.json; tail -12 gpurun_out/bench_simt.err
 echo "== bench tf32x3"; timeout 600 python bench.py --steps 3 --warmup 3 --gemm-mode tf32x3 --no-cpu-baseline 2> gpurun_out/bench_tf32x3.err | tail -1 | tee gpurun_out/bench_tf32x3.json; tail -6 gpurun_out/bench_tf32x3.err
 echo "== ncu launch list"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
-   python bench.py --steps 1 --warmup 3 --dec-steps 4 --no-cpu-baseline --gemm-mode tf32x3 > gpurun_out/ncu_bench.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches.csv \
+   python bench.py --steps 1 --warmup 1 --dec-steps 4 --no-cpu-baseline --gemm-mode tf32x3 > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log
 python scripts/summarize_launches.py gpurun_out/launches.csv 2>&1 | tail -30
