@@ -1,0 +1,273 @@
+// K4: encoder self-attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Reference: dot_product_attention (layers.py:85-157): softmax_k(q . k^T) . v, logits NOT scaled by
+// 1/sqrt(d) (layers.py:230-234), mask all ones in the encoder (network.py:283-289).
+//
+// One CTA = 128 query rows of one (batch, head); T <= 256 keys, head_dim 64.
+//   S[128 q, T k]  = Q . K^T   tcgen05.mma kind::tf32, M=128, N=128 per key chunk, K=64 (8 k-steps);
+//                               error-compensated (Qhi.Khi + Qhi.Klo + Qlo.Khi) when hi/lo operands are given
+//   P = exp(S - rowmax)         one thread per query row reads its row from TMEM (tcgen05.ld), writes P
+//                               (rounded to tf32, unnormalised) into shared memory in the 128B-swizzled
+//                               K-major layout the next MMA reads as its A operand
+//   O[128 q, 64 d] = P . V      V is consumed in its natural [key][d] layout as an MN-major B operand
+//                               (P . Vhi + P . Vlo); 1/rowsum is applied in the epilogue.
+// TMEM: S = 256 columns, O = 64 columns (512 allocated).  Shared memory (192 KB):
+//   [ Q hi/lo 64 KB | slot0 64 KB | slot1 64 KB ]   slots hold K chunk c (hi/lo) and later V chunk c (hi/lo);
+//   the Q region is recycled as the P chunk buffer once the S MMAs have completed.
+// Operands come straight from the qkv buffers the QKV GEMM epilogue wrote ([B*T, 3*H*64] hi and lo)
+// through two TMA tensor maps; output is [B*T, H*64] (hi/lo split for the out-projection GEMM).
+#pragma once
+
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "tc.cuh"
+
+namespace mt3 {
+
+// MN-major operand, 128B swizzle: rows are K (128 B = 32 MN elements each), 8-row atoms 1024 B apart
+// (stride byte offset), the next 32 MN elements `lbo_bytes` away (leading byte offset).
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+constexpr int kAtQ = 128;                 // query rows per CTA
+constexpr int kAtKC = 128;                // keys per chunk
+constexpr int kAtSub = 128 * 32 * 4;      // one [128 x 32] fp32 sub-tile = 16 KB
+constexpr int kAtSmem = 3 * 4 * kAtSub + 1024 + 256;
+
+template <bool SPLIT3>
+__global__ void __launch_bounds__(192, 1)
+enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, int T, int H,
+                        float* __restrict__ out_hi, float* __restrict__ out_lo, int ldo) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                       // Q hi: 2 sub-tiles, Q lo: 2 sub-tiles (64 KB); later the P chunk (4 sub-tiles)
+  uint8_t* slot[2] = {smem + 4 * kAtSub, smem + 8 * kAtSub};
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 12 * kAtSub);
+  uint64_t* q_full = bars;                  // Q landed
+  uint64_t* k_full = bars + 1;              // [2] K chunk landed
+  uint64_t* v_full = bars + 3;              // [2] V chunk landed
+  uint64_t* s_done = bars + 5;              // all S MMAs complete
+  uint64_t* p_full = bars + 6;              // [2] P chunk written (128 arrivals)
+  uint64_t* pv_done = bars + 8;             // [2] PV MMAs of chunk c complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAtQ;
+  const int Q = H * 64;
+  const int nchunk = (T + kAtKC - 1) / kAtKC;              // 1 or 2
+  const int row0 = b * T;
+  constexpr uint32_t kSubBytes = kAtSub;
+  const uint32_t lo_tiles = SPLIT3 ? 2u : 1u;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tm_hi);
+    if (SPLIT3) tc::prefetch_tmap(&tm_lo);
+    tc::mbar_init(q_full, 1);
+    for (int c = 0; c < 2; ++c) {
+      tc::mbar_init(&k_full[c], 1);
+      tc::mbar_init(&v_full[c], 1);
+      tc::mbar_init(&p_full[c], 128);
+      tc::mbar_init(&pv_done[c], 1);
+    }
+    tc::mbar_init(s_done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_S = *tmem_slot;            // columns [0, 256)
+  const uint32_t tmem_O = tmem_S + 256;          // columns [256, 320)
+
+  if (warp == 0) {
+    if (tc::elect_one()) {
+      // Q: columns h*64 (+32), rows row0+q0 ..
+      tc::mbar_arrive_expect_tx(q_full, 2 * lo_tiles * kSubBytes);
+      for (int sub = 0; sub < 2; ++sub) {
+        tc::tma_load_2d(sQ + sub * kAtSub, &tm_hi, q_full, h * 64 + sub * 32, row0 + q0);
+        if (SPLIT3) tc::tma_load_2d(sQ + (2 + sub) * kAtSub, &tm_lo, q_full, h * 64 + sub * 32, row0 + q0);
+      }
+      // K chunks into slot c: [hi sub0 | hi sub1 | lo sub0 | lo sub1]
+      for (int c = 0; c < nchunk; ++c) {
+        tc::mbar_arrive_expect_tx(&k_full[c], 2 * lo_tiles * kSubBytes);
+        for (int sub = 0; sub < 2; ++sub) {
+          tc::tma_load_2d(slot[c] + sub * kAtSub, &tm_hi, &k_full[c], Q + h * 64 + sub * 32, row0 + c * kAtKC);
+          if (SPLIT3) tc::tma_load_2d(slot[c] + (2 + sub) * kAtSub, &tm_lo, &k_full[c], Q + h * 64 + sub * 32, row0 + c * kAtKC);
+        }
+      }
+      // V chunks reuse the slots once every S MMA has read K
+      tc::mbar_wait(s_done, 0);
+      for (int c = 0; c < nchunk; ++c) {
+        tc::mbar_arrive_expect_tx(&v_full[c], 2 * lo_tiles * kSubBytes);
+        for (int sub = 0; sub < 2; ++sub) {
+          tc::tma_load_2d(slot[c] + sub * kAtSub, &tm_hi, &v_full[c], 2 * Q + h * 64 + sub * 32, row0 + c * kAtKC);
+          if (SPLIT3) tc::tma_load_2d(slot[c] + (2 + sub) * kAtSub, &tm_lo, &v_full[c], 2 * Q + h * 64 + sub * 32, row0 + c * kAtKC);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (tc::elect_one()) {
+      // ---- S = Q K^T ----
+      constexpr uint32_t idesc_s = tc::make_idesc(tc::kFmtTF32, 128, kAtKC, 0, 0);
+      tc::mbar_wait(q_full, 0);
+      const uint32_t q_addr = tc::smem_u32(sQ);
+      for (int c = 0; c < nchunk; ++c) {
+        tc::mbar_wait(&k_full[c], 0);
+        tc::tc_fence_after();
+        const uint32_t k_addr = tc::smem_u32(slot[c]);
+        uint32_t acc = 0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {                     // 64 d = 2 sub-tiles x 4 k-steps of 8
+          const uint32_t off = (ks >> 2) * kSubBytes + (ks & 3) * 32;
+          const uint64_t a_hi = tc::smem_desc_k_sw128(q_addr + off);
+          const uint64_t b_hi = tc::smem_desc_k_sw128(k_addr + off);
+          if (SPLIT3) {
+            const uint64_t a_lo = tc::smem_desc_k_sw128(q_addr + 2 * kSubBytes + off);
+            const uint64_t b_lo = tc::smem_desc_k_sw128(k_addr + 2 * kSubBytes + off);
+            tc::mma_tf32(tmem_S + c * kAtKC, a_lo, b_hi, idesc_s, acc);
+            tc::mma_tf32(tmem_S + c * kAtKC, a_hi, b_lo, idesc_s, 1u);
+            tc::mma_tf32(tmem_S + c * kAtKC, a_hi, b_hi, idesc_s, 1u);
+          } else {
+            tc::mma_tf32(tmem_S + c * kAtKC, a_hi, b_hi, idesc_s, acc);
+          }
+          acc = 1u;
+        }
+      }
+      tc::mma_commit(s_done);
+      // ---- O = P V ----  A = P chunk in the Q region (K-major, 4 sub-tiles of 32 keys), B = V chunk (MN-major)
+      constexpr uint32_t idesc_o = tc::make_idesc(tc::kFmtTF32, 128, 64, 0, 1);
+      uint32_t acc = 0;
+      for (int c = 0; c < nchunk; ++c) {
+        tc::mbar_wait(&v_full[c], 0);
+        tc::mbar_wait(&p_full[c], 0);
+        tc::tc_fence_after();
+        const uint32_t p_addr = tc::smem_u32(sQ);
+        const uint32_t v_addr = tc::smem_u32(slot[c]);
+#pragma unroll
+        for (int ks = 0; ks < kAtKC / 8; ++ks) {             // 128 keys = 16 k-steps of 8
+          const uint64_t a = tc::smem_desc_k_sw128(p_addr + (ks >> 2) * kSubBytes + (ks & 3) * 32);
+          const uint64_t bh = smem_desc_mn_sw128(v_addr + ks * 1024, kSubBytes);
+          tc::mma_tf32(tmem_O, a, bh, idesc_o, acc);
+          acc = 1u;
+          if (SPLIT3) {
+            const uint64_t bl = smem_desc_mn_sw128(v_addr + 2 * kSubBytes + ks * 1024, kSubBytes);
+            tc::mma_tf32(tmem_O, a, bl, idesc_o, 1u);
+          }
+        }
+        tc::mma_commit(&pv_done[c]);
+      }
+    }
+  } else {
+    // ---- softmax + epilogue: thread owns query row q0 + 32*(warp%4) + lane ----
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;                            // row inside the tile
+    const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
+    tc::mbar_wait(s_done, 0);
+    tc::tc_fence_after();
+    float mx = -INFINITY;
+    for (int c0 = 0; c0 < T; c0 += 32) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+    }
+    float sum = 0.f;
+    for (int c = 0; c < nchunk; ++c) {
+      if (c > 0) {                                           // P buffer is recycled: wait for chunk c-1's MMAs
+        tc::mbar_wait(&pv_done[c - 1], 0);
+        tc::tc_fence_after();
+      }
+      for (int cc = 0; cc < kAtKC; cc += 32) {
+        const int c0 = c * kAtKC + cc;
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
+        tc::tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float e = (c0 + j < T) ? expf(__uint_as_float(v[j]) - mx) : 0.f;
+          e = round_tf32(e);                                // exactly what the tensor core will read
+          p[j] = e;
+          sum += e;
+        }
+        // sub-tile (cc/32) of the P chunk, row r, 8 x 16-byte pieces XOR-swizzled by (r % 8)
+        uint8_t* rowp = sQ + (cc >> 5) * kAtSub + r * 128;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          *reinterpret_cast<float4*>(rowp + ((j4 ^ (r & 7)) << 4)) = make_float4(p[4 * j4], p[4 * j4 + 1], p[4 * j4 + 2], p[4 * j4 + 3]);
+      }
+      tc::fence_proxy_async();                               // generic-proxy writes -> visible to the MMA (async proxy)
+      tc::mbar_arrive(&p_full[c]);
+    }
+    tc::mbar_wait(&pv_done[nchunk - 1], 0);
+    tc::tc_fence_after();
+    const float inv = 1.0f / sum;
+    const int q = q0 + r;
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(tmem_O + lane_base + c0, v);
+      tc::tmem_ld_wait();
+      if (q < T) {
+        const long long off = (long long)(row0 + q) * ldo + h * 64 + c0;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float o[4], oh[4], ol[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            o[j] = __uint_as_float(v[4 * j4 + j]) * inv;
+            split_tf32(o[j], oh[j], ol[j]);
+          }
+          if (out_lo) {
+            *reinterpret_cast<float4*>(out_hi + off + 4 * j4) = make_float4(oh[0], oh[1], oh[2], oh[3]);
+            *reinterpret_cast<float4*>(out_lo + off + 4 * j4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
+          } else {
+            *reinterpret_cast<float4*>(out_hi + off + 4 * j4) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc(tmem_S, 512);
+}
+
+// qkv_hi / qkv_lo: [B*T, 3*H*64]; out: [B*T, H*64] (out_lo optional).  T <= 256, T % 8 == 0.
+inline int launch_enc_attention_tc(const TcOperand& qkv, int B, int T, int H, float* out_hi, float* out_lo, bool split3,
+                                   cudaStream_t s) {
+  MT3_REQUIRE(T <= 2 * kAtKC && T % 8 == 0, MT3_ERR_UNSUPPORTED, "tc attention: T=%d (needs T <= 256, multiple of 8)", T);
+  MT3_REQUIRE(!split3 || qkv.has_lo, MT3_ERR_BAD_ARG, "tc attention: TF32X3 needs hi/lo qkv");
+  static bool attr_done = false;
+  if (!attr_done) {
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    attr_done = true;
+  }
+  dim3 grid(cdiv(T, kAtQ), H, B);
+  if (split3)
+    enc_attention_tc_kernel<true><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.lo, T, H, out_hi, out_lo, H * 64);
+  else
+    enc_attention_tc_kernel<false><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.hi, T, H, out_hi, out_lo, H * 64);
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
+}  // namespace mt3

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "attention_tc.cuh"
 #include "decode.cuh"
 #include "layers.cuh"
 
@@ -84,7 +85,8 @@ struct Model {
   float* slab_tc = nullptr;       // K-major (and hi/lo) copies for the tcgen05 path
   bool tc = false, split3 = false;
   TcW t_w_in;
-  Act a_x, a_h, a_ao, a_g, a_enc; // tcgen05-path activation buffers (workspace)
+  Act a_x, a_h, a_ao, a_g, a_enc, a_qkv; // tcgen05-path activation buffers (workspace)
+  bool tc_attn_ok = true;         // MT3_TC_ATTENTION=0 in the environment forces the exact-fp32 attention kernel
   float* w_in = nullptr;
   std::vector<EncLayer> enc;
   float* enc_norm_g = nullptr;
@@ -212,18 +214,24 @@ static int encode_tc_impl(Model* m, const float* x, float* encoded, cudaStream_t
   }
   const size_t attn_smem = (size_t)(32 * kHD + 32 * (m->T + 4) + 64 * 68) * sizeof(float);
   MT3_REQUIRE(attn_smem <= 200 * 1024, MT3_ERR_UNSUPPORTED, "encode: input_length %d too long for the attention kernel", m->T);
+  const bool tc_attn = m->tc_attn_ok && m->T <= 2 * kAtKC && m->T % 8 == 0;
   for (int l = 0; l < m->Le; ++l) {
     const EncLayer& w = m->enc[l];
     row_rstd_kernel<<<cdiv(M, 8), 256, 0, s>>>(m->a_h.hi, m->a_h.lo, D, M, D, 1e-6f, m->rstd);
     MT3_LAUNCH_CHECK();
     {
-      TcGemmArgs a = tc_args(M, 3 * Q, D, m->qkv, nullptr, 3 * Q);
+      // qkv goes out as a tf32 hi/lo pair when the tcgen05 attention kernel consumes it
+      TcGemmArgs a = tc_args(M, 3 * Q, D, m->qkv, tc_attn ? m->a_qkv.lo : nullptr, 3 * Q);
       a.row_scale = m->rstd;
       MT3_TRY(launch_tc_gemm(m->a_h.op, w.t_wqkv.op, a, m->split3, s));
     }
-    enc_attention_kernel<<<dim3(cdiv(m->T, 32), m->H, m->B), 256, attn_smem, s>>>(m->qkv, 3 * Q, m->T, m->H, m->a_ao.hi,
-                                                                                   m->a_ao.lo, Q);
-    MT3_LAUNCH_CHECK();
+    if (tc_attn) {
+      MT3_TRY(launch_enc_attention_tc(m->a_qkv.op, m->B, m->T, m->H, m->a_ao.hi, m->a_ao.lo, m->split3, s));
+    } else {
+      enc_attention_kernel<<<dim3(cdiv(m->T, 32), m->H, m->B), 256, attn_smem, s>>>(m->qkv, 3 * Q, m->T, m->H, m->a_ao.hi,
+                                                                                     m->a_ao.lo, Q);
+      MT3_LAUNCH_CHECK();
+    }
     {
       TcGemmArgs a = tc_args(M, D, Q, m->a_h.hi, m->a_h.lo, D);
       a.epi = EPI_RESIDUAL; a.R_hi = m->a_h.hi; a.R_lo = m->a_h.lo; a.ldr = D;
@@ -561,6 +569,10 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
       m->sm_count = sms;
   }
+  {
+    const char* e_attn = getenv("MT3_TC_ATTENTION");
+    m->tc_attn_ok = !(e_attn && e_attn[0] == '0');
+  }
   m->tc = cfg->gemm_mode != MT3_GEMM_FP32_SIMT;
   m->split3 = cfg->gemm_mode == MT3_GEMM_TF32X3;
   if (rc == MT3_OK && m->tc) {
@@ -611,7 +623,7 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
 
 namespace {
 struct WsLayout {
-  int64_t x_hi, x_lo, h_lo, ao_lo, g_lo, enc_hi, enc_lo;
+  int64_t x_hi, x_lo, h_lo, ao_lo, g_lo, enc_hi, enc_lo, qkv_lo;
   int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, total;
 };
 WsLayout ws_layout(const Model* m, int B, int T) {
@@ -627,6 +639,7 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   w.g_lo = take(s3 ? M * F * 4 : 0);
   w.enc_hi = take(s3 ? M * D * 4 : 0);
   w.enc_lo = take(s3 ? M * D * 4 : 0);
+  w.qkv_lo = take(s3 ? M * 3 * Q * 4 : 0);
   w.h = take(M * D * 4);
   w.rstd = take(M * 4);
   w.qkv = take(M * 3 * Q * 4);
@@ -691,6 +704,8 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
     MT3_TRY(make_operand(&m->a_h.op, m->a_h.hi, m->a_h.lo, M, m->D, m->D));
     MT3_TRY(make_operand(&m->a_ao.op, m->a_ao.hi, m->a_ao.lo, M, m->Q, m->Q));
     MT3_TRY(make_operand(&m->a_g.op, m->a_g.hi, m->a_g.lo, M, m->F, m->F));
+    m->a_qkv.hi = m->qkv; m->a_qkv.lo = s3 ? (float*)(b + w.qkv_lo) : nullptr;
+    MT3_TRY(make_operand(&m->a_qkv.op, m->a_qkv.hi, m->a_qkv.lo, M, 3 * m->Q, 3 * m->Q));
   }
   return MT3_OK;
 }
@@ -805,6 +820,10 @@ extern "C" int mt3_debug_launch(mt3_model* h, int32_t kind, int32_t pos, int32_t
         break;
       }
       case MT3_K_ENC_ATTN: {
+        if (m->tc && m->tc_attn_ok && T <= 2 * kAtKC && T % 8 == 0) {
+          MT3_TRY(launch_enc_attention_tc(m->a_qkv.op, B, T, m->H, m->a_ao.hi, m->a_ao.lo, m->split3, s));
+          break;
+        }
         MT3_TRY(set_attr_once());
         const size_t attn_smem = (size_t)(32 * kHD + 32 * (T + 4) + 64 * 68) * sizeof(float);
         enc_attention_kernel<<<dim3(cdiv(T, 32), m->H, B), 256, attn_smem, s>>>(m->qkv, 3 * Q, T, m->H, m->ao, nullptr, Q);

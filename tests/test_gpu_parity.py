@@ -321,11 +321,14 @@ def test_inference_model_api_end_to_end():
 # ------------------------------------------------------------------------------------------------
 # tcgen05 GEMM modes (encoder + cross-K/V on the tensor cores)
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("attn", ["simt", "tc"])
 @pytest.mark.parametrize("mode,tol", [("tf32x3", None), ("tf32", 3e-2)])
-def test_tensor_core_encoder_parity(mode, tol):
+def test_tensor_core_encoder_parity(mode, tol, attn, monkeypatch):
     """MT3_GEMM_TF32X3 must meet the same fp32 bar as the exact-fp32 SIMT path; single-pass TF32
     is reported with its own (10-bit mantissa) tolerance and is not the default."""
     from mt3_b200 import _lib, network
+    # attn = "simt": exact-fp32 attention between tcgen05 GEMMs (isolates the GEMM); "tc": tcgen05 attention too
+    monkeypatch.setenv("MT3_TC_ATTENTION", "1" if attn == "tc" else "0")
     cfg = network.T5Config(vocab_size=1536, emb_dim=512, num_heads=6, num_encoder_layers=8, num_decoder_layers=8,
                            head_dim=64, mlp_dim=1024, mlp_activations=('gelu', 'linear'))
     ocfg = O.T5Config()
@@ -338,7 +341,7 @@ def test_tensor_core_encoder_parity(mode, tol):
     enc32 = O.encode(params, ocfg, x, np.float32)
     scale = np.abs(enc64).max()
     e_gpu, e_f32 = np.abs(enc - enc64).max() / scale, np.abs(enc32 - enc64).max() / scale
-    print(f"encoder[{mode}]: gpu vs fp64 {e_gpu:.3e}   fp32-oracle vs fp64 {e_f32:.3e}")
+    print(f"encoder[{mode},{attn}]: gpu vs fp64 {e_gpu:.3e}   fp32-oracle vs fp64 {e_f32:.3e}")
     if tol is None:
         assert e_gpu <= max(LOGIT_TOL, 4 * e_f32)
     else:
