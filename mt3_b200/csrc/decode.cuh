@@ -40,14 +40,18 @@ struct DecGemmArgs {
   int* counters;                  // [n_tiles], zero on entry, left zero on exit
 };
 
-constexpr int kDecBM = 64, kDecBN = 32, kDecBK = 16;
+constexpr int kDecBM = 64, kDecBN = 32, kDecKC = 64;     // output tile 64 x 32, K chunk per CTA
+constexpr int kDecBK = kDecKC;                               // (host-side divisibility checks)
 constexpr int kDecTileFloats = kDecBM * kDecBN + kDecBM;   // partial tile + per-row sum of squares
 
+// Each CTA handles ONE K chunk of 64: all of its global loads (8 KB of weights, 16 KB of activations)
+// are issued before anything is consumed -- one memory latency per CTA instead of one per k-tile --
+// then the 64 k-steps run out of shared memory with no further synchronisation.
 __global__ void __launch_bounds__(128)
 sgemm_dec_kernel(const DecGemmArgs p) {
-  constexpr int BM = kDecBM, BN = kDecBN, BK = kDecBK, NT = 128, APAD = 4;
-  __shared__ __align__(16) float As[2][BK][BM + APAD];
-  __shared__ __align__(16) float Bs[2][BK][BN];
+  constexpr int BM = kDecBM, BN = kDecBN, KC = kDecKC, NT = 128, APAD = 4;
+  __shared__ __align__(16) float As[KC][BM + APAD];      // transposed: [k][m]
+  __shared__ __align__(16) float Bs[KC][BN];
   __shared__ float s_ss[BM];
   __shared__ int s_last;
 
@@ -55,72 +59,65 @@ sgemm_dec_kernel(const DecGemmArgs p) {
   const int tx = tid % 8, ty = tid / 8;                  // thread tile: rows ty*4.., cols tx*4..
   const int n0 = blockIdx.x * BN;
   const int splits = gridDim.y, ks = blockIdx.y;
-  const int kc = p.K / splits;                           // host guarantees kc % BK == 0
-  const int kbeg = ks * kc;
+  const int kbeg = ks * KC;                              // host guarantees K == splits * KC
 
-  float4 ra[2], rb;
-  float ss[2] = {0.f, 0.f};                              // sum of squares of rows tid/4 and tid/4 + 32
-  auto load_tiles = [&](int k0) {
+  // ---- load phase: 4 weight + 8 activation 16-byte loads per thread, all in flight together ----
+  float4 rb[4], ra[8];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int idx = tid + i * NT;
-      const int row = idx >> 2, kq = idx & 3;
-      ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < p.M) ra[i] = *reinterpret_cast<const float4*>(p.A + (long long)row * p.lda + k0 + kq * 4);
-      ss[i] += ra[i].x * ra[i].x + ra[i].y * ra[i].y + ra[i].z * ra[i].z + ra[i].w * ra[i].w;
-    }
-    {
-      const int kr = tid >> 3, nq = tid & 7;
-      rb = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + nq * 4 < p.N) rb = __ldg(reinterpret_cast<const float4*>(p.W + (long long)(k0 + kr) * p.ldw + n0 + nq * 4));
-    }
-  };
-  auto store_tiles = [&](int buf) {
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + i * NT;                        // 512 float4: [64 k][8 column quads]
+    const int kr = idx >> 3, nq = idx & 7;
+    rb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n0 + nq * 4 < p.N) rb[i] = __ldg(reinterpret_cast<const float4*>(p.W + (long long)(kbeg + kr) * p.ldw + n0 + nq * 4));
+  }
+  // weights do not depend on the previous kernel: they are in flight while it drains (PDL)
+  pdl_wait();
+  pdl_trigger();
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int idx = tid + i * NT;
-      const int row = idx >> 2, kq = idx & 3;
-      As[buf][kq * 4 + 0][row] = ra[i].x;
-      As[buf][kq * 4 + 1][row] = ra[i].y;
-      As[buf][kq * 4 + 2][row] = ra[i].z;
-      As[buf][kq * 4 + 3][row] = ra[i].w;
-    }
-    *reinterpret_cast<float4*>(&Bs[buf][tid >> 3][(tid & 7) * 4]) = rb;
-  };
+  for (int i = 0; i < 8; ++i) {
+    const int idx = tid + i * NT;                        // 1024 float4: [64 m][16 k quads]
+    const int row = idx >> 4, kq = idx & 15;
+    ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < p.M) ra[i] = *reinterpret_cast<const float4*>(p.A + (long long)row * p.lda + kbeg + kq * 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int idx = tid + i * NT;
+    *reinterpret_cast<float4*>(&Bs[idx >> 3][(idx & 7) * 4]) = rb[i];
+  }
+  // rows handled by this thread in the A load: (tid >> 4) + 8 i ; 16 consecutive lanes share a row
+  float ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int idx = tid + i * NT;
+    const int row = idx >> 4, kq = idx & 15;
+    As[kq * 4 + 0][row] = ra[i].x;
+    As[kq * 4 + 1][row] = ra[i].y;
+    As[kq * 4 + 2][row] = ra[i].z;
+    As[kq * 4 + 3][row] = ra[i].w;
+    float v = ra[i].x * ra[i].x + ra[i].y * ra[i].y + ra[i].z * ra[i].z + ra[i].w * ra[i].w;
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    ss[i] = v;                                           // sum of squares of row (tid>>4) + 8 i over this K chunk
+  }
+  __syncthreads();
 
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-  const int nk = kc / BK;
-  load_tiles(kbeg);
-  store_tiles(0);
-  __syncthreads();
-  for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nk) load_tiles(kbeg + (kt + 1) * BK);
+#pragma unroll 16
+  for (int k = 0; k < KC; ++k) {
+    const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+    const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-    if (kt + 1 < nk) {
-      store_tiles(buf ^ 1);
-      __syncthreads();
-    }
-  }
-  // per-row sum of squares over this CTA's K range: the 4 threads sharing a row are adjacent lanes
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 1);
-    ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], 2);
+      for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
   }
 
   const int n_tiles = gridDim.x;
@@ -129,9 +126,9 @@ sgemm_dec_kernel(const DecGemmArgs p) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       *reinterpret_cast<float4*>(mine + (ty * 4 + i) * BN + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    if ((tid & 3) == 0) {
-      mine[BM * BN + (tid >> 2)] = ss[0];
-      mine[BM * BN + (tid >> 2) + 32] = ss[1];
+    if ((tid & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mine[BM * BN + (tid >> 4) + 8 * i] = ss[i];
     }
     __threadfence();
     __syncthreads();
@@ -149,20 +146,33 @@ sgemm_dec_kernel(const DecGemmArgs p) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     float sst = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const float* src = p.partial + ((long long)s * n_tiles + blockIdx.x) * kDecTileFloats;
+    for (int s0 = 0; s0 < splits; s0 += 4) {
+      float4 v[4][4];
+      float sv[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (ty * 4 + i) * BN + tx * 4));
-        acc[i][0] += v.x; acc[i][1] += v.y; acc[i][2] += v.z; acc[i][3] += v.w;
+      for (int u = 0; u < 4; ++u) {                      // 4 partial tiles in flight per round
+        const int s = s0 + u;
+        const float* src = p.partial + ((long long)min(s, splits - 1) * n_tiles + blockIdx.x) * kDecTileFloats;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[u][i] = __ldcg(reinterpret_cast<const float4*>(src + (ty * 4 + i) * BN + tx * 4));
+        sv[u] = (tid < BM) ? __ldcg(src + BM * BN + tid) : 0.f;
       }
-      if (tid < BM) sst += __ldcg(src + BM * BN + tid);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (s0 + u < splits) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i][0] += v[u][i].x; acc[i][1] += v[u][i].y; acc[i][2] += v[u][i].z; acc[i][3] += v[u][i].w;
+          }
+          sst += sv[u];
+        }
+      }
     }
     if (tid < BM) s_ss[tid] = sst;
   } else {
-    if ((tid & 3) == 0) {
-      s_ss[tid >> 2] = ss[0];
-      s_ss[(tid >> 2) + 32] = ss[1];
+    if ((tid & 15) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_ss[(tid >> 4) + 8 * i] = ss[i];
     }
   }
   __syncthreads();
@@ -193,22 +203,17 @@ sgemm_dec_kernel(const DecGemmArgs p) {
   }
 }
 
-// K split so that about one wave of CTAs streams the weight matrix.
+// One CTA per (32-column tile, 64-deep K chunk).
 inline int dec_gemm_splits(int N, int K, int sm_count) {
-  const int n_tiles = cdiv(N, kDecBN);
-  int best = 1;
-  for (int s = 2; s <= 16; s *= 2) {
-    if (K % s != 0 || (K / s) % kDecBK != 0 || K / s < 32) break;
-    if (n_tiles * s <= sm_count + sm_count / 8) best = s;
-  }
-  return best;
+  (void)N; (void)sm_count;
+  return K / kDecKC;
 }
 
-inline int launch_dec_gemm(const DecGemmArgs& a, int splits, cudaStream_t s) {
+inline int launch_dec_gemm(const DecGemmArgs& a, int splits, cudaStream_t s, bool pdl = false) {
   MT3_REQUIRE(a.M <= kDecBM, MT3_ERR_UNSUPPORTED, "decode gemm: M=%d > %d rows", a.M, kDecBM);
-  MT3_REQUIRE(a.K % (splits * kDecBK) == 0 && a.N % 4 == 0 && a.lda % 4 == 0 && a.ldw % 4 == 0 && a.n_split % 4 == 0,
-              MT3_ERR_UNSUPPORTED, "decode gemm: K=%d splits=%d N=%d not tileable", a.K, splits, a.N);
-  sgemm_dec_kernel<<<dim3(cdiv(a.N, kDecBN), splits), 128, 0, s>>>(a);
+  MT3_REQUIRE(a.K == splits * kDecKC && a.N % 4 == 0 && a.lda % 4 == 0 && a.ldw % 4 == 0 && a.n_split % 4 == 0,
+              MT3_ERR_UNSUPPORTED, "decode gemm: K=%d must be splits(%d) x %d; N=%d", a.K, splits, kDecKC, a.N);
+  MT3_CUDA_CHECK(launch_kernel(sgemm_dec_kernel, dim3(cdiv(a.N, kDecBN), splits), dim3(128), 0, s, pdl, a));
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }
@@ -263,6 +268,10 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
 
   if (warp == 4) {
     // ---- producer: K tiles 0..nt-1, then V tiles 0..nt-1 ----
+    // self-attention (len_ptr set): the newest cache row comes from the preceding QKV GEMM -> wait;
+    // the hoisted cross K/V is independent of every decode-step kernel -> stream it right away (PDL)
+    if (len_ptr) pdl_wait();
+    pdl_trigger();
     if (lane == 0) {
       for (int j = 0; j < 2 * nt; ++j) {
         const int s = j % kAttStages;
@@ -281,6 +290,8 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
 
   // ---- consumers (128 threads) ----
   // pass 1: scores.  16 lanes cover one key row (conflict-free 256-byte read), 2 keys per warp instruction.
+  pdl_wait();                                                    // q comes from the preceding GEMM
+  pdl_trigger();
   const int c = lane & 15, half = lane >> 4;
   const float4 q4 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + q_off + h * 64 + c * 4);
   float lmax = -INFINITY;

@@ -191,6 +191,8 @@ enc_attention_kernel(const float* __restrict__ qkv, int ld, int T, int H, float*
 // ---------------------------------------------------------------------------------
 __global__ void embed_kernel(const int* __restrict__ tok, const float* __restrict__ emb, int D, int vocab,
                              const float* __restrict__ pe, const int* __restrict__ pos_ptr, float* __restrict__ y) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x;
   int t = tok[b];
   t = min(max(t, 0), vocab - 1);
@@ -217,6 +219,8 @@ argmax_step_kernel(const float* __restrict__ logits, int V, int B, int* __restri
                    int* __restrict__ state, int advance) {
   __shared__ float sv[8];
   __shared__ int si[8];
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* l = logits + (long long)b * V;
   float best = -INFINITY;
@@ -265,7 +269,10 @@ argmax_step_kernel(const float* __restrict__ logits, int V, int B, int* __restri
 }
 
 // advance the position without an argmax (decode_step called with tok_out == NULL)
-__global__ void advance_pos_kernel(int* state) { state[0] += 1; }
+__global__ void advance_pos_kernel(int* state) {
+  pdl_wait();
+  state[0] += 1;
+}
 
 // GenericTokenVocabulary._decode_tf (vocabularies.py:241-271).
 __global__ void vocab_decode_kernel(const int* __restrict__ ids, int B, int L, int num_regular, int* __restrict__ out) {

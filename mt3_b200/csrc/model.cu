@@ -86,6 +86,7 @@ struct Model {
   bool tc = false, split3 = false;
   TcW t_w_in;
   Act a_x, a_h, a_ao, a_g, a_enc, a_qkv; // tcgen05-path activation buffers (workspace)
+  bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between the decode-step kernels
   bool tc_attn_ok = true;         // MT3_TC_ATTENTION=0 in the environment forces the exact-fp32 attention kernel
   float* w_in = nullptr;
   std::vector<EncLayer> enc;
@@ -356,7 +357,7 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
       a.C1 = kv + (int64_t)r0 * 2 * m->H * m->L * 64; a.hm_rows_per_b = 1; a.hm_cap = m->L; a.hm_H = m->H; a.hm_pos = pos;
     }
     a.partial = m->dpartial; a.counters = m->dcounters;
-    MT3_TRY(launch_dec_gemm(a, splits, s));
+    MT3_TRY(launch_dec_gemm(a, splits, s, m->pdl));
   }
   return MT3_OK;
 }
@@ -371,8 +372,8 @@ static int launch_dec_attention(Model* m, const float* q, const float* kv, int c
     attr_done = true;
   }
   MT3_REQUIRE(smem <= 100 * 1024, MT3_ERR_UNSUPPORTED, "decode attention: length %d too long", max_len);
-  dec_attention_bulk_kernel<<<dim3(m->H, m->B), kAttThreads, smem, s>>>(q, m->Q, 0, kv, m->H, cap, len_ptr, len_add, max_len,
-                                                                         out, m->Q);
+  MT3_CUDA_CHECK(launch_kernel(dec_attention_bulk_kernel, dim3(m->H, m->B), dim3(kAttThreads), smem, s, m->pdl, q, m->Q, 0, kv,
+                               m->H, cap, len_ptr, len_add, max_len, out, m->Q));
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }
@@ -385,7 +386,8 @@ static int decode_step_impl(Model* m, const int* tok_in, float* logits, int gree
                             int* tokens_ws, cudaStream_t s) {
   const int B = m->B, D = m->D, Q = m->Q, F = m->F, V = m->V, L = m->L, T = m->T;
   int* pos = m->state;
-  embed_kernel<<<B, 128, 0, s>>>(tok_in, m->emb, D, V, m->pe, pos, m->dy);
+  MT3_CUDA_CHECK(launch_kernel(embed_kernel, dim3(B), dim3(128), 0, s, m->pdl, tok_in, (const float*)m->emb, D, V,
+                               (const float*)m->pe, (const int*)pos, m->dy));
   MT3_LAUNCH_CHECK();
   for (int l = 0; l < m->Ld; ++l) {
     const DecLayer& w = m->dec[l];
@@ -403,11 +405,12 @@ static int decode_step_impl(Model* m, const int* tok_in, float* logits, int gree
   }
   MT3_TRY(dec_gemm(m, m->dy, D, m->w_logits, V, D, 1, EPI_STORE, logits, V, V, nullptr, nullptr, s));
   if (greedy) {
-    argmax_step_kernel<<<B, 256, 0, s>>>(logits, V, B, use_finished ? m->tok_cur : nullptr,
-                                         use_finished ? m->finished : nullptr, tokens_ws, L, tok_user, m->state, 1);
+    MT3_CUDA_CHECK(launch_kernel(argmax_step_kernel, dim3(B), dim3(256), 0, s, m->pdl, (const float*)logits, V, B,
+                                 use_finished ? m->tok_cur : (int*)nullptr, use_finished ? m->finished : (int*)nullptr,
+                                 tokens_ws, L, tok_user, m->state, 1));
     MT3_LAUNCH_CHECK();
   } else {
-    advance_pos_kernel<<<1, 1, 0, s>>>(m->state);
+    MT3_CUDA_CHECK(launch_kernel(advance_pos_kernel, dim3(1), dim3(1), 0, s, m->pdl, m->state));
     MT3_LAUNCH_CHECK();
   }
   return MT3_OK;
@@ -463,8 +466,8 @@ extern "C" int64_t mt3_model_param_offset(const mt3_model_config* cfg, const cha
 extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weights, mt3_model** out, void* stream) {
   MT3_REQUIRE(cfg && weights && out, MT3_ERR_BAD_ARG, "mt3_model_create: null argument");
   MT3_REQUIRE(cfg->head_dim == kHD, MT3_ERR_UNSUPPORTED, "mt3_model_create: head_dim %d (kernels are built for 64)", cfg->head_dim);
-  MT3_REQUIRE(cfg->emb_dim % 16 == 0 && cfg->mlp_dim % 16 == 0 && cfg->input_depth % 16 == 0 && cfg->vocab_size % 4 == 0,
-              MT3_ERR_UNSUPPORTED, "mt3_model_create: emb/mlp/input dims must be multiples of 16, vocab of 4");
+  MT3_REQUIRE(cfg->emb_dim % 64 == 0 && cfg->mlp_dim % 64 == 0 && cfg->input_depth % 16 == 0 && cfg->vocab_size % 4 == 0,
+              MT3_ERR_UNSUPPORTED, "mt3_model_create: emb/mlp dims must be multiples of 64, input depth of 16, vocab of 4");
   MT3_REQUIRE(cfg->num_heads > 0 && cfg->num_encoder_layers >= 0 && cfg->num_decoder_layers > 0 && cfg->max_batch > 0 &&
                   cfg->max_input_length > 0 && cfg->max_decode_length > 0,
               MT3_ERR_BAD_ARG, "mt3_model_create: non-positive size");
@@ -570,6 +573,8 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
       m->sm_count = sms;
   }
   {
+    const char* e_pdl = getenv("MT3_PDL");
+    m->pdl = e_pdl && e_pdl[0] == '1';
     const char* e_attn = getenv("MT3_TC_ATTENTION");
     m->tc_attn_ok = !(e_attn && e_attn[0] == '0');
   }

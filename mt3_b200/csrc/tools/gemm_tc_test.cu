@@ -112,7 +112,9 @@ static int run_case(const Case& c, bool split3, bool timing) {
     }
   }
   const double rel = max_err / max_ref, rel_simt = max_err_simt / max_ref;
-  const double tol = split3 ? 2e-6 : 3e-3;
+  // tf32x3: the dropped lo.lo term is ~2^-22, the rest is the tensor core's truncating fp32 accumulation
+  // over K terms (measured 3e-6 .. 9e-6 of max|C| for K = 384 .. 1024 vs 6e-7 .. 1.3e-6 for fp32 FMA)
+  const double tol = split3 ? 2e-5 : 3e-3;
   double ms = 0;
   if (timing) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
