@@ -10,10 +10,9 @@ tf.data / seqio / T5X are replaced by plain Python lists and the CUDA library:
     audio --host pad/split--> segments --H2D--> log-mel kernel --> encoder + greedy decoder
           --D2H--> token ids --vocabulary.decode_tf--> per-segment predictions
 
-A "dataset" here is a list of example dicts.  Known divergences from the notebook are
-recorded in DESIGN.md: greedy instead of T5X beam_search(num_decodes=1) and
-`__call__` returning the per-segment predictions (the input of
-metrics_utils.event_predictions_to_ns) until the note-sequence stitch row is built.
+A "dataset" here is a list of example dicts.  Known divergence from the notebook, recorded in
+DESIGN.md: greedy instead of T5X beam_search(num_decodes=1).  `__call__` returns a
+NoteSequence built by the host-side stitch in mt3_b200/note_decoding.py.
 """
 from __future__ import annotations
 
@@ -23,7 +22,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from . import _lib, gin_lite, network, spectrograms, vocabularies, weights
+from . import _lib, gin_lite, network, note_decoding, spectrograms, vocabularies, weights
 
 _GIN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gin")
 
@@ -168,11 +167,19 @@ class InferenceModel(object):
         return torch.cat([spec, pad], dim=1)
 
     def __call__(self, audio):
-        """Infer event tokens from audio samples (notebook :283-308).
+        """Infer note sequence from audio samples (notebook :283-308).
 
         audio: 1-d numpy array of audio samples (16kHz) for a single example.
-        Returns the list of per-segment predictions {'est_tokens', 'start_time', 'raw_inputs'} --
-        exactly what the notebook passes to metrics_utils.event_predictions_to_ns."""
+        Returns the transcribed NoteSequence (mt3_b200.note_decoding.NoteSequence, the stand-in for
+        note_seq's protobuf): segments are decoded on the GPU, their event tokens stitched on the host
+        by event_predictions_to_ns exactly as the notebook does (:305-308)."""
+        predictions = self.predict_segments(audio)
+        result = note_decoding.event_predictions_to_ns(predictions, codec=self.codec, encoding_spec=self.encoding_spec)
+        return result['est_ns']
+
+    def predict_segments(self, audio):
+        """audio -> list of per-segment predictions {'est_tokens', 'start_time', 'raw_inputs'} (the
+        argument of metrics_utils.event_predictions_to_ns)."""
         ds = self.audio_to_dataset(audio)
         ds = self.preprocess(ds)
         hop = self.spectrogram_config.hop_width

@@ -1,0 +1,133 @@
+"""Known-answer tests of the token -> NoteSequence stitch, restated from the reference's
+note_sequences_test.py:290-501 and metrics_utils_test.py:28-238 (same tokens, same expected notes)."""
+import numpy as np
+import pytest
+
+from mt3_b200 import event_codec as ec
+from mt3_b200 import note_decoding as nd
+
+
+def _codec(*types):
+    ranges = {'pitch': ec.EventRange('pitch', 0, 127), 'velocity': ec.EventRange('velocity', 0, 127),
+              'drum': ec.EventRange('drum', 0, 127), 'program': ec.EventRange('program', 0, 127),
+              'tie': ec.EventRange('tie', 0, 0)}
+    return ec.Codec(max_shift_steps=100, steps_per_second=100, event_ranges=[ranges[t] for t in types])
+
+
+FULL = _codec('pitch', 'velocity', 'drum', 'program', 'tie')     # note_sequences_test.py:23-35
+
+
+def _decode(tokens, spec, start_time=0, max_time=None, codec=FULL):
+    d = nd.NoteDecoder(codec, spec)
+    inv, drop = d.feed(tokens, start_time, max_time)
+    return d.flush(), inv, drop
+
+
+def _notes(ns):
+    return [(n.pitch, n.velocity, round(n.start_time, 6), round(n.end_time, 6), n.program, n.is_drum, n.instrument)
+            for n in ns.notes]
+
+
+def test_onsets_only():
+    ns, inv, drop = _decode([25, 161, 50, 162], 'NoteOnsetEncodingSpec')          # :290-313
+    assert (inv, drop) == (0, 0)
+    assert _notes(ns) == [(60, 100, 0.25, 0.26, 0, False, 0), (61, 100, 0.50, 0.51, 0, False, 0)]
+    assert ns.total_time == pytest.approx(0.51)
+    ns, inv, drop = _decode([5, 161, 25, 162], 'NoteOnsetEncodingSpec')           # :315-338
+    assert _notes(ns) == [(60, 100, 0.05, 0.06, 0, False, 0), (61, 100, 0.25, 0.26, 0, False, 0)]
+
+
+def test_velocity_and_missing_offset():
+    ns, inv, drop = _decode([5, 356, 161, 25, 229, 161], 'NoteEncodingSpec')       # :340-357
+    assert (inv, drop) == (0, 0)
+    assert _notes(ns) == [(60, 127, 0.05, 0.25, 0, False, 0)] and ns.total_time == pytest.approx(0.25)
+    ns, inv, drop = _decode([5, 356, 161, 10, 161, 25, 229, 161], 'NoteEncodingSpec')   # :359-381
+    assert _notes(ns) == [(60, 127, 0.05, 0.10, 0, False, 0), (60, 127, 0.10, 0.25, 0, False, 0)]
+
+
+def test_multitrack():
+    ns, inv, drop = _decode([5, 525, 356, 161, 15, 356, 394, 25, 525, 229, 161], 'NoteEncodingSpec')   # :383-409
+    assert (inv, drop) == (0, 0)
+    assert _notes(ns) == [(37, 127, 0.15, 0.16, 0, True, 9), (60, 127, 0.05, 0.25, 40, False, 0)]
+
+
+def test_invalid_tokens_and_events():
+    ns, inv, drop = _decode([5, -1, 161, -2, 25, 162, 9999], 'NoteOnsetEncodingSpec')   # :411-435
+    assert (inv, drop) == (3, 0)
+    assert _notes(ns) == [(60, 100, 0.05, 0.06, 0, False, 0), (61, 100, 0.25, 0.26, 0, False, 0)]
+    ns, inv, drop = _decode([25, 230, 50, 161], 'NoteOnsetEncodingSpec')           # :483-501 (velocity event is invalid here)
+    assert (inv, drop) == (1, 0)
+    assert _notes(ns) == [(60, 100, 0.50, 0.51, 0, False, 0)]
+
+
+def test_max_time():
+    ns, inv, drop = _decode([161, 25, 162], 'NoteOnsetEncodingSpec', start_time=1.0, max_time=1.25)    # :437-461
+    assert (inv, drop) == (0, 0)
+    assert _notes(ns) == [(60, 100, 1.00, 1.01, 0, False, 0), (61, 100, 1.25, 1.26, 0, False, 0)]
+    ns, inv, drop = _decode([5, 161, 30, 162], 'NoteOnsetEncodingSpec', start_time=1.0, max_time=1.25)  # :463-481
+    assert (inv, drop) == (0, 2)
+    assert _notes(ns) == [(60, 100, 1.05, 1.06, 0, False, 0)]
+
+
+def _preds(tok_lists):
+    return [{'raw_inputs': [i, i], 'start_time': 0.4 * i, 'est_tokens': t} for i, t in enumerate(tok_lists)]
+
+
+def test_event_predictions_to_ns_onsets():
+    res = nd.event_predictions_to_ns(_preds([[20, 160], [20, 161, 50, 162], [163, 20, 164]]), _codec('pitch'),
+                                     'NoteOnsetEncodingSpec')                      # metrics_utils_test.py:28-80
+    assert _notes(res['est_ns']) == [(59, 100, 0.20, 0.21, 0, False, 0), (60, 100, 0.60, 0.61, 0, False, 0),
+                                     (62, 100, 0.80, 0.81, 0, False, 0), (63, 100, 1.00, 1.01, 0, False, 0)]
+    assert res['est_ns'].total_time == pytest.approx(1.01)
+    assert (res['est_invalid_events'], res['est_dropped_events']) == (0, 2)
+    np.testing.assert_array_equal(res['raw_inputs'], [0, 0, 1, 1, 2, 2])
+    assert res['start_times'] == [0.0, 0.4, 0.8]
+
+
+def test_event_predictions_to_ns_with_offsets():
+    res = nd.event_predictions_to_ns(_preds([[20, 356, 160], [20, 292, 161], [20, 229, 160, 161]]),
+                                     _codec('pitch', 'velocity'), 'NoteEncodingSpec')   # :82-128
+    assert _notes(res['est_ns']) == [(59, 127, 0.20, 1.00, 0, False, 0), (60, 63, 0.60, 1.00, 0, False, 0)]
+    assert (res['est_invalid_events'], res['est_dropped_events']) == (0, 0)
+
+
+def test_event_predictions_to_ns_multitrack_and_ties():
+    c4 = _codec('pitch', 'velocity', 'drum', 'program')
+    res = nd.event_predictions_to_ns(_preds([[20, 517, 356, 160], [20, 356, 399], [20, 517, 229, 160]]), c4,
+                                     'NoteEncodingSpec')                           # :130-180
+    assert _notes(res['est_ns']) == [(42, 127, 0.60, 0.61, 0, True, 9), (59, 127, 0.20, 1.00, 32, False, 0)]
+    res = nd.event_predictions_to_ns(_preds([[613, 20, 517, 356, 160], [517, 160, 613, 20, 356, 399], [613]]), FULL,
+                                     'NoteEncodingWithTiesSpec')                   # :182-238
+    assert _notes(res['est_ns']) == [(42, 127, 0.60, 0.61, 0, True, 9), (59, 127, 0.20, 0.80, 32, False, 0)]
+    assert res['est_ns'].total_time == pytest.approx(0.80)
+    assert (res['est_invalid_events'], res['est_dropped_events']) == (0, 0)
+    # predictions arriving out of order are sorted by start time (metrics_utils.py:88)
+    p = _preds([[613, 20, 517, 356, 160], [517, 160, 613, 20, 356, 399], [613]])
+    res2 = nd.event_predictions_to_ns(list(reversed(p)), FULL, 'NoteEncodingWithTiesSpec')
+    assert _notes(res2['est_ns']) == _notes(res['est_ns'])
+
+
+def test_assign_instruments_skips_drum_channel():
+    ns = nd.NoteSequence()
+    for prog in range(11):
+        ns.add(0.0, 0.1, 60, 100, program=prog)
+    ns.add(0.0, 0.1, 36, 100, is_drum=True)
+    nd.assign_instruments(ns)
+    assert [n.instrument for n in ns.notes] == [0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 9]    # note_sequences.py:72-84
+
+
+def test_midi_writer_roundtrip_header(tmp_path):
+    ns, _, _ = _decode([5, 525, 356, 161, 15, 356, 394, 25, 525, 229, 161], 'NoteEncodingSpec')
+    data = nd.note_sequence_to_midi_bytes(ns)
+    assert data[:4] == b'MThd' and int.from_bytes(data[8:10], 'big') == 1
+    assert int.from_bytes(data[10:12], 'big') == 3          # tempo track + melodic + drums
+    assert int.from_bytes(data[12:14], 'big') == 220
+    assert data.count(b'MTrk') == 3
+    f = tmp_path / "t.mid"
+    nd.note_sequence_to_midi_file(ns, str(f))
+    assert f.read_bytes() == data
+
+
+def test_unknown_spec():
+    with pytest.raises(ValueError):
+        nd.NoteDecoder(FULL, 'NoSuchSpec')
