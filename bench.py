@@ -335,6 +335,23 @@ def run_ours(args):
         roofline = {"kernel": "dec_attention_bulk_kernel (decode self-attention, cache length 512, B=64, 6 heads)", "bound": "hbm",
                     "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                     "peak_source": peak_src, "us_per_launch": us, "algorithmic_bytes_per_launch": alg_bytes}
+        # back-to-back launch time of the other hot kernels at the bench shapes (device events, stream order)
+        kernels_us = {}
+        for name, kind, p_, it_ in (("dec_self_attention_len512", _lib.K_DEC_SELF_ATTN, 511, 64),
+                                    ("dec_cross_attention_len256", _lib.K_DEC_CROSS_ATTN, 0, 64),
+                                    ("dec_qkv_gemm_64x1152x512", _lib.K_DEC_QKV_GEMM, 0, 64),
+                                    ("enc_qkv_gemm_16384x1152x512", _lib.K_ENC_QKV_GEMM, 0, 16),
+                                    ("enc_attention_64x6x256x256", _lib.K_ENC_ATTN, 0, 16)):
+            _lib.check(lib.mt3_debug_launch(h, kind, p_, 4, stream))
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(lib.mt3_debug_launch(h, kind, p_, it_, stream))
+            e1.record()
+            torch.cuda.synchronize(dev)
+            kernels_us[name] = 1000.0 * e0.elapsed_time(e1) / it_
+        roofline["other_kernels_us_per_launch"] = kernels_us
+        log("kernel microbench: " + ", ".join(f"{k}={v:.1f}us" for k, v in kernels_us.items()))
         if world == 1 and not args.no_cpu_baseline:
             log("cpu baseline (torch-CPU port) ...")
             v, cores, desc, _ = cpu_port_sample(params, audio_host, args.ref_batch, dec_steps, args.ref_budget_s)

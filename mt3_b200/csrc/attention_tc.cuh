@@ -50,7 +50,9 @@ constexpr int kAtSmem = 3 * 4 * kAtSub + 1024 + 256;
 template <bool SPLIT3>
 __global__ void __launch_bounds__(192, 1)
 enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, int T, int H,
-                        float* __restrict__ out_hi, float* __restrict__ out_lo, int ldo) {
+                        float* __restrict__ out_hi, float* __restrict__ out_lo, int ldo, float* __restrict__ dbg_S,
+                        int variant) {
+  // dbg_S (bring-up tool only): raw S rows [B][H][T][T].  variant: V-descriptor hypothesis under test.
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                       // Q hi: 2 sub-tiles, Q lo: 2 sub-tiles (64 KB); later the P chunk (4 sub-tiles)
@@ -162,13 +164,15 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
 #pragma unroll
         for (int ks = 0; ks < kAtKC / 8; ++ks) {             // 128 keys = 16 k-steps of 8
           const uint64_t a = tc::smem_desc_k_sw128(p_addr + (ks >> 2) * kSubBytes + (ks & 3) * 32);
-          const uint64_t bh = smem_desc_mn_sw128(v_addr + ks * 1024, kSubBytes);
-          tc::mma_tf32(tmem_O, a, bh, idesc_o, acc);
-          acc = 1u;
-          if (SPLIT3) {
-            const uint64_t bl = smem_desc_mn_sw128(v_addr + 2 * kSubBytes + ks * 1024, kSubBytes);
-            tc::mma_tf32(tmem_O, a, bl, idesc_o, 1u);
+          uint64_t bh = smem_desc_mn_sw128(v_addr + ks * 1024, kSubBytes);
+          uint64_t bl = smem_desc_mn_sw128(v_addr + 2 * kSubBytes + ks * 1024, kSubBytes);
+          if (variant == 1) {   // hypothesis: LBO / SBO roles swapped for MN-major
+            bh = (bh & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(kSubBytes >> 4) << 32);
+            bl = (bl & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(kSubBytes >> 4) << 32);
           }
+          tc::mma_tf32(tmem_O, a, bh, variant == 2 ? tc::make_idesc(tc::kFmtTF32, 128, 64, 0, 0) : idesc_o, acc);
+          acc = 1u;
+          if (SPLIT3) tc::mma_tf32(tmem_O, a, bl, variant == 2 ? tc::make_idesc(tc::kFmtTF32, 128, 64, 0, 0) : idesc_o, 1u);
         }
         tc::mma_commit(&pv_done[c]);
       }
@@ -188,6 +192,11 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+      if (dbg_S && q0 + r < T) {
+        float* drow = dbg_S + (((long long)b * H + h) * T + q0 + r) * T + c0;
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < T) drow[j] = __uint_as_float(v[j]);
+      }
     }
     float sum = 0.f;
     for (int c = 0; c < nchunk; ++c) {
@@ -252,7 +261,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
 
 // qkv_hi / qkv_lo: [B*T, 3*H*64]; out: [B*T, H*64] (out_lo optional).  T <= 256, T % 8 == 0.
 inline int launch_enc_attention_tc(const TcOperand& qkv, int B, int T, int H, float* out_hi, float* out_lo, bool split3,
-                                   cudaStream_t s) {
+                                   cudaStream_t s, float* dbg_S = nullptr, int variant = 0) {
   MT3_REQUIRE(T <= 2 * kAtKC && T % 8 == 0, MT3_ERR_UNSUPPORTED, "tc attention: T=%d (needs T <= 256, multiple of 8)", T);
   MT3_REQUIRE(!split3 || qkv.has_lo, MT3_ERR_BAD_ARG, "tc attention: TF32X3 needs hi/lo qkv");
   static bool attr_done = false;
@@ -263,9 +272,9 @@ inline int launch_enc_attention_tc(const TcOperand& qkv, int B, int T, int H, fl
   }
   dim3 grid(cdiv(T, kAtQ), H, B);
   if (split3)
-    enc_attention_tc_kernel<true><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.lo, T, H, out_hi, out_lo, H * 64);
+    enc_attention_tc_kernel<true><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.lo, T, H, out_hi, out_lo, H * 64, dbg_S, variant);
   else
-    enc_attention_tc_kernel<false><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.hi, T, H, out_hi, out_lo, H * 64);
+    enc_attention_tc_kernel<false><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.hi, T, H, out_hi, out_lo, H * 64, dbg_S, variant);
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }

@@ -40,6 +40,20 @@ struct DecGemmArgs {
   int* counters;                  // [n_tiles], zero on entry, left zero on exit
 };
 
+// Volatile PTX loads: emitted in program order, so a run of them stays a run of independent loads in
+// flight (the compiler otherwise pairs each load with its shared-memory store and serialises the latency).
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {      // read-once weights: no L1 allocation
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+#define MT3_COMPILER_BARRIER() asm volatile("" ::: "memory")
+
 constexpr int kDecBM = 64, kDecBN = 32, kDecKC = 64;     // output tile 64 x 32, K chunk per CTA
 constexpr int kDecBK = kDecKC;                               // (host-side divisibility checks)
 constexpr int kDecTileFloats = kDecBM * kDecBN + kDecBM;   // partial tile + per-row sum of squares
@@ -203,6 +217,166 @@ sgemm_dec_kernel(const DecGemmArgs p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Cluster variant (the default on sm_100a): the S = K/KC CTAs of one 64 x 32 output tile form a
+// thread-block cluster (1, S, 1).  Each CTA computes its K chunk as above, parks the partial tile in
+// its own shared memory, and after one cluster barrier CTA r reduces rows [r*64/S, (r+1)*64/S) across
+// all S CTAs through distributed shared memory IN RANK ORDER (bit-reproducible), applies the fused
+// epilogue and stores.  No global scratch, no __threadfence, no atomic ticket, no second L2 pass.
+// ---------------------------------------------------------------------------------------------
+template <int KC>
+__global__ void __launch_bounds__(128)
+sgemm_dec_cluster_kernel(const DecGemmArgs p) {
+  constexpr int BM = kDecBM, BN = kDecBN, NT = 128, LDA = KC + 4;   // A rows padded: conflict-free 16-byte reads
+  constexpr int WQ = KC * 8 / NT;            // weight 16-byte copies per thread
+  constexpr int AQ = KC * 16 / NT;           // activation 16-byte copies per thread
+  extern __shared__ __align__(16) float dsm[];
+  float* As = dsm;                            // [BM][LDA] activations, row-major; later the partial tile
+  float* Bs = dsm + BM * LDA;                 // [KC][BN]
+  float* Ps = dsm;                            // [BM][BN] partial tile (aliases As after the k-loop)
+  float* Ss = dsm + BM * BN;                  // [BM] partial sums of squares
+
+  const unsigned S = gridDim.y;
+  unsigned rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  const int tid = threadIdx.x;
+  const int tx = tid % 8, ty = tid / 8;       // thread tile: rows ty + 16 i (i < 4), columns tx*4 .. +3
+  const int n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.y * KC;
+
+  // ---- load phase: cp.async (global -> shared, no register staging): every copy of the CTA's 8-16 KB of
+  // weights and 12-32 KB of activations is in flight at once; one wait.  Weights are issued BEFORE the PDL
+  // wait (they do not depend on the previous kernel).
+#pragma unroll
+  for (int i = 0; i < WQ; ++i) {
+    const int idx = tid + i * NT;
+    const int kr = idx >> 3, nq = idx & 7;
+    const bool ok = n0 + nq * 4 < p.N;
+    const float* src = p.W + (long long)(kbeg + kr) * p.ldw + (ok ? n0 + nq * 4 : 0);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(&Bs[kr * BN + nq * 4])), "l"(src),
+                 "r"(ok ? 16 : 0) : "memory");
+  }
+  pdl_wait();
+  pdl_trigger();
+#pragma unroll
+  for (int i = 0; i < AQ; ++i) {
+    const int idx = tid + i * NT;
+    const int row = idx / (KC / 4), kq = idx % (KC / 4);
+    const bool ok = row < p.M;
+    const float* src = p.A + (long long)(ok ? row : 0) * p.lda + kbeg + kq * 4;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(&As[row * LDA + kq * 4])), "l"(src),
+                 "r"(ok ? 16 : 0) : "memory");
+  }
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int k = 0; k < KC; k += 4) {
+    float4 a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(&As[(ty + 16 * i) * LDA + k]);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) b[kk] = *reinterpret_cast<const float4*>(&Bs[(k + kk) * BN + tx * 4]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {                  // k ascending: same summation order as a scalar k-loop
+        acc[i][0] = fmaf(av[kk], b[kk].x, acc[i][0]);
+        acc[i][1] = fmaf(av[kk], b[kk].y, acc[i][1]);
+        acc[i][2] = fmaf(av[kk], b[kk].z, acc[i][2]);
+        acc[i][3] = fmaf(av[kk], b[kk].w, acc[i][3]);
+      }
+    }
+  }
+  // sum of squares of this CTA's K chunk, row tid (sequential over k: deterministic)
+  float ss = 0.f;
+  if (p.norm && tid < BM) {
+#pragma unroll 8
+    for (int k = 0; k < KC; ++k) {
+      const float v = As[tid * LDA + k];
+      ss = fmaf(v, v, ss);
+    }
+  }
+  __syncthreads();                              // everyone is done reading As: recycle it as the partial tile
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    *reinterpret_cast<float4*>(&Ps[(ty + 16 * i) * BN + tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  if (tid < BM) Ss[tid] = ss;
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+
+  // ---- reduce my rows across the cluster (rank order) + fused epilogue ----
+  const int rows_per_rank = BM / (int)S;
+  const int c2 = (tid & 15) * 2;
+  const int n = n0 + c2;
+  for (int rl = tid >> 4; rl < rows_per_rank; rl += 8) {
+    const int m = (int)rank * rows_per_rank + rl;
+    float2 v = make_float2(0.f, 0.f);
+    float sst = 0.f;
+    const uint32_t my_p = tc::smem_u32(&Ps[m * BN + c2]);
+    const uint32_t my_s = tc::smem_u32(&Ss[m]);
+    for (unsigned s = 0; s < S; ++s) {
+      uint32_t rp, rs_addr;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rp) : "r"(my_p), "r"(s));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rs_addr) : "r"(my_s), "r"(s));
+      float2 t;
+      float tss;
+      asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(rp) : "memory");
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(tss) : "r"(rs_addr) : "memory");
+      v.x += t.x; v.y += t.y; sst += tss;
+    }
+    if (m >= p.M || n >= p.N) continue;
+    const float rs = p.norm ? 1.0f / sqrtf(sst / (float)p.K + p.eps) : 1.f;
+    v.x *= rs; v.y *= rs;
+    if (p.epi == EPI_GATED_GELU) {
+      p.C[(long long)m * p.ldc + (n >> 1)] = gelu_tanh(v.x) * v.y;
+      continue;
+    }
+    if (p.epi == EPI_RESIDUAL) {
+      const float2 q = *reinterpret_cast<const float2*>(p.R + (long long)m * p.ldr + n);
+      v.x += q.x; v.y += q.y;
+    }
+    if (n < p.n_split) {
+      *reinterpret_cast<float2*>(p.C + (long long)m * p.ldc + n) = v;
+    } else {
+      const int pos = p.hm_pos ? *p.hm_pos : 0;
+      *reinterpret_cast<float2*>(p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos)) = v;
+    }
+  }
+  // nobody may exit (and release its shared memory) while a peer can still be reading it
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int KC>
+inline int launch_dec_gemm_cluster_kc(const DecGemmArgs& a, int S, cudaStream_t s, bool pdl) {
+  constexpr size_t smem = (size_t)(kDecBM * (KC + 4) + KC * kDecBN) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  MT3_CUDA_CHECK(launch_kernel_cluster(sgemm_dec_cluster_kernel<KC>, dim3(cdiv(a.N, kDecBN), S), dim3(128), smem, s, pdl,
+                                       (unsigned)S, a));
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
+// Returns MT3_ERR_UNSUPPORTED (without launching) when K does not split into 8 chunks of 48/64/128.
+inline int launch_dec_gemm_cluster(const DecGemmArgs& a, cudaStream_t s, bool pdl) {
+  if (a.M > kDecBM || a.N % 4 != 0 || a.lda % 4 != 0 || a.ldw % 4 != 0 || a.n_split % 4 != 0 || a.K % 8 != 0) return MT3_ERR_UNSUPPORTED;
+  switch (a.K / 8) {
+    case 48: return launch_dec_gemm_cluster_kc<48>(a, 8, s, pdl);
+    case 64: return launch_dec_gemm_cluster_kc<64>(a, 8, s, pdl);
+    case 128: return launch_dec_gemm_cluster_kc<128>(a, 8, s, pdl);
+    default: return MT3_ERR_UNSUPPORTED;
+  }
+}
+
 // One CTA per (32-column tile, 64-deep K chunk).
 inline int dec_gemm_splits(int N, int K, int sm_count) {
   (void)N; (void)sm_count;
@@ -226,10 +400,18 @@ constexpr int kAttStages = 6;
 constexpr int kAttTileFloats = kAttKT * 64;
 constexpr int kAttThreads = 160;                 // 4 consumer warps + 1 producer warp
 
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+// K/V rows are read once per step and are 10x the size of L2: stream them with an evict-first policy so
+// that the 104 MB of decoder weights (re-read every step) stay L2-resident.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                :
-               : "r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(tc::smem_u32(bar))
+               : "r"(tc::smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(tc::smem_u32(bar)),
+                 "l"(policy)
                : "memory");
 }
 
@@ -273,6 +455,7 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
     if (len_ptr) pdl_wait();
     pdl_trigger();
     if (lane == 0) {
+      const uint64_t policy = l2_evict_first_policy();
       for (int j = 0; j < 2 * nt; ++j) {
         const int s = j % kAttStages;
         const uint32_t ph = (j / kAttStages) & 1;
@@ -282,7 +465,7 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
         const uint32_t bytes = (uint32_t)keys * 64 * 4;
         const float* src = (j < nt ? kbase : vbase) + (long long)t * kAttTileFloats;
         tc::mbar_arrive_expect_tx(&full[s], bytes);
-        bulk_g2s(ring + s * kAttTileFloats, src, bytes, &full[s]);
+        bulk_g2s(ring + s * kAttTileFloats, src, bytes, &full[s], policy);
       }
     }
     return;

@@ -107,7 +107,7 @@ constexpr int kHalf = 1024;
 constexpr int kScratchF2 = 32 * 33;  // padded 32x32 complex transpose buffer per warp
 
 template <int FRAMES_PER_CTA, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 2)   // <= 128 registers: two CTAs (16 warps) per SM
 logmel2048_kernel(const float* __restrict__ audio, long long audio_stride, int n_samples, int hop,
                   const int* __restrict__ n_valid_frames, int T, const float* __restrict__ window,
                   const float2* __restrict__ tw1024, const float2* __restrict__ rtw,
@@ -309,7 +309,7 @@ extern "C" int mt3_logmel_f32(const mt3_frontend* h, const float* audio, int64_t
   const Frontend* fe = reinterpret_cast<const Frontend*>(h);
   const int hop = fe->cfg.hop_width;
   const int T = (n_samples + hop - 1) / hop;
-  constexpr int F = 16, W = 8;
+  constexpr int F = 32, W = 8;   // 32 frames per CTA (4 per warp): ~100 KB of smem, two CTAs per SM
   const int chunk = (F - 1) * hop + kFft;
   const size_t smem = (size_t)(((chunk + 3) & ~3) + kFft) * sizeof(float) + (size_t)W * kScratchF2 * sizeof(float2);
   MT3_REQUIRE(smem <= 227 * 1024, MT3_ERR_UNSUPPORTED, "mt3_logmel_f32: hop %d needs %zu B of shared memory", hop, smem);

@@ -87,6 +87,7 @@ struct Model {
   TcW t_w_in;
   Act a_x, a_h, a_ao, a_g, a_enc, a_qkv; // tcgen05-path activation buffers (workspace)
   bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between the decode-step kernels
+  bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
   bool tc_attn_ok = true;         // MT3_TC_ATTENTION=0 in the environment forces the exact-fp32 attention kernel
   float* w_in = nullptr;
   std::vector<EncLayer> enc;
@@ -357,7 +358,9 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
       a.C1 = kv + (int64_t)r0 * 2 * m->H * m->L * 64; a.hm_rows_per_b = 1; a.hm_cap = m->L; a.hm_H = m->H; a.hm_pos = pos;
     }
     a.partial = m->dpartial; a.counters = m->dcounters;
-    MT3_TRY(launch_dec_gemm(a, splits, s, m->pdl));
+    int rc = m->dec_cluster ? launch_dec_gemm_cluster(a, s, m->pdl) : MT3_ERR_UNSUPPORTED;
+    if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, splits, s, m->pdl);   // shapes the cluster kernel does not tile
+    MT3_TRY(rc);
   }
   return MT3_OK;
 }
@@ -575,6 +578,8 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
   {
     const char* e_pdl = getenv("MT3_PDL");
     m->pdl = e_pdl && e_pdl[0] == '1';
+    const char* e_clu = getenv("MT3_DEC_CLUSTER");
+    m->dec_cluster = !(e_clu && e_clu[0] == '0');
     const char* e_attn = getenv("MT3_TC_ATTENTION");
     m->tc_attn_ok = !(e_attn && e_attn[0] == '0');
   }

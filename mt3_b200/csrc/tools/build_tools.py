@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-TOOLS = ["gemm_tc_test"]
+TOOLS = ["gemm_tc_test", "attn_tc_test"]
 
 
 def main():

@@ -301,6 +301,18 @@ def test_inference_model_api_end_to_end():
     np.testing.assert_array_equal(dec, O.vocab_decode(toks, 1388))
     with pytest.raises(ValueError):
         inference.InferenceModel('synthetic', 'bogus')
+    # __call__: audio -> segments -> GPU -> tokens -> stitched NoteSequence (notebook :283-308); the stitch of the
+    # GPU's tokens must equal the stitch of the same tokens done segment by segment on the host
+    from mt3_b200 import note_decoding
+    im.outputs_length = 1024
+    preds = im.predict_segments(audio)
+    # segment starts 0 / 2.048 / 4.096 s, rounded DOWN to the 10 ms token grid (notebook :349-351)
+    assert len(preds) == 3 and [round(p['start_time'], 3) for p in preds] == [0.0, 2.04, 4.09]
+    ns = im(audio)
+    assert isinstance(ns, note_decoding.NoteSequence)
+    ref_ns = note_decoding.event_predictions_to_ns(preds, im.codec, im.encoding_spec)['est_ns']
+    assert [(n.pitch, n.start_time, n.end_time, n.program) for n in ns.notes] == \
+           [(n.pitch, n.start_time, n.end_time, n.program) for n in ref_ns.notes]
     ism = inference.InferenceModel('synthetic:1', 'ismir2021', device=DEV, batch_size=1)
     assert ism.inputs_length == 512 and ism.model.config.vocab_size == 1664
     clip = O.sine_mix(32000, 5)                                   # BASELINE config 1: single 2 s clip
