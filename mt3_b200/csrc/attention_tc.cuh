@@ -9,8 +9,10 @@
 //   P = exp(S - rowmax)         one thread per query row reads its row from TMEM (tcgen05.ld), writes P
 //                               (rounded to tf32, unnormalised) into shared memory in the 128B-swizzled
 //                               K-major layout the next MMA reads as its A operand
-//   O[128 q, 64 d] = P . V      V is consumed in its natural [key][d] layout as an MN-major B operand
-//                               (P . Vhi + P . Vlo); 1/rowsum is applied in the epilogue.
+//   O[128 q, 64 d] = P . V      B operand = V^T tiles [64 d x 32 keys] (keys contiguous, K-major), written per head
+//                               by the QKV GEMM epilogue (TcGemmArgs::VT_*): P . Vhi + P . Vlo; 1/rowsum is
+//                               applied in the epilogue.  (An MN-major tf32 B operand returned zeros on sm_100a
+//                               in bring-up, so V is transposed once at its producer instead.)
 // TMEM: S = 256 columns, O = 64 columns (512 allocated).  Shared memory (192 KB):
 //   [ Q hi/lo 64 KB | slot0 64 KB | slot1 64 KB ]   slots hold K chunk c (hi/lo) and later V chunk c (hi/lo);
 //   the Q region is recycled as the P chunk buffer once the S MMAs have completed.
@@ -45,14 +47,17 @@ __device__ __forceinline__ float round_tf32(float x) {
 constexpr int kAtQ = 128;                 // query rows per CTA
 constexpr int kAtKC = 128;                // keys per chunk
 constexpr int kAtSub = 128 * 32 * 4;      // one [128 x 32] fp32 sub-tile = 16 KB
+constexpr int kVSub = 64 * 32 * 4;        // one [64 d x 32 keys] V^T sub-tile = 8 KB
 constexpr int kAtSmem = 3 * 4 * kAtSub + 1024 + 256;
 
 template <bool SPLIT3>
 __global__ void __launch_bounds__(192, 1)
-enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo, int T, int H,
+enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                        const __grid_constant__ CUtensorMap tv_hi, const __grid_constant__ CUtensorMap tv_lo, int T, int H,
                         float* __restrict__ out_hi, float* __restrict__ out_lo, int ldo, float* __restrict__ dbg_S,
                         int variant) {
-  // dbg_S (bring-up tool only): raw S rows [B][H][T][T].  variant: V-descriptor hypothesis under test.
+  // dbg_S (bring-up tool only): raw S rows [B][H][T][T].
+  (void)variant;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                       // Q hi: 2 sub-tiles, Q lo: 2 sub-tiles (64 KB); later the P chunk (4 sub-tiles)
@@ -113,13 +118,15 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
           if (SPLIT3) tc::tma_load_2d(slot[c] + (2 + sub) * kAtSub, &tm_lo, &k_full[c], Q + h * 64 + sub * 32, row0 + c * kAtKC);
         }
       }
-      // V chunks reuse the slots once every S MMA has read K
+      // V^T chunks reuse the slots once every S MMA has read K
       tc::mbar_wait(s_done, 0);
+      // V^T chunk c: 4 sub-tiles [64 d x 32 keys] (8 KB each) hi, then 4 lo
+      const int vrow = (b * H + h) * 64;
       for (int c = 0; c < nchunk; ++c) {
-        tc::mbar_arrive_expect_tx(&v_full[c], 2 * lo_tiles * kSubBytes);
-        for (int sub = 0; sub < 2; ++sub) {
-          tc::tma_load_2d(slot[c] + sub * kAtSub, &tm_hi, &v_full[c], 2 * Q + h * 64 + sub * 32, row0 + c * kAtKC);
-          if (SPLIT3) tc::tma_load_2d(slot[c] + (2 + sub) * kAtSub, &tm_lo, &v_full[c], 2 * Q + h * 64 + sub * 32, row0 + c * kAtKC);
+        tc::mbar_arrive_expect_tx(&v_full[c], 4 * lo_tiles * kVSub);
+        for (int sub = 0; sub < 4; ++sub) {
+          tc::tma_load_2d(slot[c] + sub * kVSub, &tv_hi, &v_full[c], c * kAtKC + sub * 32, vrow);
+          if (SPLIT3) tc::tma_load_2d(slot[c] + (4 + sub) * kVSub, &tv_lo, &v_full[c], c * kAtKC + sub * 32, vrow);
         }
       }
     }
@@ -153,7 +160,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
       }
       tc::mma_commit(s_done);
       // ---- O = P V ----  A = P chunk in the Q region (K-major, 4 sub-tiles of 32 keys), B = V chunk (MN-major)
-      constexpr uint32_t idesc_o = tc::make_idesc(tc::kFmtTF32, 128, 64, 0, 1);
+      constexpr uint32_t idesc_o = tc::make_idesc(tc::kFmtTF32, 128, 64, 0, 0);
       uint32_t acc = 0;
       for (int c = 0; c < nchunk; ++c) {
         tc::mbar_wait(&v_full[c], 0);
@@ -164,15 +171,10 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
 #pragma unroll
         for (int ks = 0; ks < kAtKC / 8; ++ks) {             // 128 keys = 16 k-steps of 8
           const uint64_t a = tc::smem_desc_k_sw128(p_addr + (ks >> 2) * kSubBytes + (ks & 3) * 32);
-          uint64_t bh = smem_desc_mn_sw128(v_addr + ks * 1024, kSubBytes);
-          uint64_t bl = smem_desc_mn_sw128(v_addr + 2 * kSubBytes + ks * 1024, kSubBytes);
-          if (variant == 1) {   // hypothesis: LBO / SBO roles swapped for MN-major
-            bh = (bh & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(kSubBytes >> 4) << 32);
-            bl = (bl & ~((0x3FFFull << 16) | (0x3FFFull << 32))) | ((uint64_t)(1024 >> 4) << 16) | ((uint64_t)(kSubBytes >> 4) << 32);
-          }
-          tc::mma_tf32(tmem_O, a, bh, variant == 2 ? tc::make_idesc(tc::kFmtTF32, 128, 64, 0, 0) : idesc_o, acc);
+          const uint32_t voff = (ks >> 2) * kVSub + (ks & 3) * 32;
+          tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + voff), idesc_o, acc);
           acc = 1u;
-          if (SPLIT3) tc::mma_tf32(tmem_O, a, bl, variant == 2 ? tc::make_idesc(tc::kFmtTF32, 128, 64, 0, 0) : idesc_o, 1u);
+          if (SPLIT3) tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + 4 * kVSub + voff), idesc_o, 1u);
         }
         tc::mma_commit(&pv_done[c]);
       }
@@ -259,9 +261,10 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
   if (warp == 1) tc::tmem_dealloc(tmem_S, 512);
 }
 
-// qkv_hi / qkv_lo: [B*T, 3*H*64]; out: [B*T, H*64] (out_lo optional).  T <= 256, T % 8 == 0.
-inline int launch_enc_attention_tc(const TcOperand& qkv, int B, int T, int H, float* out_hi, float* out_lo, bool split3,
-                                   cudaStream_t s, float* dbg_S = nullptr, int variant = 0) {
+// qkv_hi / qkv_lo: [B*T, 3*H*64] (q and k are read); vt: V^T [B*H*64, T] (box rows 64); out: [B*T, H*64]
+// (out_lo optional).  T <= 256, T % 8 == 0.
+inline int launch_enc_attention_tc(const TcOperand& qkv, const TcOperand& vt, int B, int T, int H, float* out_hi, float* out_lo,
+                                   bool split3, cudaStream_t s, float* dbg_S = nullptr, int variant = 0) {
   MT3_REQUIRE(T <= 2 * kAtKC && T % 8 == 0, MT3_ERR_UNSUPPORTED, "tc attention: T=%d (needs T <= 256, multiple of 8)", T);
   MT3_REQUIRE(!split3 || qkv.has_lo, MT3_ERR_BAD_ARG, "tc attention: TF32X3 needs hi/lo qkv");
   static bool attr_done = false;
@@ -272,9 +275,9 @@ inline int launch_enc_attention_tc(const TcOperand& qkv, int B, int T, int H, fl
   }
   dim3 grid(cdiv(T, kAtQ), H, B);
   if (split3)
-    enc_attention_tc_kernel<true><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.lo, T, H, out_hi, out_lo, H * 64, dbg_S, variant);
+    enc_attention_tc_kernel<true><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.lo, vt.hi, vt.lo, T, H, out_hi, out_lo, H * 64, dbg_S, variant);
   else
-    enc_attention_tc_kernel<false><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.hi, T, H, out_hi, out_lo, H * 64, dbg_S, variant);
+    enc_attention_tc_kernel<false><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.hi, vt.hi, vt.hi, T, H, out_hi, out_lo, H * 64, dbg_S, variant);
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }

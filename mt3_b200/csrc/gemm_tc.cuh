@@ -35,6 +35,10 @@ struct TcGemmArgs {
   const float* pe; int pe_T; int pe_ld;
   float* C_hi; float* C_lo; int ldc;       // C_lo != null: write hi/lo split of the result
   int n_split; float* C1; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // head-major K/V store, see kv_dest()
+  // Transposed per-head store for columns >= vt_col0 (the V third of a fused QKV projection), enabled by VT_hi:
+  // vt[((b*H + h)*64 + d)*vt_T + t] with row m = b*vt_T + t, column = vt_col0 + h*64 + d.  This is the K-major
+  // (keys contiguous) operand the tcgen05 attention kernel reads for P.V.
+  float* VT_hi; float* VT_lo; int vt_col0; int vt_T; int vt_H;
 };
 
 constexpr int kTcBM = 128, kTcBN = 128, kTcBK = 32;
@@ -152,6 +156,23 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * rs;
+      if (p.VT_hi && n >= p.vt_col0) {        // lanes are consecutive rows (t): each store below is one coalesced line
+        const int bb = m / p.vt_T, tt = m % p.vt_T;
+        const int hh = (n - p.vt_col0) >> 6, d0 = (n - p.vt_col0) & 63;
+        const long long base = (((long long)bb * p.vt_H + hh) * 64 + d0) * p.vt_T + tt;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (p.VT_lo) {
+            float hi, lo;
+            split_tf32(v[j], hi, lo);
+            p.VT_hi[base + (long long)j * p.vt_T] = hi;
+            p.VT_lo[base + (long long)j * p.vt_T] = lo;
+          } else {
+            p.VT_hi[base + (long long)j * p.vt_T] = v[j];
+          }
+        }
+        continue;
+      }
       if (p.epi == EPI_GATED_GELU) {
         float* ch = p.C_hi + (long long)m * p.ldc + (n >> 1);
         float* cl = p.C_lo ? p.C_lo + (long long)m * p.ldc + (n >> 1) : nullptr;
@@ -259,11 +280,12 @@ struct TcOperand {           // an [rows, K] K-major operand, optionally hi/lo s
   bool has_lo = false;
 };
 
-inline int make_operand(TcOperand* op, const float* hi, const float* lo, uint64_t rows, uint64_t K, uint64_t ld) {
-  int r = make_tmap_2d(&op->hi, hi, rows, K, ld, 128);
+inline int make_operand(TcOperand* op, const float* hi, const float* lo, uint64_t rows, uint64_t K, uint64_t ld,
+                        uint32_t box_rows = 128) {
+  int r = make_tmap_2d(&op->hi, hi, rows, K, ld, box_rows);
   if (r != MT3_OK) return r;
   op->has_lo = lo != nullptr;
-  if (lo) return make_tmap_2d(&op->lo, lo, rows, K, ld, 128);
+  if (lo) return make_tmap_2d(&op->lo, lo, rows, K, ld, box_rows);
   op->lo = op->hi;
   return MT3_OK;
 }

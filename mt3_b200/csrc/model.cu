@@ -85,7 +85,7 @@ struct Model {
   float* slab_tc = nullptr;       // K-major (and hi/lo) copies for the tcgen05 path
   bool tc = false, split3 = false;
   TcW t_w_in;
-  Act a_x, a_h, a_ao, a_g, a_enc, a_qkv; // tcgen05-path activation buffers (workspace)
+  Act a_x, a_h, a_ao, a_g, a_enc, a_qkv, a_vt; // tcgen05-path activation buffers (workspace); a_vt = per-head V^T
   bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between the decode-step kernels
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
   bool tc_attn_ok = true;         // MT3_TC_ATTENTION=0 in the environment forces the exact-fp32 attention kernel
@@ -225,10 +225,13 @@ static int encode_tc_impl(Model* m, const float* x, float* encoded, cudaStream_t
       // qkv goes out as a tf32 hi/lo pair when the tcgen05 attention kernel consumes it
       TcGemmArgs a = tc_args(M, 3 * Q, D, m->qkv, tc_attn ? m->a_qkv.lo : nullptr, 3 * Q);
       a.row_scale = m->rstd;
+      if (tc_attn) {   // the V third goes out transposed per head: the K-major operand of P.V
+        a.VT_hi = m->a_vt.hi; a.VT_lo = m->a_vt.lo; a.vt_col0 = 2 * Q; a.vt_T = m->T; a.vt_H = m->H;
+      }
       MT3_TRY(launch_tc_gemm(m->a_h.op, w.t_wqkv.op, a, m->split3, s));
     }
     if (tc_attn) {
-      MT3_TRY(launch_enc_attention_tc(m->a_qkv.op, m->B, m->T, m->H, m->a_ao.hi, m->a_ao.lo, m->split3, s));
+      MT3_TRY(launch_enc_attention_tc(m->a_qkv.op, m->a_vt.op, m->B, m->T, m->H, m->a_ao.hi, m->a_ao.lo, m->split3, s));
     } else {
       enc_attention_kernel<<<dim3(cdiv(m->T, 32), m->H, m->B), 256, attn_smem, s>>>(m->qkv, 3 * Q, m->T, m->H, m->a_ao.hi,
                                                                                      m->a_ao.lo, Q);
@@ -633,7 +636,7 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
 
 namespace {
 struct WsLayout {
-  int64_t x_hi, x_lo, h_lo, ao_lo, g_lo, enc_hi, enc_lo, qkv_lo;
+  int64_t x_hi, x_lo, h_lo, ao_lo, g_lo, enc_hi, enc_lo, qkv_lo, vt_hi, vt_lo;
   int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, total;
 };
 WsLayout ws_layout(const Model* m, int B, int T) {
@@ -650,6 +653,8 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   w.enc_hi = take(s3 ? M * D * 4 : 0);
   w.enc_lo = take(s3 ? M * D * 4 : 0);
   w.qkv_lo = take(s3 ? M * 3 * Q * 4 : 0);
+  w.vt_hi = take(m->tc ? M * Q * 4 : 0);
+  w.vt_lo = take(s3 ? M * Q * 4 : 0);
   w.h = take(M * D * 4);
   w.rstd = take(M * 4);
   w.qkv = take(M * 3 * Q * 4);
@@ -716,6 +721,9 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
     MT3_TRY(make_operand(&m->a_g.op, m->a_g.hi, m->a_g.lo, M, m->F, m->F));
     m->a_qkv.hi = m->qkv; m->a_qkv.lo = s3 ? (float*)(b + w.qkv_lo) : nullptr;
     MT3_TRY(make_operand(&m->a_qkv.op, m->a_qkv.hi, m->a_qkv.lo, M, 3 * m->Q, 3 * m->Q));
+    m->a_vt.hi = (float*)(b + w.vt_hi); m->a_vt.lo = s3 ? (float*)(b + w.vt_lo) : nullptr;
+    if (input_length % 4 == 0)   // TMA row pitch must be a multiple of 16 bytes; otherwise the SIMT attention kernel runs
+      MT3_TRY(make_operand(&m->a_vt.op, m->a_vt.hi, m->a_vt.lo, (uint64_t)batch * m->H * 64, input_length, input_length, 64));
   }
   return MT3_OK;
 }
@@ -831,7 +839,7 @@ extern "C" int mt3_debug_launch(mt3_model* h, int32_t kind, int32_t pos, int32_t
       }
       case MT3_K_ENC_ATTN: {
         if (m->tc && m->tc_attn_ok && T <= 2 * kAtKC && T % 8 == 0) {
-          MT3_TRY(launch_enc_attention_tc(m->a_qkv.op, B, T, m->H, m->a_ao.hi, m->a_ao.lo, m->split3, s));
+          MT3_TRY(launch_enc_attention_tc(m->a_qkv.op, m->a_vt.op, B, T, m->H, m->a_ao.hi, m->a_ao.lo, m->split3, s));
           break;
         }
         MT3_TRY(set_attr_once());
