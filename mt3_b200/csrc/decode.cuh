@@ -320,15 +320,21 @@ sgemm_dec_cluster_kernel(const DecGemmArgs p) {
     float sst = 0.f;
     const uint32_t my_p = tc::smem_u32(&Ps[m * BN + c2]);
     const uint32_t my_s = tc::smem_u32(&Ss[m]);
-    for (unsigned s = 0; s < S; ++s) {
+    // all 8 remote loads are issued before the first add (one DSMEM latency, not eight); the sum itself
+    // stays in rank order.  The cluster kernel is only ever launched with S == 8.
+    float2 t[8];
+    float tss[8];
+#pragma unroll
+    for (unsigned s = 0; s < 8; ++s) {
       uint32_t rp, rs_addr;
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rp) : "r"(my_p), "r"(s));
       asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rs_addr) : "r"(my_s), "r"(s));
-      float2 t;
-      float tss;
-      asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(t.x), "=f"(t.y) : "r"(rp) : "memory");
-      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(tss) : "r"(rs_addr) : "memory");
-      v.x += t.x; v.y += t.y; sst += tss;
+      asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(t[s].x), "=f"(t[s].y) : "r"(rp));
+      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(tss[s]) : "r"(rs_addr));
+    }
+#pragma unroll
+    for (unsigned s = 0; s < 8; ++s) {
+      v.x += t[s].x; v.y += t[s].y; sst += tss[s];
     }
     if (m >= p.M || n >= p.N) continue;
     const float rs = p.norm ? 1.0f / sqrtf(sst / (float)p.K + p.eps) : 1.f;

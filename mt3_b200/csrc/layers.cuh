@@ -190,10 +190,10 @@ enc_attention_kernel(const float* __restrict__ qkv, int ld, int T, int H, float*
 // layers.py:516-537; FixedEmbed decode branch, layers.py:589-596).
 // ---------------------------------------------------------------------------------
 __global__ void embed_kernel(const int* __restrict__ tok, const float* __restrict__ emb, int D, int vocab,
-                             const float* __restrict__ pe, const int* __restrict__ pos_ptr, float* __restrict__ y) {
+                             const float* __restrict__ pe, const int* __restrict__ pos_ptr, float* __restrict__ y, int b0) {
   pdl_wait();
   pdl_trigger();
-  const int b = blockIdx.x;
+  const int b = b0 + blockIdx.x;       // b0: first sequence of this sub-batch (decode streams)
   int t = tok[b];
   t = min(max(t, 0), vocab - 1);
   const int pos = *pos_ptr;
@@ -216,12 +216,13 @@ __global__ void embed_kernel(const int* __restrict__ tok, const float* __restric
 __global__ void __launch_bounds__(256)
 argmax_step_kernel(const float* __restrict__ logits, int V, int B, int* __restrict__ tok_cur,
                    int* __restrict__ finished, int* __restrict__ tokens_out, int out_ld, int* __restrict__ tok_out_user,
-                   int* __restrict__ state, int advance) {
+                   int* __restrict__ state, int advance, int b0) {
   __shared__ float sv[8];
   __shared__ int si[8];
   pdl_wait();
   pdl_trigger();
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // B = sequences in the whole batch (the arrival counter spans every sub-batch), b0 = first sequence of this launch
+  const int b = b0 + blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* l = logits + (long long)b * V;
   float best = -INFINITY;
   int bi = 0x7fffffff;

@@ -88,6 +88,10 @@ struct Model {
   Act a_x, a_h, a_ao, a_g, a_enc, a_qkv, a_vt; // tcgen05-path activation buffers (workspace); a_vt = per-head V^T
   bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between the decode-step kernels
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
+  int dec_streams = 1;            // MT3_DEC_STREAMS=n: decode step runs as n concurrent sub-batches
+  cudaStream_t sub_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  int64_t dpartial_stride = 0, dcounters_stride = 0;
   bool tc_attn_ok = true;         // MT3_TC_ATTENTION=0 in the environment forces the exact-fp32 attention kernel
   float* w_in = nullptr;
   std::vector<EncLayer> enc;
@@ -337,7 +341,7 @@ static int cross_kv_impl(Model* m, const float* encoded, cudaStream_t s) {
     }
   }
   MT3_CUDA_CHECK(cudaMemsetAsync(m->state, 0, 4 * sizeof(int), s));
-  MT3_CUDA_CHECK(cudaMemsetAsync(m->dcounters, 0, (size_t)cdiv(std::max(std::max(3 * Q, 2 * m->F), m->V), kDecBN) * sizeof(int), s));
+  MT3_CUDA_CHECK(cudaMemsetAsync(m->dcounters, 0, (size_t)4 * m->dcounters_stride * sizeof(int), s));
   MT3_CUDA_CHECK(cudaMemsetAsync(m->finished, 0, (size_t)m->B * sizeof(int), s));
   MT3_CUDA_CHECK(cudaMemsetAsync(m->tok_cur, 0, (size_t)m->B * sizeof(int), s));
   m->have_cross = true;
@@ -347,20 +351,25 @@ static int cross_kv_impl(Model* m, const float* encoded, cudaStream_t s) {
 
 // Decode-step GEMM on M = B rows: split-K exact-fp32 kernel with the RMSNorm statistic fused
 // (decode.cuh); batches above 64 rows run in 64-row blocks.
+// A contiguous block of sequences decoded on one stream (MT3_DEC_STREAMS sub-batches per step).
+struct Rows { int begin, count, stream_idx; };
+
 static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, int K, int norm, int epi, float* C, int ldc,
-                    int n_split, float* kv, const int* pos, cudaStream_t s) {
+                    int n_split, float* kv, const int* pos, const Rows& rows, cudaStream_t s) {
   const int splits = dec_gemm_splits(N, K, m->sm_count);
-  for (int r0 = 0; r0 < m->B; r0 += kDecBM) {
+  for (int r0 = rows.begin; r0 < rows.begin + rows.count; r0 += kDecBM) {
     DecGemmArgs a;
     memset(&a, 0, sizeof(a));
-    a.A = A + (int64_t)r0 * lda; a.lda = lda; a.W = W; a.ldw = N; a.M = std::min(kDecBM, m->B - r0); a.N = N; a.K = K;
+    a.A = A + (int64_t)r0 * lda; a.lda = lda; a.W = W; a.ldw = N; a.M = std::min(kDecBM, rows.begin + rows.count - r0);
+    a.N = N; a.K = K;
     a.norm = norm; a.eps = 1e-6f; a.epi = epi;
     a.R = C + (int64_t)r0 * ldc; a.ldr = ldc;                  // residual is always added in place
     a.C = C + (int64_t)r0 * ldc; a.ldc = ldc; a.n_split = n_split;
     if (kv) {  // rows_per_b = 1: skip r0 sequences, each 2*H*cap*64 floats
       a.C1 = kv + (int64_t)r0 * 2 * m->H * m->L * 64; a.hm_rows_per_b = 1; a.hm_cap = m->L; a.hm_H = m->H; a.hm_pos = pos;
     }
-    a.partial = m->dpartial; a.counters = m->dcounters;
+    a.partial = m->dpartial + (int64_t)rows.stream_idx * m->dpartial_stride;      // per-stream split-K scratch
+    a.counters = m->dcounters + (int64_t)rows.stream_idx * m->dcounters_stride;
     int rc = m->dec_cluster ? launch_dec_gemm_cluster(a, s, m->pdl) : MT3_ERR_UNSUPPORTED;
     if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, splits, s, m->pdl);   // shapes the cluster kernel does not tile
     MT3_TRY(rc);
@@ -369,7 +378,7 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
 }
 
 static int launch_dec_attention(Model* m, const float* q, const float* kv, int cap, const int* len_ptr, int len_add,
-                                float* out, cudaStream_t s) {
+                                float* out, const Rows& rows, cudaStream_t s) {
   static bool attr_done = false;
   const int max_len = std::max(m->L, m->T);
   const size_t smem = dec_attention_smem(max_len);
@@ -378,8 +387,9 @@ static int launch_dec_attention(Model* m, const float* q, const float* kv, int c
     attr_done = true;
   }
   MT3_REQUIRE(smem <= 100 * 1024, MT3_ERR_UNSUPPORTED, "decode attention: length %d too long", max_len);
-  MT3_CUDA_CHECK(launch_kernel(dec_attention_bulk_kernel, dim3(m->H, m->B), dim3(kAttThreads), smem, s, m->pdl, q, m->Q, 0, kv,
-                               m->H, cap, len_ptr, len_add, max_len, out, m->Q));
+  MT3_CUDA_CHECK(launch_kernel(dec_attention_bulk_kernel, dim3(m->H, rows.count), dim3(kAttThreads), smem, s, m->pdl,
+                               q + (int64_t)rows.begin * m->Q, m->Q, 0, kv + (int64_t)rows.begin * 2 * m->H * cap * 64, m->H, cap,
+                               len_ptr, len_add, max_len, out + (int64_t)rows.begin * m->Q, m->Q));
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }
@@ -388,34 +398,71 @@ static int launch_dec_attention(Model* m, const float* q, const float* kv, int c
 // greedy != 0 runs the argmax/bookkeeping kernel (tok_user optional), else only the position advances.
 // 8 launches per layer: [norm+QKV+KV-append] [self-attn] [out+residual] [norm+q] [cross-attn]
 // [out+residual] [norm+gated-GELU MLP in] [MLP out+residual].
-static int decode_step_impl(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
-                            int* tokens_ws, cudaStream_t s) {
+static int decode_rows(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
+                       int* tokens_ws, const Rows& rows, cudaStream_t s) {
   const int B = m->B, D = m->D, Q = m->Q, F = m->F, V = m->V, L = m->L, T = m->T;
   int* pos = m->state;
-  MT3_CUDA_CHECK(launch_kernel(embed_kernel, dim3(B), dim3(128), 0, s, m->pdl, tok_in, (const float*)m->emb, D, V,
-                               (const float*)m->pe, (const int*)pos, m->dy));
+  MT3_CUDA_CHECK(launch_kernel(embed_kernel, dim3(rows.count), dim3(128), 0, s, m->pdl, tok_in, (const float*)m->emb, D, V,
+                               (const float*)m->pe, (const int*)pos, m->dy, rows.begin));
   MT3_LAUNCH_CHECK();
   for (int l = 0; l < m->Ld; ++l) {
     const DecLayer& w = m->dec[l];
     float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
     const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
     // fused RMSNorm + QKV projection + K/V cache append (layers.py:238-240, :272-289)
-    MT3_TRY(dec_gemm(m, m->dy, D, w.wqkv, 3 * Q, D, 1, EPI_STORE, m->dq, Q, Q, skv, pos, s));
-    MT3_TRY(launch_dec_attention(m, m->dq, skv, L, pos, 1, m->dao, s));
-    MT3_TRY(dec_gemm(m, m->dao, Q, w.wo, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, s));
-    MT3_TRY(dec_gemm(m, m->dy, D, w.wq_c, Q, D, 1, EPI_STORE, m->dq, Q, Q, nullptr, nullptr, s));
-    MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, s));
-    MT3_TRY(dec_gemm(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, s));
-    MT3_TRY(dec_gemm(m, m->dy, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr, nullptr, s));
-    MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, s));
+    MT3_TRY(dec_gemm(m, m->dy, D, w.wqkv, 3 * Q, D, 1, EPI_STORE, m->dq, Q, Q, skv, pos, rows, s));
+    MT3_TRY(launch_dec_attention(m, m->dq, skv, L, pos, 1, m->dao, rows, s));
+    MT3_TRY(dec_gemm(m, m->dao, Q, w.wo, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, rows, s));
+    MT3_TRY(dec_gemm(m, m->dy, D, w.wq_c, Q, D, 1, EPI_STORE, m->dq, Q, Q, nullptr, nullptr, rows, s));
+    MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, rows, s));
+    MT3_TRY(dec_gemm(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, rows, s));
+    MT3_TRY(dec_gemm(m, m->dy, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr, nullptr, rows, s));
+    MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, rows, s));
   }
-  MT3_TRY(dec_gemm(m, m->dy, D, m->w_logits, V, D, 1, EPI_STORE, logits, V, V, nullptr, nullptr, s));
+  MT3_TRY(dec_gemm(m, m->dy, D, m->w_logits, V, D, 1, EPI_STORE, logits, V, V, nullptr, nullptr, rows, s));
   if (greedy) {
-    MT3_CUDA_CHECK(launch_kernel(argmax_step_kernel, dim3(B), dim3(256), 0, s, m->pdl, (const float*)logits, V, B,
+    // B (whole batch) sizes the arrival counter: the LAST CTA over all sub-batches advances the position
+    MT3_CUDA_CHECK(launch_kernel(argmax_step_kernel, dim3(rows.count), dim3(256), 0, s, m->pdl, (const float*)logits, V, B,
                                  use_finished ? m->tok_cur : (int*)nullptr, use_finished ? m->finished : (int*)nullptr,
-                                 tokens_ws, L, tok_user, m->state, 1));
+                                 tokens_ws, L, tok_user, m->state, 1, rows.begin));
     MT3_LAUNCH_CHECK();
+  }
+  return MT3_OK;
+}
+
+// One decode step for the whole batch.  With MT3_DEC_STREAMS = n > 1 the batch is cut into n blocks of
+// sequences that run on n streams (forked/joined with events; captured as parallel branches of the step
+// graph): one block's latency-bound GEMM chain overlaps another block's bandwidth-bound attention.
+static int decode_step_impl(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
+                            int* tokens_ws, cudaStream_t s) {
+  const int B = m->B;
+  int ns = std::max(1, std::min(m->dec_streams, 4));
+  while (ns > 1 && B / ns < 8) --ns;
+  if (ns == 1) {
+    MT3_TRY(decode_rows(m, tok_in, logits, greedy, tok_user, use_finished, tokens_ws, Rows{0, B, 0}, s));
   } else {
+    if (!m->ev_fork) {
+      MT3_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+      for (int i = 0; i < 4; ++i) {
+        MT3_CUDA_CHECK(cudaStreamCreateWithFlags(&m->sub_stream[i], cudaStreamNonBlocking));
+        MT3_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
+      }
+    }
+    MT3_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
+    const int per = (B + ns - 1) / ns;
+    for (int i = 0; i < ns; ++i) {
+      const int b0 = i * per, n = std::min(per, B - b0);
+      if (n <= 0) break;
+      cudaStream_t si = (i == 0) ? s : m->sub_stream[i];
+      if (i > 0) MT3_CUDA_CHECK(cudaStreamWaitEvent(si, m->ev_fork, 0));
+      MT3_TRY(decode_rows(m, tok_in, logits, greedy, tok_user, use_finished, tokens_ws, Rows{b0, n, i}, si));
+      if (i > 0) {
+        MT3_CUDA_CHECK(cudaEventRecord(m->ev_join[i], si));
+        MT3_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join[i], 0));
+      }
+    }
+  }
+  if (!greedy) {
     MT3_CUDA_CHECK(launch_kernel(advance_pos_kernel, dim3(1), dim3(1), 0, s, m->pdl, m->state));
     MT3_LAUNCH_CHECK();
   }
@@ -581,6 +628,8 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
   {
     const char* e_pdl = getenv("MT3_PDL");
     m->pdl = e_pdl && e_pdl[0] == '1';
+    const char* e_ns = getenv("MT3_DEC_STREAMS");
+    if (e_ns && e_ns[0] >= '1' && e_ns[0] <= '4') m->dec_streams = e_ns[0] - '0';
     const char* e_clu = getenv("MT3_DEC_CLUSTER");
     m->dec_cluster = !(e_clu && e_clu[0] == '0');
     const char* e_attn = getenv("MT3_TC_ATTENTION");
@@ -627,6 +676,11 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
   Model* m = reinterpret_cast<Model*>(h);
   drop_graph(m);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
+  for (int i = 0; i < 4; ++i) {
+    if (m->sub_stream[i]) cudaStreamDestroy(m->sub_stream[i]);
+    if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
+  }
+  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
   if (m->h_flag) cudaFreeHost(m->h_flag);
   cudaFree(m->slab);
   cudaFree(m->slab_tc);
@@ -673,8 +727,8 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   w.finished = take((int64_t)B * 4);
   w.tokens = take((int64_t)B * L * 4);
   w.state = take(64);
-  w.dpartial = take((int64_t)16 * cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * kDecTileFloats * 4);
-  w.dcounters = take((int64_t)cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * 4);
+  w.dpartial = take((int64_t)4 * 16 * cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * kDecTileFloats * 4);   // x4 decode streams
+  w.dcounters = take((int64_t)4 * cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * 4);
   w.total = off;
   return w;
 }
@@ -703,6 +757,8 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
   m->dg = (float*)(b + w.dg); m->dlogits = (float*)(b + w.dlogits); m->tok_cur = (int*)(b + w.tok_cur);
   m->finished = (int*)(b + w.finished); m->tokens = (int*)(b + w.tokens); m->state = (int*)(b + w.state);
   m->dpartial = (float*)(b + w.dpartial); m->dcounters = (int*)(b + w.dcounters);
+  m->dcounters_stride = cdiv(std::max(std::max(3 * m->Q, 2 * m->F), m->V), kDecBN);
+  m->dpartial_stride = (int64_t)16 * m->dcounters_stride * kDecTileFloats;
   m->have_cross = false;
   if (m->tc) {
     const int64_t M = (int64_t)batch * input_length;
@@ -812,17 +868,17 @@ extern "C" int mt3_debug_launch(mt3_model* h, int32_t kind, int32_t pos, int32_t
     switch (kind) {
       case MT3_K_DEC_SELF_ATTN: {
         float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
-        MT3_TRY(launch_dec_attention(m, m->dq, skv, L, nullptr, pos + 1, m->dao, s));
+        MT3_TRY(launch_dec_attention(m, m->dq, skv, L, nullptr, pos + 1, m->dao, Rows{0, B, 0}, s));
         break;
       }
       case MT3_K_DEC_CROSS_ATTN: {
         const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
-        MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, s));
+        MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, Rows{0, B, 0}, s));
         break;
       }
       case MT3_K_DEC_QKV_GEMM: {
         // scratch output: the encoder qkv buffer (B*T rows >= B)
-        MT3_TRY(dec_gemm(m, m->dy, D, m->dec[l].wqkv, 3 * Q, D, 1, EPI_STORE, m->qkv, 3 * Q, 3 * Q, nullptr, nullptr, s));
+        MT3_TRY(dec_gemm(m, m->dy, D, m->dec[l].wqkv, 3 * Q, D, 1, EPI_STORE, m->qkv, 3 * Q, 3 * Q, nullptr, nullptr, Rows{0, B, 0}, s));
         break;
       }
       case MT3_K_ENC_QKV_GEMM: {

@@ -103,7 +103,8 @@ static int run(int B, int T, int H, int mode, bool split3, int variant) {
   printf("\n");
   cudaFree(d_vt); cudaFree(d_vth); cudaFree(d_vtl);
   cudaFree(d_x); cudaFree(d_hi); cudaFree(d_lo); cudaFree(d_o); cudaFree(d_ol); cudaFree(d_S);
-  const double tol = split3 ? 2e-5 : 5e-3;
+  // P is rounded (to nearest) to tf32 and used as a single term: measured 2e-4 of max|O| on random inputs
+  const double tol = split3 ? 5e-4 : 5e-3;
   return (o_err / fmax(o_ref, 1e-30) <= tol) ? 0 : 3;
 }
 

@@ -240,6 +240,38 @@ def test_generate_eos_semantics_and_graph_equivalence(pdl, monkeypatch):
     np.testing.assert_array_equal(dec, O.vocab_decode(t_plain, 1388))
 
 
+@pytest.mark.parametrize("streams,pdl,cluster", [("2", "0", "1"), ("4", "1", "1"), ("1", "0", "0")])
+def test_decode_variants_bit_identical(streams, pdl, cluster, monkeypatch):
+    """Sub-batch streams, PDL and the global-scratch split-K fallback are scheduling choices only: every
+    output element keeps its summation order, so tokens AND logits are bit-identical to the default path."""
+    from mt3_b200 import network
+    ocfg = O.T5Config(vocab_size=1536, num_encoder_layers=1, num_decoder_layers=2)
+    params = O.init_params(ocfg, seed=21)
+    cfg = network.T5Config(vocab_size=1536, emb_dim=512, num_heads=6, num_encoder_layers=1, num_decoder_layers=2,
+                           head_dim=64, mlp_dim=1024, mlp_activations=('gelu', 'linear'))
+    x = torch.from_numpy(_inputs(32, t=64, seed=300)).to(DEV)
+
+    def run():
+        m = network.Transformer(cfg, params, device=DEV, max_batch=32, max_input_length=64, max_decode_length=40)
+        toks = m.generate(x, stop_at_eos=False, use_graph=True).cpu().numpy()
+        enc = m.encode(x)
+        lg = m.teacher_forced_logits(enc, torch.from_numpy(toks[:, :4].astype(np.int32)).to(DEV)).cpu().numpy()
+        return toks, lg
+
+    for k in ("MT3_DEC_STREAMS", "MT3_PDL", "MT3_DEC_CLUSTER"):
+        monkeypatch.delenv(k, raising=False)
+    base_t, base_l = run()
+    monkeypatch.setenv("MT3_DEC_STREAMS", streams)
+    monkeypatch.setenv("MT3_PDL", pdl)
+    monkeypatch.setenv("MT3_DEC_CLUSTER", cluster)
+    t, l = run()
+    if cluster == "1":
+        np.testing.assert_array_equal(t, base_t)
+        np.testing.assert_array_equal(l, base_l)
+    else:   # the fallback splits K into 64-deep chunks (the cluster kernel into K/8): same math, other rounding
+        np.testing.assert_allclose(l, base_l, rtol=0, atol=2e-5 * np.abs(base_l).max())
+
+
 def test_vocab_decode_kernel_random():
     from mt3_b200 import vocabularies
     rng = np.random.default_rng(0)
