@@ -19,6 +19,7 @@
 #include "gemm_tc.cuh"
 #include "attention_tc.cuh"
 #include "decode.cuh"
+#include "decode_mega.cuh"
 #include "layers.cuh"
 
 namespace mt3 {
@@ -89,6 +90,9 @@ struct Model {
   bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between the decode-step kernels
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
   int dec_streams = 1;            // MT3_DEC_STREAMS=n: decode step runs as n concurrent sub-batches
+  bool mega = false;              // MT3_DEC_MEGA=1: the whole decode step as one persistent kernel (decode_mega.cuh)
+  MegaPhase* mega_prog = nullptr; int64_t mega_prog_bytes = 0; unsigned* mega_bar = nullptr;
+  int mega_phases = 0, mega_clusters = 0; bool mega_ready = false;
   cudaStream_t sub_stream[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t dpartial_stride = 0, dcounters_stride = 0;
@@ -469,6 +473,101 @@ static int decode_step_impl(Model* m, const int* tok_in, float* logits, int gree
   return MT3_OK;
 }
 
+// ---- the decode step as one persistent kernel (decode_mega.cuh); generate path, B <= 64 ------------------
+static DecGemmArgs mega_gemm_args(Model* m, const float* A, int lda, const float* W, int N, int K, int norm, int epi,
+                                  float* C, int ldc, int n_split, float* kv) {
+  DecGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.A = A; a.lda = lda; a.W = W; a.ldw = N; a.M = m->B; a.N = N; a.K = K; a.norm = norm; a.eps = 1e-6f; a.epi = epi;
+  a.R = C; a.ldr = ldc; a.C = C; a.ldc = ldc; a.n_split = n_split;
+  if (kv) { a.C1 = kv; a.hm_rows_per_b = 1; a.hm_cap = m->L; a.hm_H = m->H; a.hm_pos = m->state; }
+  return a;
+}
+
+static bool mega_supported(const Model* m) {
+  auto kc_ok = [](int K) { return K % 8 == 0 && (K / 8 == 48 || K / 8 == 64 || K / 8 == 128); };
+  return m->B <= kDecBM && kc_ok(m->D) && kc_ok(m->Q) && kc_ok(m->F);
+}
+
+static int build_mega_program(Model* m) {
+  std::vector<MegaPhase> prog;
+  auto gemm_phase = [&](const DecGemmArgs& g) {
+    MegaPhase p;
+    memset(&p, 0, sizeof(p));
+    p.type = PH_GEMM; p.g = g; p.kc = g.K / 8;
+    prog.push_back(p);
+  };
+  auto attn_phase = [&](const float* kv, int cap, const int* len_ptr, int len_add) {
+    MegaPhase p;
+    memset(&p, 0, sizeof(p));
+    p.type = PH_ATTN; p.q = m->dq; p.kv = kv; p.cap = cap; p.len_ptr = len_ptr; p.len_add = len_add; p.out = m->dao;
+    prog.push_back(p);
+  };
+  const int B = m->B, D = m->D, Q = m->Q, F = m->F, V = m->V, L = m->L, T = m->T;
+  MegaPhase e;
+  memset(&e, 0, sizeof(e));
+  e.type = PH_EMBED;
+  prog.push_back(e);
+  for (int l = 0; l < m->Ld; ++l) {
+    const DecLayer& w = m->dec[l];
+    float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
+    const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
+    gemm_phase(mega_gemm_args(m, m->dy, D, w.wqkv, 3 * Q, D, 1, EPI_STORE, m->dq, Q, Q, skv));
+    attn_phase(skv, L, m->state, 1);
+    gemm_phase(mega_gemm_args(m, m->dao, Q, w.wo, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr));
+    gemm_phase(mega_gemm_args(m, m->dy, D, w.wq_c, Q, D, 1, EPI_STORE, m->dq, Q, Q, nullptr));
+    attn_phase(ckv, T, nullptr, T);
+    gemm_phase(mega_gemm_args(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr));
+    gemm_phase(mega_gemm_args(m, m->dy, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr));
+    gemm_phase(mega_gemm_args(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, m->dy, D, D, nullptr));
+  }
+  gemm_phase(mega_gemm_args(m, m->dy, D, m->w_logits, V, D, 1, EPI_STORE, m->dlogits, V, V, nullptr));
+  e.type = PH_ARGMAX;
+  prog.push_back(e);
+  MT3_REQUIRE((int64_t)prog.size() * (int64_t)sizeof(MegaPhase) <= m->mega_prog_bytes, MT3_ERR_WORKSPACE,
+              "mega program (%zu phases) does not fit its workspace slot", prog.size());
+  MT3_CUDA_CHECK(cudaMemcpy(m->mega_prog, prog.data(), prog.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+  MT3_CUDA_CHECK(cudaMemset(m->mega_bar, 0, 64));
+  m->mega_phases = (int)prog.size();
+  // co-resident clusters of 8 CTAs: the grid barrier needs every CTA on an SM at the same time
+  const size_t smem = mega_smem_bytes(std::max(L, T));
+  MT3_CUDA_CHECK(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(8 * 64); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int max_clusters = 0;
+  MT3_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, decode_mega_kernel, &cfg));
+  m->mega_clusters = std::min(64, max_clusters - 2);      // two clusters of slack
+  MT3_REQUIRE(m->mega_clusters >= 16, MT3_ERR_UNSUPPORTED, "only %d co-resident clusters for the persistent decode kernel",
+              max_clusters);
+  return MT3_OK;
+}
+
+static int decode_step_mega(Model* m, cudaStream_t s) {
+  MegaArgs a;
+  memset(&a, 0, sizeof(a));
+  a.prog = m->mega_prog; a.n_phases = m->mega_phases; a.bar = m->mega_bar;
+  a.B = m->B; a.H = m->H; a.Q = m->Q; a.D = m->D; a.V = m->V; a.L = m->L; a.max_len = std::max(m->L, m->T);
+  a.tok_in = m->tok_cur; a.emb = m->emb; a.pe = m->pe; a.y = m->dy;
+  a.logits = m->dlogits; a.tok_cur = m->tok_cur; a.finished = m->finished; a.tokens_out = m->tokens; a.tok_user = nullptr;
+  a.state = m->state; a.greedy = 1;
+  const size_t smem = mega_smem_bytes(a.max_len);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(8 * m->mega_clusters); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  MT3_CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_mega_kernel, a));
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
 static void drop_graph(Model* m) {
   if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
   if (m->graph) cudaGraphDestroy(m->graph);
@@ -481,7 +580,8 @@ static int ensure_graph(Model* m) {
   if (!m->cap_stream) MT3_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
   const uint64_t before = g_launch_count.load();
   MT3_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-  int r = decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, m->cap_stream);
+  int r = (m->mega && m->mega_ready) ? decode_step_mega(m, m->cap_stream)
+                                      : decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, m->cap_stream);
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
   if (r != MT3_OK) {
@@ -628,6 +728,8 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
   {
     const char* e_pdl = getenv("MT3_PDL");
     m->pdl = e_pdl && e_pdl[0] == '1';
+    const char* e_mega = getenv("MT3_DEC_MEGA");
+    m->mega = e_mega && e_mega[0] == '1';
     const char* e_ns = getenv("MT3_DEC_STREAMS");
     if (e_ns && e_ns[0] >= '1' && e_ns[0] <= '4') m->dec_streams = e_ns[0] - '0';
     const char* e_clu = getenv("MT3_DEC_CLUSTER");
@@ -691,7 +793,7 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
 namespace {
 struct WsLayout {
   int64_t x_hi, x_lo, h_lo, ao_lo, g_lo, enc_hi, enc_lo, qkv_lo, vt_hi, vt_lo;
-  int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, total;
+  int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, mega_prog, mega_bar, total;
 };
 WsLayout ws_layout(const Model* m, int B, int T) {
   WsLayout w;
@@ -729,6 +831,8 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   w.state = take(64);
   w.dpartial = take((int64_t)4 * 16 * cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * kDecTileFloats * 4);   // x4 decode streams
   w.dcounters = take((int64_t)4 * cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * 4);
+  w.mega_prog = take((int64_t)(8 * m->Ld + 8) * (int64_t)sizeof(MegaPhase));
+  w.mega_bar = take(64);
   w.total = off;
   return w;
 }
@@ -758,6 +862,8 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
   m->finished = (int*)(b + w.finished); m->tokens = (int*)(b + w.tokens); m->state = (int*)(b + w.state);
   m->dpartial = (float*)(b + w.dpartial); m->dcounters = (int*)(b + w.dcounters);
   m->dcounters_stride = cdiv(std::max(std::max(3 * m->Q, 2 * m->F), m->V), kDecBN);
+  m->mega_prog = (MegaPhase*)(b + w.mega_prog); m->mega_prog_bytes = (int64_t)(8 * m->Ld + 8) * (int64_t)sizeof(MegaPhase);
+  m->mega_bar = (unsigned*)(b + w.mega_bar); m->mega_ready = false;
   m->dpartial_stride = (int64_t)16 * m->dcounters_stride * kDecTileFloats;
   m->have_cross = false;
   if (m->tc) {
@@ -824,6 +930,10 @@ extern "C" int mt3_generate(mt3_model* h, const float* x, int32_t num_steps, int
   MT3_CUDA_CHECK(cudaMemsetAsync(m->tokens, 0, (size_t)m->B * m->L * sizeof(int), s));
   const bool use_graph = (flags & MT3_GEN_USE_GRAPH) != 0;
   const bool stop = (flags & MT3_GEN_STOP_AT_EOS) != 0;
+  if (m->mega && !m->mega_ready && mega_supported(m)) {
+    MT3_TRY(build_mega_program(m));
+    m->mega_ready = true;
+  }
   if (use_graph) MT3_TRY(ensure_graph(m));
   int ran = 0;
   for (int step = 0; step < num_steps; ++step) {
@@ -831,7 +941,8 @@ extern "C" int mt3_generate(mt3_model* h, const float* x, int32_t num_steps, int
       MT3_CUDA_CHECK(cudaGraphLaunch(m->graph_exec, s));
       count_launch(m->graph_kernels);
     } else {
-      MT3_TRY(decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, s));
+      if (m->mega && m->mega_ready) MT3_TRY(decode_step_mega(m, s));
+      else MT3_TRY(decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, s));
     }
     ++ran;
     m->host_pos += 1;
