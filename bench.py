@@ -391,7 +391,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=8, help="CPU sample: segments (the notebook's batch size)")
     ap.add_argument("--ref-budget-s", type=float, default=15.0, help="CPU sample: wall-time budget of the decode loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gemm-mode", default="simt", choices=["simt", "tf32x3", "tf32"],
+    ap.add_argument("--gemm-mode", default="tf32x3", choices=["simt", "tf32x3", "tf32"],
                     help="encoder/cross-K/V GEMMs: exact fp32 CUDA cores, or tcgen05 tf32 (x3 = fp32-faithful split)")
     args = ap.parse_args()
     if args.impl == "reference":

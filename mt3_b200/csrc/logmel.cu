@@ -25,6 +25,7 @@
 // segment; with hop 128 every sample feeds 16 frames, so the kernel is bound by
 // fp32 issue / shared memory, not HBM ("K1").
 #include <math.h>
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -37,9 +38,9 @@ struct Frontend {
   float* d_window;         // [fft]
   float2* d_tw1024;        // [32 k1][32 lane]  W_1024^(lane*k1)
   float2* d_rtw;           // [1024]            W_2048^k
-  int* d_mel_start;        // [n_mel + 1]
-  int* d_mel_bin0;         // [n_mel]
-  float* d_mel_w;          // [nnz]
+  int* d_mel_bin0;         // [n_mel] first FFT bin of the tap window
+  float* d_mel_w;          // [taps][n_mel] zero-padded band of the mel matrix
+  int taps;                // taps per mel bin (max support width)
   int nnz;
 };
 
@@ -107,32 +108,47 @@ constexpr int kHalf = 1024;
 constexpr int kScratchF2 = 32 * 33;  // padded 32x32 complex transpose buffer per warp
 
 template <int FRAMES_PER_CTA, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2)   // <= 128 registers: two CTAs (16 warps) per SM
+__global__ void __launch_bounds__(WARPS * 32, 2)
 logmel2048_kernel(const float* __restrict__ audio, long long audio_stride, int n_samples, int hop,
                   const int* __restrict__ n_valid_frames, int T, const float* __restrict__ window,
                   const float2* __restrict__ tw1024, const float2* __restrict__ rtw,
-                  const int* __restrict__ mel_start, const int* __restrict__ mel_bin0,
-                  const float* __restrict__ mel_w, int n_mel, float log_eps, float* __restrict__ out) {
+                  const int* __restrict__ mel_bin0, const float* __restrict__ mel_wpad, int mel_taps, int mel_in_smem,
+                  int n_mel, float log_eps, float* __restrict__ out) {
+  // Every lookup table lives in shared memory: with ~100 KB of it carved out per CTA the L1 that is left
+  // (~20 KB) cannot hold the 40 KB of twiddle / mel tables, and their loads would each pay an L2 round trip.
   extern __shared__ __align__(16) float smem[];
   const int chunk = (FRAMES_PER_CTA - 1) * hop + kFft;     // samples staged per CTA
   const int chunk_pad = (chunk + 3) & ~3;
   float* s_audio = smem;                                   // [chunk_pad]
   float* s_win = s_audio + chunk_pad;                      // [2048]
-  float2* s_scratch = reinterpret_cast<float2*>(s_win + kFft);  // [WARPS][32*33]
+  float2* s_tw = reinterpret_cast<float2*>(s_win + kFft);  // [32][32]  W_1024^(lane*k1)
+  float2* s_rtw = s_tw + 1024;                             // [1024]    W_2048^k
+  float2* s_scratch = s_rtw + 1024;                        // [WARPS][32*33]
+  int* s_bin0 = reinterpret_cast<int*>(s_scratch + WARPS * kScratchF2);   // [n_mel]
+  float* s_melw = reinterpret_cast<float*>(s_bin0 + ((n_mel + 3) & ~3));  // [mel_taps][n_mel] (if it fits)
 
   const int seg = blockIdx.y;
   const int t0 = blockIdx.x * FRAMES_PER_CTA;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  constexpr int NTHR = WARPS * 32;
 
   const float* a = audio + (long long)seg * audio_stride;
   const long long s0 = (long long)t0 * hop;
-  for (int i = tid; i < chunk; i += WARPS * 32) {
+  for (int i = tid; i < chunk; i += NTHR) {
     const long long g = s0 + i;
     s_audio[i] = (g < n_samples) ? __ldg(a + g) : 0.f;   // pad_end=True zeros
   }
-  for (int i = tid; i < kFft; i += WARPS * 32) s_win[i] = __ldg(window + i);
+  for (int i = tid; i < kFft; i += NTHR) s_win[i] = __ldg(window + i);
+  for (int i = tid; i < 1024; i += NTHR) {
+    s_tw[i] = __ldg(tw1024 + i);
+    s_rtw[i] = __ldg(rtw + i);
+  }
+  for (int i = tid; i < n_mel; i += NTHR) s_bin0[i] = __ldg(mel_bin0 + i);
+  if (mel_in_smem)
+    for (int i = tid; i < mel_taps * n_mel; i += NTHR) s_melw[i] = __ldg(mel_wpad + i);
   __syncthreads();
+  const float* melw = mel_in_smem ? s_melw : mel_wpad;
 
   const int n_valid = n_valid_frames ? n_valid_frames[seg] : T;
   float2* scratch = s_scratch + warp * kScratchF2;
@@ -164,7 +180,7 @@ logmel2048_kernel(const float* __restrict__ audio, long long audio_stride, int n
       const int k1 = brev5(r);
       float vr = xr[r], vi = xi[r];
       if (k1 != 0) {
-        const float2 w = __ldg(tw1024 + k1 * 32 + lane);
+        const float2 w = s_tw[k1 * 32 + lane];
         const float nr = vr * w.x - vi * w.y;
         vi = vr * w.y + vi * w.x;
         vr = nr;
@@ -195,18 +211,20 @@ logmel2048_kernel(const float* __restrict__ audio, long long audio_stride, int n
       const int k = lane + 32 * k2;
       const float er = 0.5f * (zr + qr), ei = 0.5f * (zi - qi);
       const float orr = 0.5f * (zi + qi), oi = -0.5f * (zr - qr);
-      const float2 w = __ldg(rtw + k);
+      const float2 w = s_rtw[k];
       const float Xr = er + (w.x * orr - w.y * oi);
       const float Xi = ei + (w.x * oi + w.y * orr);
       mag[k] = sqrtf(Xr * Xr + Xi * Xi);
       if (r == 0 && lane == 0) mag[kHalf] = fabsf(zr - zi);   // Nyquist bin
     }
     __syncwarp();
+    // banded mel: every mel bin reads the same number of taps (zero-padded), ascending FFT bin order;
+    // weights are laid out [tap][mel] so that a warp's reads are consecutive.
     for (int m = lane; m < n_mel; m += 32) {
-      const int b = mel_start[m], e = mel_start[m + 1];
-      const float* mg = mag + mel_bin0[m];
+      const float* mg = mag + s_bin0[m];
       float acc = 0.f;
-      for (int i = b; i < e; ++i) acc = fmaf(mg[i - b], __ldg(mel_w + i), acc);
+#pragma unroll 5
+      for (int j = 0; j < mel_taps; ++j) acc = fmaf(mg[j], melw[j * n_mel + m], acc);
       orow[m] = logf(acc <= 0.f ? log_eps : acc);      // safe_log: replace, not add
     }
     __syncwarp();
@@ -244,25 +262,27 @@ extern "C" int mt3_frontend_create(const mt3_frontend_config* cfg, const float* 
     const double th = -2.0 * M_PI * (double)k / 2048.0;
     rt[k] = make_float2((float)cos(th), (float)sin(th));
   }
-  // banded form of the [n_bins, n_mel] matrix: per mel bin the contiguous span of non-zero FFT bins
-  std::vector<int> start(n_mel + 1, 0), bin0(n_mel, 0);
-  std::vector<float> w;
+  // banded form of the [n_bins, n_mel] matrix: per mel bin the contiguous span of non-zero FFT bins, padded
+  // with zeros to a common width `taps` (window start clamped so that it stays inside the spectrum)
+  std::vector<int> lo(n_mel, -1), hi(n_mel, -1), bin0(n_mel, 0);
+  int taps = 1, nnz = 0;
   for (int m = 0; m < n_mel; ++m) {
-    int lo = -1, hi = -1;
     for (int b = 0; b < fe->n_bins; ++b)
       if (mel_matrix[(size_t)b * n_mel + m] != 0.f) {
-        if (lo < 0) lo = b;
-        hi = b;
+        if (lo[m] < 0) lo[m] = b;
+        hi[m] = b;
+        ++nnz;
       }
-    start[m] = (int)w.size();
-    if (lo >= 0) {
-      bin0[m] = lo;
-      for (int b = lo; b <= hi; ++b) w.push_back(mel_matrix[(size_t)b * n_mel + m]);
-    }
+    if (lo[m] >= 0) taps = std::max(taps, hi[m] - lo[m] + 1);
   }
-  start[n_mel] = (int)w.size();
-  fe->nnz = (int)w.size();
-  if (w.empty()) w.push_back(0.f);
+  std::vector<float> w((size_t)taps * n_mel, 0.f);
+  for (int m = 0; m < n_mel; ++m) {
+    if (lo[m] < 0) continue;
+    bin0[m] = std::min(lo[m], fe->n_bins - taps);
+    for (int j = 0; j < taps; ++j) w[(size_t)j * n_mel + m] = mel_matrix[(size_t)(bin0[m] + j) * n_mel + m];
+  }
+  fe->taps = taps;
+  fe->nnz = nnz;
 
 #define FE_ALLOC_COPY(dst, vec)                                                            \
   MT3_CUDA_CHECK(cudaMalloc((void**)&(dst), (vec).size() * sizeof((vec)[0])));            \
@@ -270,7 +290,6 @@ extern "C" int mt3_frontend_create(const mt3_frontend_config* cfg, const float* 
   FE_ALLOC_COPY(fe->d_window, win);
   FE_ALLOC_COPY(fe->d_tw1024, tw);
   FE_ALLOC_COPY(fe->d_rtw, rt);
-  FE_ALLOC_COPY(fe->d_mel_start, start);
   FE_ALLOC_COPY(fe->d_mel_bin0, bin0);
   FE_ALLOC_COPY(fe->d_mel_w, w);
 #undef FE_ALLOC_COPY
@@ -284,7 +303,6 @@ extern "C" int mt3_frontend_destroy(mt3_frontend* h) {
   cudaFree(fe->d_window);
   cudaFree(fe->d_tw1024);
   cudaFree(fe->d_rtw);
-  cudaFree(fe->d_mel_start);
   cudaFree(fe->d_mel_bin0);
   cudaFree(fe->d_mel_w);
   delete fe;
@@ -309,9 +327,14 @@ extern "C" int mt3_logmel_f32(const mt3_frontend* h, const float* audio, int64_t
   const Frontend* fe = reinterpret_cast<const Frontend*>(h);
   const int hop = fe->cfg.hop_width;
   const int T = (n_samples + hop - 1) / hop;
-  constexpr int F = 32, W = 8;   // 32 frames per CTA (4 per warp): ~100 KB of smem, two CTAs per SM
+  constexpr int F = 16, W = 4;   // 16 frames per CTA, 4 warps: ~96 KB of smem incl. all tables -> two CTAs per SM
   const int chunk = (F - 1) * hop + kFft;
-  const size_t smem = (size_t)(((chunk + 3) & ~3) + kFft) * sizeof(float) + (size_t)W * kScratchF2 * sizeof(float2);
+  const int n_mel = fe->cfg.num_mel_bins;
+  const size_t base = (size_t)(((chunk + 3) & ~3) + kFft) * sizeof(float) + 2 * 1024 * sizeof(float2) +
+                      (size_t)W * kScratchF2 * sizeof(float2) + (size_t)((n_mel + 3) & ~3) * sizeof(int);
+  const size_t mel_bytes = (size_t)fe->taps * n_mel * sizeof(float);
+  const int mel_in_smem = base + mel_bytes <= 110 * 1024;
+  const size_t smem = base + (mel_in_smem ? mel_bytes : 0);
   MT3_REQUIRE(smem <= 227 * 1024, MT3_ERR_UNSUPPORTED, "mt3_logmel_f32: hop %d needs %zu B of shared memory", hop, smem);
   auto kern = logmel2048_kernel<F, W>;
   static bool attr_set = false;
@@ -320,10 +343,9 @@ extern "C" int mt3_logmel_f32(const mt3_frontend* h, const float* audio, int64_t
     attr_set = true;
   }
   dim3 grid((T + F - 1) / F, num_segments);
-  kern<<<grid, W * 32, smem, (cudaStream_t)stream>>>(audio, audio_stride, n_samples, hop, n_valid_frames, T,
-                                                     fe->d_window, fe->d_tw1024, fe->d_rtw, fe->d_mel_start,
-                                                     fe->d_mel_bin0, fe->d_mel_w, fe->cfg.num_mel_bins,
-                                                     fe->cfg.log_eps, out);
+  kern<<<grid, W * 32, smem, (cudaStream_t)stream>>>(audio, audio_stride, n_samples, hop, n_valid_frames, T, fe->d_window,
+                                                     fe->d_tw1024, fe->d_rtw, fe->d_mel_bin0, fe->d_mel_w, fe->taps,
+                                                     mel_in_smem, n_mel, fe->cfg.log_eps, out);
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }

@@ -31,7 +31,7 @@ class InferenceModel(object):
     """Wrapper of the B200 model for music transcription."""
 
     def __init__(self, checkpoint_path, model_type='mt3', *, device='cuda:0', batch_size: int = 8,
-                 gin_dir: Optional[str] = None, gemm_mode: int = _lib.GEMM_FP32_SIMT, use_graph: bool = True):
+                 gin_dir: Optional[str] = None, gemm_mode: int = _lib.GEMM_TF32X3, use_graph: bool = True):
         # Model Constants (notebook :175-185).
         if model_type == 'ismir2021':
             num_velocity_bins = 127
