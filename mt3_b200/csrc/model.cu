@@ -19,6 +19,7 @@
 #include "gemm_tc.cuh"
 #include "attention_tc.cuh"
 #include "decode.cuh"
+#include "decode_chain.cuh"
 #include "decode_mega.cuh"
 #include "layers.cuh"
 
@@ -90,6 +91,8 @@ struct Model {
   bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between the decode-step kernels
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
   int dec_streams = 1;            // MT3_DEC_STREAMS=n: decode step runs as n concurrent sub-batches
+  bool chain = false;             // MT3_DEC_CHAIN=1: cluster-local GEMM chains (decode_chain.cuh), 35 launches per step
+  int chain_cluster = 0;          // cluster size picked for the chain kernel (16 or 8)
   bool mega = false;              // MT3_DEC_MEGA=1: the whole decode step as one persistent kernel (decode_mega.cuh)
   MegaPhase* mega_prog = nullptr; int64_t mega_prog_bytes = 0; unsigned* mega_bar = nullptr;
   int mega_phases = 0, mega_clusters = 0; bool mega_ready = false;
@@ -434,12 +437,17 @@ static int decode_rows(Model* m, const int* tok_in, float* logits, int greedy, i
   return MT3_OK;
 }
 
+static int decode_step_chain(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
+                             int* tokens_ws, cudaStream_t s);
+
 // One decode step for the whole batch.  With MT3_DEC_STREAMS = n > 1 the batch is cut into n blocks of
 // sequences that run on n streams (forked/joined with events; captured as parallel branches of the step
 // graph): one block's latency-bound GEMM chain overlaps another block's bandwidth-bound attention.
 static int decode_step_impl(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
                             int* tokens_ws, cudaStream_t s) {
   const int B = m->B;
+  if (m->chain && m->chain_cluster)
+    return decode_step_chain(m, tok_in, logits, greedy, tok_user, use_finished, tokens_ws, s);
   int ns = std::max(1, std::min(m->dec_streams, 4));
   while (ns > 1 && B / ns < 8) --ns;
   if (ns == 1) {
@@ -467,6 +475,114 @@ static int decode_step_impl(Model* m, const int* tok_in, float* logits, int gree
     }
   }
   if (!greedy) {
+    MT3_CUDA_CHECK(launch_kernel(advance_pos_kernel, dim3(1), dim3(1), 0, s, m->pdl, m->state));
+    MT3_LAUNCH_CHECK();
+  }
+  return MT3_OK;
+}
+
+// ---- decode step with cluster-local GEMM chains (decode_chain.cuh): 35 launches instead of 67 -------------
+static ChainStage chain_stage(Model* m, const float* A, int lda, int K, const float* W, int N, int norm, int epi, float* C,
+                              int ldc, int n_split, float* kv) {
+  ChainStage s;
+  memset(&s, 0, sizeof(s));
+  s.A = A; s.lda = lda; s.K = K; s.W = W; s.N = N; s.norm = norm; s.epi = epi; s.C = C; s.ldc = ldc; s.n_split = n_split;
+  if (kv) { s.kv = kv; s.kv_cap = m->L; s.kv_H = m->H; s.kv_pos = m->state; }
+  return s;
+}
+
+static bool chain_supported(const Model* m, int cl) {
+  const int ns[] = {3 * m->Q, m->D, m->Q, 2 * m->F, m->V};
+  for (int n : ns)
+    if (n % (cl * 8) != 0 || n / cl > kChMaxNc) return false;
+  return m->D % 4 == 0 && m->F % 4 == 0 && m->Q % 4 == 0 && std::max(std::max(m->D, m->F), m->Q) <= kChMaxK;
+}
+
+static int launch_chain(Model* m, const ChainArgs& a, cudaStream_t s) {
+  const int cl = m->chain_cluster;
+  const int n_clusters = cdiv(m->B, kChRows);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(n_clusters * cl); cfg.blockDim = dim3(kChThreads); cfg.dynamicSmemBytes = chain_smem_bytes(); cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = m->pdl ? 2 : 1;
+  MT3_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dec_chain_kernel, a));
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
+static int chain_setup(Model* m) {
+  if (m->chain_cluster) return MT3_OK;
+  MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes()));
+  MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_chain_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  for (int cl : {16, 8}) {
+    if (!chain_supported(m, cl)) continue;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(cl); cfg.blockDim = dim3(kChThreads); cfg.dynamicSmemBytes = chain_smem_bytes();
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, dec_chain_kernel, &cfg) == cudaSuccess && n >= 1) {
+      m->chain_cluster = cl;
+      return MT3_OK;
+    }
+    cudaGetLastError();
+  }
+  return fail(MT3_ERR_UNSUPPORTED, "no cluster size (16, 8) fits the GEMM-chain kernel for this model");
+}
+
+// greedy step, whole batch: embed | chain{QKV0} | 8 x [self-attn | chain A | cross-attn | chain B] | argmax
+static int decode_step_chain(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
+                             int* tokens_ws, cudaStream_t s) {
+  const int B = m->B, D = m->D, Q = m->Q, F = m->F, V = m->V, L = m->L, T = m->T;
+  int* pos = m->state;
+  const Rows all{0, B, 0};
+  MT3_CUDA_CHECK(launch_kernel(embed_kernel, dim3(B), dim3(128), 0, s, m->pdl, tok_in, (const float*)m->emb, D, V,
+                               (const float*)m->pe, (const int*)pos, m->dy, 0));
+  MT3_LAUNCH_CHECK();
+  ChainArgs c0;
+  memset(&c0, 0, sizeof(c0));
+  c0.B = B; c0.eps = 1e-6f; c0.n_stages = 1;
+  c0.st[0] = chain_stage(m, m->dy, D, D, m->dec[0].wqkv, 3 * Q, 1, EPI_STORE, m->dq, Q, Q, m->skv);
+  MT3_TRY(launch_chain(m, c0, s));
+  for (int l = 0; l < m->Ld; ++l) {
+    const DecLayer& w = m->dec[l];
+    float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
+    const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
+    MT3_TRY(launch_dec_attention(m, m->dq, skv, L, pos, 1, m->dao, all, s));
+    ChainArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.B = B; ca.eps = 1e-6f; ca.n_stages = 2;
+    ca.st[0] = chain_stage(m, m->dao, Q, Q, w.wo, D, 0, EPI_RESIDUAL, m->dy, D, D, nullptr);
+    ca.st[1] = chain_stage(m, m->dy, D, D, w.wq_c, Q, 1, EPI_STORE, m->dq, Q, Q, nullptr);
+    MT3_TRY(launch_chain(m, ca, s));
+    MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, all, s));
+    ChainArgs cb;
+    memset(&cb, 0, sizeof(cb));
+    cb.B = B; cb.eps = 1e-6f; cb.n_stages = 4;
+    cb.st[0] = chain_stage(m, m->dao, Q, Q, w.wo_c, D, 0, EPI_RESIDUAL, m->dy, D, D, nullptr);
+    cb.st[1] = chain_stage(m, m->dy, D, D, w.wi, 2 * F, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr);
+    cb.st[2] = chain_stage(m, m->dg, F, F, w.wo2, D, 0, EPI_RESIDUAL, m->dy, D, D, nullptr);
+    if (l + 1 < m->Ld)
+      cb.st[3] = chain_stage(m, m->dy, D, D, m->dec[l + 1].wqkv, 3 * Q, 1, EPI_STORE, m->dq, Q, Q,
+                             m->skv + (int64_t)(l + 1) * B * L * 2 * Q);
+    else
+      cb.st[3] = chain_stage(m, m->dy, D, D, m->w_logits, V, 1, EPI_STORE, logits, V, V, nullptr);
+    MT3_TRY(launch_chain(m, cb, s));
+  }
+  if (greedy) {
+    MT3_CUDA_CHECK(launch_kernel(argmax_step_kernel, dim3(B), dim3(256), 0, s, m->pdl, (const float*)logits, V, B,
+                                 use_finished ? m->tok_cur : (int*)nullptr, use_finished ? m->finished : (int*)nullptr,
+                                 tokens_ws, L, tok_user, m->state, 1, 0));
+    MT3_LAUNCH_CHECK();
+  } else {
     MT3_CUDA_CHECK(launch_kernel(advance_pos_kernel, dim3(1), dim3(1), 0, s, m->pdl, m->state));
     MT3_LAUNCH_CHECK();
   }
@@ -728,6 +844,8 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
   {
     const char* e_pdl = getenv("MT3_PDL");
     m->pdl = e_pdl && e_pdl[0] == '1';
+    const char* e_chain = getenv("MT3_DEC_CHAIN");
+    m->chain = e_chain && e_chain[0] == '1';
     const char* e_mega = getenv("MT3_DEC_MEGA");
     m->mega = e_mega && e_mega[0] == '1';
     const char* e_ns = getenv("MT3_DEC_STREAMS");
@@ -864,6 +982,7 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
   m->dcounters_stride = cdiv(std::max(std::max(3 * m->Q, 2 * m->F), m->V), kDecBN);
   m->mega_prog = (MegaPhase*)(b + w.mega_prog); m->mega_prog_bytes = (int64_t)(8 * m->Ld + 8) * (int64_t)sizeof(MegaPhase);
   m->mega_bar = (unsigned*)(b + w.mega_bar); m->mega_ready = false;
+  if (m->chain) MT3_TRY(chain_setup(m));
   m->dpartial_stride = (int64_t)16 * m->dcounters_stride * kDecTileFloats;
   m->have_cross = false;
   if (m->tc) {
