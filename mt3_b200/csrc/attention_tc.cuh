@@ -214,7 +214,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
         float p[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float e = (c0 + j < T) ? expf(__uint_as_float(v[j]) - mx) : 0.f;
+          // ex2.approx (2 ulp) is ample: the value is rounded to tf32 (2^-11) on the next line
+          float e = (c0 + j < T) ? exp2f((__uint_as_float(v[j]) - mx) * 1.4426950408889634f) : 0.f;
           e = round_tf32(e);                                // exactly what the tensor core will read
           p[j] = e;
           sum += e;
