@@ -35,6 +35,22 @@ def broadcast_weights(blob: torch.Tensor, src: int = 0) -> torch.Tensor:
     return blob
 
 
+def broadcast_params(params, cfg, device, src: int = 0):
+    """Weights at load, data-parallel: only rank `src` needs `params` ({tree path: array}); the flat
+    blob is broadcast once and every rank gets the same {path: array} dict back.  With one process
+    this is the identity."""
+    from . import weights
+    rank, n = world()
+    if n == 1:
+        return params
+    if rank == src:
+        blob = torch.from_numpy(weights.flatten(params, cfg)).to(device)
+    else:
+        blob = torch.empty(weights.num_params(cfg), dtype=torch.float32, device=device)
+    broadcast_weights(blob, src=src)
+    return weights.unflatten(blob.cpu().numpy(), cfg)
+
+
 def gather_tokens(local_tokens: torch.Tensor, num_segments: int) -> torch.Tensor:
     """All-gather of the per-rank int32 [S_local, L] token streams -> [num_segments, L] on every
     rank, in global segment order.  Shards are padded to ceil(S/N) rows for the collective."""

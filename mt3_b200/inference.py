@@ -108,13 +108,19 @@ class InferenceModel(object):
         """Restore weights (notebook :247-262).  `checkpoint_path` is a .npz keyed by the Flax tree
         paths (mt3_b200.weights), a {path: array} dict, or 'synthetic[:SEED]' for random weights
         drawn from the reference's initialisers (the published checkpoints are unreachable offline)."""
-        if isinstance(checkpoint_path, dict):
-            params = checkpoint_path
-        elif isinstance(checkpoint_path, str) and checkpoint_path.startswith('synthetic'):
-            seed = int(checkpoint_path.split(':', 1)[1]) if ':' in checkpoint_path else 0
-            params = weights.synthetic_params(self._model_config(), seed)
-        else:
-            params = weights.load(checkpoint_path)
+        from . import distributed as mt3_dist
+        rank, world_size = mt3_dist.world()
+        params = None
+        if rank == 0 or world_size == 1:
+            if isinstance(checkpoint_path, dict):
+                params = checkpoint_path
+            elif isinstance(checkpoint_path, str) and checkpoint_path.startswith('synthetic'):
+                seed = int(checkpoint_path.split(':', 1)[1]) if ':' in checkpoint_path else 0
+                params = weights.synthetic_params(self._model_config(), seed)
+            else:
+                params = weights.load(checkpoint_path)
+        # data-parallel (one process per GPU): only rank 0 reads the checkpoint; ONE broadcast at load
+        params = mt3_dist.broadcast_params(params, self._model_config(), self.device, src=0)
         self.model = self._load_model(params)
 
     # ---------------------------------------------------------------------------------
@@ -155,6 +161,29 @@ class InferenceModel(object):
             out[s0:s1].copy_(toks, non_blocking=True)
         torch.cuda.synchronize(self.device)
         return out.numpy()
+
+    def transcribe_segments_sharded(self, audio_segments, **kwargs) -> np.ndarray:
+        """Data-parallel transcribe_segments: every rank passes the SAME global segment
+        list, transcribes its contiguous shard on its own GPU and receives all token streams
+        int32 [S, 1024] in segment order after ONE all-gather.  Identity with a single process."""
+        from . import distributed as mt3_dist
+        rank, world_size = mt3_dist.world()
+        a = audio_segments
+        if isinstance(a, np.ndarray):
+            a = torch.from_numpy(a)
+        S = a.shape[0]
+        if world_size == 1:
+            return self.transcribe_segments(a, **kwargs)
+        lo, hi = mt3_dist.shard_range(S, rank, world_size)
+        nv = kwargs.pop('n_valid_frames', None)
+        if nv is not None:
+            nv = np.asarray(nv)[lo:hi]
+        if hi > lo:
+            local = torch.from_numpy(self.transcribe_segments(a[lo:hi], n_valid_frames=nv, **kwargs))
+        else:
+            local = torch.empty((0, self.outputs_length), dtype=torch.int32)
+        gathered = mt3_dist.gather_tokens(local.to(self.device), S)
+        return gathered.cpu().numpy()
 
     def _pad_inputs(self, spec: torch.Tensor) -> torch.Tensor:
         """Feature converter (models.py:96): trim/pad the frame axis to inputs_length with 0.0."""

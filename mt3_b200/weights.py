@@ -71,6 +71,19 @@ def flatten(params: Dict[str, np.ndarray], cfg) -> np.ndarray:
     return out
 
 
+def unflatten(blob: np.ndarray, cfg) -> Dict[str, np.ndarray]:
+    """Inverse of flatten(): views into the float32 blob keyed by tree path."""
+    blob = np.asarray(blob, np.float32).reshape(-1)
+    if blob.size != num_params(cfg):
+        raise ValueError(f"weight blob has {blob.size} floats, expected {num_params(cfg)}")
+    out, off = {}, 0
+    for name, shape in param_shapes(cfg).items():
+        n = int(np.prod(shape))
+        out[name] = blob[off:off + n].reshape(shape)
+        off += n
+    return out
+
+
 def synthetic_params(cfg, seed: int = 0) -> Dict[str, np.ndarray]:
     """Random fp32 weights drawn from the reference's initialiser distributions
     (layers.py:182-183,233-234,385-386,449-450; network.py:177,222; layers.py:608) --

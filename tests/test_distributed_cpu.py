@@ -35,6 +35,13 @@ def _worker(rank, world, port, s_total, q):
         blob = torch.arange(1000, dtype=torch.float32) * 0.5 if rank == 0 else torch.zeros(1000)
         D.broadcast_weights(blob, src=0)
         ok_w = bool(torch.equal(blob, torch.arange(1000, dtype=torch.float32) * 0.5))
+        # parameter-dict form used by InferenceModel.restore_from_checkpoint: only rank 0 has the weights
+        from mt3_b200 import network, weights
+        cfg = network.T5Config(vocab_size=128, emb_dim=64, num_heads=2, num_encoder_layers=1, num_decoder_layers=1,
+                               head_dim=64, mlp_dim=128, mlp_activations=('gelu', 'linear'))
+        want = weights.synthetic_params(cfg, 3)
+        got = D.broadcast_params(want if rank == 0 else None, cfg, torch.device("cpu"), src=0)
+        ok_w = ok_w and list(got) == list(want) and all(np.array_equal(got[k], want[k]) for k in want)
         # each rank "decodes" its shard: token[i, :] = global segment index
         lo, hi = D.shard_range(s_total, rank, world)
         local = torch.arange(lo, hi, dtype=torch.int32)[:, None].repeat(1, 16)
