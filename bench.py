@@ -158,6 +158,15 @@ def cpu_port_sample(params, audio, nb, dec_steps, budget_s):
     return nb * SEG_SECONDS / full, cores, desc, 1000.0 * (t_fixed + t_dec)
 
 
+def load_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return float(json.load(f)[kernel]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -317,7 +326,7 @@ def run_ours(args):
         us = 1000.0 * e0.elapsed_time(e1) / iters
         ach = alg_bytes / (us * 1e-6) / 1e9
         roofline = {"kernel": "dec_attention_bulk_kernel (decode self-attention, cache length 512, B=64, 6 heads)", "bound": "hbm",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": load_traffic("dec_attention_bulk_kernel"),
                     "peak_source": peak_src, "us_per_launch": us, "algorithmic_bytes_per_launch": alg_bytes}
         # back-to-back launch time of the other hot kernels at the bench shapes (device events, stream order)
         kernels_us = {}
