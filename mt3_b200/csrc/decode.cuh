@@ -458,15 +458,21 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
     // ---- producer: K tiles 0..nt-1, then V tiles 0..nt-1 ----
     // self-attention (len_ptr set): the newest cache row comes from the preceding QKV GEMM -> wait;
     // the hoisted cross K/V is independent of every decode-step kernel -> stream it right away (PDL)
-    if (len_ptr) pdl_wait();
+    // self-attention: every cache row but the newest (tile nt-1) was written by earlier steps, so those tiles are
+    // streamed before the wait as well and only the last K tile is held back until the QKV GEMM has completed.
     pdl_trigger();
     if (lane == 0) {
       const uint64_t policy = l2_evict_first_policy();
+      bool waited = len_ptr == nullptr;
       for (int j = 0; j < 2 * nt; ++j) {
         const int s = j % kAttStages;
         const uint32_t ph = (j / kAttStages) & 1;
-        tc::mbar_wait(&empty[s], ph ^ 1);
         const int t = j < nt ? j : j - nt;
+        if (!waited && t == nt - 1) {
+          pdl_wait();
+          waited = true;
+        }
+        tc::mbar_wait(&empty[s], ph ^ 1);
         const int keys = min(kAttKT, len - t * kAttKT);
         const uint32_t bytes = (uint32_t)keys * 64 * 4;
         const float* src = (j < nt ? kbase : vbase) + (long long)t * kAttTileFloats;

@@ -88,7 +88,9 @@ struct Model {
   bool tc = false, split3 = false;
   TcW t_w_in;
   Act a_x, a_h, a_ao, a_g, a_enc, a_qkv, a_vt; // tcgen05-path activation buffers (workspace); a_vt = per-head V^T
-  bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between the decode-step kernels
+  bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between all decode-step kernels
+  bool pdl_attn = false;          // MT3_PDL=2: only the attention launches (K/V prefetch under the preceding GEMM)
+  bool pdl_gemm = false;          // MT3_PDL=4: only the GEMM launches; bits combine (6 = attention + GEMM)
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
   int dec_streams = 1;            // MT3_DEC_STREAMS=n: decode step runs as n concurrent sub-batches
   bool chain = false;             // MT3_DEC_CHAIN=1: cluster-local GEMM chains (decode_chain.cuh), 35 launches per step
@@ -377,8 +379,8 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
     }
     a.partial = m->dpartial + (int64_t)rows.stream_idx * m->dpartial_stride;      // per-stream split-K scratch
     a.counters = m->dcounters + (int64_t)rows.stream_idx * m->dcounters_stride;
-    int rc = m->dec_cluster ? launch_dec_gemm_cluster(a, s, m->pdl) : MT3_ERR_UNSUPPORTED;
-    if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, splits, s, m->pdl);   // shapes the cluster kernel does not tile
+    int rc = m->dec_cluster ? launch_dec_gemm_cluster(a, s, m->pdl_gemm) : MT3_ERR_UNSUPPORTED;
+    if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, splits, s, m->pdl_gemm);   // shapes the cluster kernel does not tile
     MT3_TRY(rc);
   }
   return MT3_OK;
@@ -394,7 +396,7 @@ static int launch_dec_attention(Model* m, const float* q, const float* kv, int c
     attr_done = true;
   }
   MT3_REQUIRE(smem <= 100 * 1024, MT3_ERR_UNSUPPORTED, "decode attention: length %d too long", max_len);
-  MT3_CUDA_CHECK(launch_kernel(dec_attention_bulk_kernel, dim3(m->H, rows.count), dim3(kAttThreads), smem, s, m->pdl,
+  MT3_CUDA_CHECK(launch_kernel(dec_attention_bulk_kernel, dim3(m->H, rows.count), dim3(kAttThreads), smem, s, m->pdl_attn,
                                q + (int64_t)rows.begin * m->Q, m->Q, 0, kv + (int64_t)rows.begin * 2 * m->H * cap * 64, m->H, cap,
                                len_ptr, len_add, max_len, out + (int64_t)rows.begin * m->Q, m->Q));
   MT3_LAUNCH_CHECK();
@@ -843,7 +845,10 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
   }
   {
     const char* e_pdl = getenv("MT3_PDL");
-    m->pdl = e_pdl && e_pdl[0] == '1';
+    const int pdl_bits = e_pdl ? atoi(e_pdl) : 0;
+    m->pdl = (pdl_bits & 1) != 0;
+    m->pdl_attn = (pdl_bits & 3) != 0;
+    m->pdl_gemm = (pdl_bits & 5) != 0;
     const char* e_chain = getenv("MT3_DEC_CHAIN");
     m->chain = e_chain && e_chain[0] == '1';
     const char* e_mega = getenv("MT3_DEC_MEGA");
