@@ -331,6 +331,9 @@ def run_ours(args):
         # back-to-back launch time of the other hot kernels at the bench shapes (device events, stream order)
         kernels_us = {}
         for name, kind, p_, it_ in (("dec_self_attention_len512", _lib.K_DEC_SELF_ATTN, 511, 64),
+                                    ("dec_self_attention_len32", _lib.K_DEC_SELF_ATTN, 31, 64),
+                                    ("dec_self_attention_len128", _lib.K_DEC_SELF_ATTN, 127, 64),
+                                    ("dec_self_attention_len1024", _lib.K_DEC_SELF_ATTN, 1023, 64),
                                     ("dec_cross_attention_len256", _lib.K_DEC_CROSS_ATTN, 0, 64),
                                     ("dec_qkv_gemm_64x1152x512", _lib.K_DEC_QKV_GEMM, 0, 64),
                                     ("enc_qkv_gemm_16384x1152x512", _lib.K_ENC_QKV_GEMM, 0, 16),
@@ -347,7 +350,8 @@ def run_ours(args):
         log("kernel microbench: " + ", ".join(f"{k}={v:.1f}us" for k, v in kernels_us.items()))
         if world == 1 and not args.no_cpu_baseline:
             log("cpu baseline (torch-CPU port) ...")
-            v, cores, desc, _ = cpu_port_sample(params, audio_host, args.ref_batch, dec_steps, args.ref_budget_s)
+            v, cores, desc, _ = cpu_port_sample(weights.synthetic_params(im._model_config(), 0), audio_host, args.ref_batch,
+                                                dec_steps, args.ref_budget_s)
             cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": desc}
 
     if rank == 0:

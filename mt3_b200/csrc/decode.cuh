@@ -38,7 +38,15 @@ struct DecGemmArgs {
   int n_split; float* C1; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;
   float* partial;                 // [splits][n_tiles][64*32 + 64] scratch
   int* counters;                  // [n_tiles], zero on entry, left zero on exit
+  unsigned long long* trace;      // debug timeline slot (mt3_debug_trace_step) or null: [0] min start, [1] max end (ns,
+                                  // %globaltimer); [2..6] clock64 deltas of CTA (0,0) at its phase boundaries
 };
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // Volatile PTX loads: emitted in program order, so a run of them stays a run of independent loads in
 // flight (the compiler otherwise pairs each load with its shared-memory store and serialises the latency).
@@ -243,6 +251,13 @@ sgemm_dec_cluster_kernel(const DecGemmArgs p) {
   const int tx = tid % 8, ty = tid / 8;       // thread tile: rows ty + 16 i (i < 4), columns tx*4 .. +3
   const int n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.y * KC;
+  const bool tr = p.trace != nullptr && tid == 0;
+  const bool tr0 = tr && blockIdx.x == 0 && blockIdx.y == 0;
+  long long c0 = 0;
+  if (tr) {
+    atomicMin(p.trace, gtime_ns());
+    c0 = clock64();
+  }
 
   // ---- load phase: cp.async (global -> shared, no register staging): every copy of the CTA's 8-16 KB of
   // weights and 12-32 KB of activations is in flight at once; one wait.  Weights are issued BEFORE the PDL
@@ -269,6 +284,7 @@ sgemm_dec_cluster_kernel(const DecGemmArgs p) {
   }
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  if (tr0) p.trace[2] = (unsigned long long)(clock64() - c0);      // loads landed
 
   float acc[4][4];
 #pragma unroll
@@ -304,11 +320,13 @@ sgemm_dec_cluster_kernel(const DecGemmArgs p) {
     }
   }
   __syncthreads();                              // everyone is done reading As: recycle it as the partial tile
+  if (tr0) p.trace[3] = (unsigned long long)(clock64() - c0);      // FMA loop done
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     *reinterpret_cast<float4*>(&Ps[(ty + 16 * i) * BN + tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   if (tid < BM) Ss[tid] = ss;
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (tr0) p.trace[4] = (unsigned long long)(clock64() - c0);      // cluster barrier passed
 
   // ---- reduce my rows across the cluster (rank order) + fused epilogue ----
   const int rows_per_rank = BM / (int)S;
@@ -354,8 +372,13 @@ sgemm_dec_cluster_kernel(const DecGemmArgs p) {
       *reinterpret_cast<float2*>(p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos)) = v;
     }
   }
+  if (tr0) p.trace[5] = (unsigned long long)(clock64() - c0);      // DSMEM reduce + epilogue stores issued
   // nobody may exit (and release its shared memory) while a peer can still be reading it
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (tr) {
+    if (tr0) p.trace[6] = (unsigned long long)(clock64() - c0);
+    atomicMax(p.trace + 1, gtime_ns());
+  }
 }
 
 template <int KC>
@@ -429,7 +452,8 @@ inline size_t dec_attention_smem(int max_len) {
 // len = (len_ptr ? *len_ptr : 0) + len_add.
 __global__ void __launch_bounds__(kAttThreads)
 dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const float* __restrict__ kv, int H, int cap,
-                          const int* __restrict__ len_ptr, int len_add, int max_len, float* __restrict__ out, int ldo) {
+                          const int* __restrict__ len_ptr, int len_add, int max_len, float* __restrict__ out, int ldo,
+                          unsigned long long* trace) {
   extern __shared__ __align__(128) float sm[];
   float* ring = sm;                                              // [stages][32*64]
   float* sP = ring + kAttStages * kAttTileFloats;                // [max_len4]
@@ -444,6 +468,13 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
   const int nt = (len + kAttKT - 1) / kAttKT;
   const float* kbase = kv + (((long long)b * 2 + 0) * H + h) * (long long)cap * 64;
   const float* vbase = kv + (((long long)b * 2 + 1) * H + h) * (long long)cap * 64;
+  const bool tr = trace != nullptr && tid == 0;
+  const bool tr0 = tr && blockIdx.x == 0 && blockIdx.y == 0;
+  long long c0 = 0;
+  if (tr) {
+    atomicMin(trace, gtime_ns());
+    c0 = clock64();
+  }
 
   if (tid == 0) {
     for (int s = 0; s < kAttStages; ++s) {
@@ -493,6 +524,7 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
   for (int j = 0; j < nt; ++j) {
     const int s = j % kAttStages;
     tc::mbar_wait(&full[s], (j / kAttStages) & 1);
+    if (tr0 && j == 0) trace[2] = (unsigned long long)(clock64() - c0);      // first K tile landed
     const float* tile = ring + s * kAttTileFloats;
     const int k0 = j * kAttKT;
 #pragma unroll
@@ -515,6 +547,7 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(&empty[s]);
   }
+  if (tr0) trace[3] = (unsigned long long)(clock64() - c0);       // pass 1 (K tiles) consumed
   lmax = warp_max(lmax);
   if (lane == 0) s_stat[warp] = lmax;
   asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -529,6 +562,7 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
   if (lane == 0) s_stat[4 + warp] = lsum;
   asm volatile("bar.sync 1, 128;" ::: "memory");
   const float inv = 1.0f / (s_stat[4] + s_stat[5] + s_stat[6] + s_stat[7]);
+  if (tr0) trace[4] = (unsigned long long)(clock64() - c0);       // softmax done
 
   // pass 2: O = P V.  thread -> key group (tid / 16: 8 groups) x 4 dims (tid % 16)
   const int kg = tid >> 4, d4 = tid & 15;
@@ -551,6 +585,7 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
     __syncwarp();
     if (lane == 0) tc::mbar_arrive(&empty[s]);
   }
+  if (tr0) trace[5] = (unsigned long long)(clock64() - c0);       // pass 2 (V tiles) consumed
   *reinterpret_cast<float4*>(sRed + kg * 64 + d4 * 4) = acc;
   asm volatile("bar.sync 1, 128;" ::: "memory");
   if (tid < 64) {
@@ -558,6 +593,10 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
 #pragma unroll
     for (int g = 0; g < 8; ++g) s += sRed[g * 64 + tid];
     out[(long long)b * ldo + h * 64 + tid] = s * inv;
+  }
+  if (tr) {
+    if (tr0) trace[6] = (unsigned long long)(clock64() - c0);
+    atomicMax(trace + 1, gtime_ns());
   }
 }
 

@@ -93,6 +93,10 @@ struct Model {
   bool pdl_gemm = false;          // MT3_PDL=4: only the GEMM launches; bits combine (6 = attention + GEMM)
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
   int dec_streams = 1;            // MT3_DEC_STREAMS=n: decode step runs as n concurrent sub-batches
+  // debug timeline (mt3_debug_trace_step): while `tracing` is set every decode GEMM / attention launch gets a slot
+  unsigned long long* trace = nullptr;
+  bool tracing = false;
+  std::vector<std::string> trace_names;
   bool chain = false;             // MT3_DEC_CHAIN=1: cluster-local GEMM chains (decode_chain.cuh), 35 launches per step
   int chain_cluster = 0;          // cluster size picked for the chain kernel (16 or 8)
   bool mega = false;              // MT3_DEC_MEGA=1: the whole decode step as one persistent kernel (decode_mega.cuh)
@@ -363,6 +367,13 @@ static int cross_kv_impl(Model* m, const float* encoded, cudaStream_t s) {
 // A contiguous block of sequences decoded on one stream (MT3_DEC_STREAMS sub-batches per step).
 struct Rows { int begin, count, stream_idx; };
 
+constexpr int kTraceSlots = 256, kTraceWords = 8;
+static unsigned long long* trace_slot(Model* m, const char* name) {
+  if (!m->tracing || (int)m->trace_names.size() >= kTraceSlots) return nullptr;
+  m->trace_names.push_back(name);
+  return m->trace + (size_t)(m->trace_names.size() - 1) * kTraceWords;
+}
+
 static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, int K, int norm, int epi, float* C, int ldc,
                     int n_split, float* kv, const int* pos, const Rows& rows, cudaStream_t s) {
   const int splits = dec_gemm_splits(N, K, m->sm_count);
@@ -379,6 +390,7 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
     }
     a.partial = m->dpartial + (int64_t)rows.stream_idx * m->dpartial_stride;      // per-stream split-K scratch
     a.counters = m->dcounters + (int64_t)rows.stream_idx * m->dcounters_stride;
+    a.trace = trace_slot(m, K == m->F ? "gemm_mlp_out" : (N == 2 * m->F ? "gemm_mlp_in" : (kv ? "gemm_qkv_append" : (N == m->V ? "gemm_logits" : (K == m->Q ? "gemm_attn_out" : "gemm_cross_q")))));
     int rc = m->dec_cluster ? launch_dec_gemm_cluster(a, s, m->pdl_gemm) : MT3_ERR_UNSUPPORTED;
     if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, splits, s, m->pdl_gemm);   // shapes the cluster kernel does not tile
     MT3_TRY(rc);
@@ -398,7 +410,8 @@ static int launch_dec_attention(Model* m, const float* q, const float* kv, int c
   MT3_REQUIRE(smem <= 100 * 1024, MT3_ERR_UNSUPPORTED, "decode attention: length %d too long", max_len);
   MT3_CUDA_CHECK(launch_kernel(dec_attention_bulk_kernel, dim3(m->H, rows.count), dim3(kAttThreads), smem, s, m->pdl_attn,
                                q + (int64_t)rows.begin * m->Q, m->Q, 0, kv + (int64_t)rows.begin * 2 * m->H * cap * 64, m->H, cap,
-                               len_ptr, len_add, max_len, out + (int64_t)rows.begin * m->Q, m->Q));
+                               len_ptr, len_add, max_len, out + (int64_t)rows.begin * m->Q, m->Q,
+                               trace_slot(m, len_ptr ? "attn_self" : "attn_cross")));
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }
@@ -1088,6 +1101,56 @@ extern "C" int mt3_vocab_decode(const int32_t* ids, int32_t batch, int32_t lengt
   if (batch == 0 || length == 0) return MT3_OK;
   vocab_decode_kernel<<<cdiv(batch, 64), 64, 0, (cudaStream_t)stream>>>(ids, batch, length, num_regular_tokens, out);
   MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
+__global__ void trace_reset_kernel(unsigned long long* t, int n_slots) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_slots * mt3::kTraceWords) t[i] = (i % mt3::kTraceWords == 0) ? ~0ull : 0ull;
+}
+
+extern "C" int mt3_debug_trace_step(mt3_model* h, int32_t pos, uint64_t* out, int32_t max_slots, char* names,
+                                    int32_t names_bytes, int32_t* n_slots, void* stream) {
+  MT3_REQUIRE(h && out && names && n_slots, MT3_ERR_BAD_ARG, "mt3_debug_trace_step: null argument");
+  Model* m = reinterpret_cast<Model*>(h);
+  MT3_NEED_WS(m);
+  MT3_REQUIRE(pos >= 2 && pos < m->L, MT3_ERR_BAD_ARG, "mt3_debug_trace_step: pos must be in [2, %d)", m->L);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!m->trace) MT3_CUDA_CHECK(cudaMalloc(&m->trace, sizeof(unsigned long long) * kTraceSlots * kTraceWords));
+  if (!m->cap_stream) MT3_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+  // capture one greedy step with a trace slot baked into every GEMM / attention node
+  m->trace_names.clear();
+  m->tracing = true;
+  const uint64_t before = g_launch_count.load();
+  MT3_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int r = decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, m->cap_stream);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
+  m->tracing = false;
+  g_launch_count.store(before);
+  if (r != MT3_OK || e != cudaSuccess) {
+    if (g) cudaGraphDestroy(g);
+    return r != MT3_OK ? r : fail(MT3_ERR_CUDA, "mt3_debug_trace_step: capture -> %s", cudaGetErrorString(e));
+  }
+  cudaGraphExec_t ge = nullptr;
+  MT3_CUDA_CHECK(cudaGraphInstantiate(&ge, g, 0));
+  const int n = (int)m->trace_names.size();
+  const int start_pos = pos - 2;                      // two warm replays, the third one (at `pos`) is read back
+  MT3_CUDA_CHECK(cudaMemcpyAsync(m->state, &start_pos, sizeof(int), cudaMemcpyHostToDevice, s));
+  MT3_CUDA_CHECK(cudaMemsetAsync(m->finished, 0, sizeof(int) * m->B, s));
+  for (int it = 0; it < 3; ++it) {
+    trace_reset_kernel<<<cdiv(kTraceSlots * kTraceWords, 256), 256, 0, s>>>(m->trace, kTraceSlots);
+    MT3_CUDA_CHECK(cudaGraphLaunch(ge, s));
+  }
+  MT3_CUDA_CHECK(cudaStreamSynchronize(s));
+  const int n_out = std::min(n, (int)max_slots);
+  MT3_CUDA_CHECK(cudaMemcpy(out, m->trace, sizeof(unsigned long long) * n_out * kTraceWords, cudaMemcpyDeviceToHost));
+  std::string all;
+  for (int i = 0; i < n_out; ++i) { all += m->trace_names[i]; all += '\n'; }
+  snprintf(names, names_bytes, "%s", all.c_str());
+  *n_slots = n_out;
+  cudaGraphExecDestroy(ge);
+  cudaGraphDestroy(g);
   return MT3_OK;
 }
 
