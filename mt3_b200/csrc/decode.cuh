@@ -226,49 +226,83 @@ sgemm_dec_kernel(const DecGemmArgs p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cluster variant (the default on sm_100a): the S = K/KC CTAs of one 64 x 32 output tile form a
-// thread-block cluster (1, S, 1).  Each CTA computes its K chunk as above, parks the partial tile in
-// its own shared memory, and after one cluster barrier CTA r reduces rows [r*64/S, (r+1)*64/S) across
-// all S CTAs through distributed shared memory IN RANK ORDER (bit-reproducible), applies the fused
-// epilogue and stores.  No global scratch, no __threadfence, no atomic ticket, no second L2 pass.
+// Cluster variant (the default on sm_100a): the 8 CTAs of one 64 x 32 output tile form a thread-block
+// cluster (1, 8, 1) and split K.  Each CTA computes the partial tile of its K chunk, then PUSHES the 8 rows
+// owned by rank r into rank r's shared memory (st.shared::cluster); after ONE cluster barrier every rank sums
+// the 8 partials of its own rows from LOCAL shared memory in rank order (bit-reproducible), applies the
+// fused epilogue and stores.  No global scratch, no atomics, no second barrier (nobody reads remote memory
+// after the barrier, so a CTA may exit as soon as it is done).
+//
+// MODE 0: exact fp32 FMA (parity anchor).  MODE 1: 3xTF32 on the tensor cores (mma.sync m16n8k8: x = hi + lo,
+// hi*hi + hi*lo + lo*hi, fp32 accumulate: fp32-faithful, ~3e-6 relative) -- the measured FMA loop was
+// 1.4-3.6 us of a 4.6-8.4 us node (scripts/trace_step.py), the MMA version is ~0.3 us.  MODE 2: 1xTF32.
+// mma.sync and not tcgen05 on purpose: the tile is 64 x 32 x KC (KC <= 128) per CTA, 0.5 MFLOP; a TMEM
+// allocation + descriptor set-up + commit/ld round trip costs more than the whole MMA loop.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t cluster_map(uint32_t smem_addr, unsigned rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f2(uint32_t addr, float x, float y) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(x), "f"(y) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_f1(uint32_t addr, float x) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(x) : "memory");
+}
+
+constexpr int kDecLDB = kDecBN + 8;            // padded weight rows: conflict-free mma B-fragment reads
+constexpr int kDecRedFloats = 8 * 8 * kDecBN;  // [src rank][8 local rows][32 cols] partials pushed to this CTA
 template <int KC>
+constexpr size_t dec_cluster_smem() {
+  return (size_t)(kDecBM * (KC + 4) + KC * kDecLDB + kDecRedFloats + 64) * sizeof(float);
+}
+
+template <int KC, int MODE, bool TRACE>
 __global__ void __launch_bounds__(128)
 sgemm_dec_cluster_kernel(const DecGemmArgs p) {
-  constexpr int BM = kDecBM, BN = kDecBN, NT = 128, LDA = KC + 4;   // A rows padded: conflict-free 16-byte reads
+  constexpr int BM = kDecBM, BN = kDecBN, NT = 128, LDA = KC + 4, LDB = kDecLDB;
   constexpr int WQ = KC * 8 / NT;            // weight 16-byte copies per thread
   constexpr int AQ = KC * 16 / NT;           // activation 16-byte copies per thread
   extern __shared__ __align__(16) float dsm[];
-  float* As = dsm;                            // [BM][LDA] activations, row-major; later the partial tile
-  float* Bs = dsm + BM * LDA;                 // [KC][BN]
-  float* Ps = dsm;                            // [BM][BN] partial tile (aliases As after the k-loop)
-  float* Ss = dsm + BM * BN;                  // [BM] partial sums of squares
+  float* As = dsm;                            // [BM][LDA] activations, row-major
+  float* Bs = As + BM * LDA;                  // [KC][LDB] weights
+  float* Red = Bs + KC * LDB;                 // [8 src][8 rows][BN] partial tiles of MY rows (written by all ranks)
+  float* Rss = Red + kDecRedFloats;           // [8 src][8 rows] partial sums of squares of my rows
 
-  const unsigned S = gridDim.y;
   unsigned rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-  const int tid = threadIdx.x;
-  const int tx = tid % 8, ty = tid / 8;       // thread tile: rows ty + 16 i (i < 4), columns tx*4 .. +3
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = blockIdx.x * BN;
   const int kbeg = blockIdx.y * KC;
-  const bool tr = p.trace != nullptr && tid == 0;
+  const bool tr = TRACE && p.trace != nullptr && tid == 0;
   const bool tr0 = tr && blockIdx.x == 0 && blockIdx.y == 0;
   long long c0 = 0;
   if (tr) {
     atomicMin(p.trace, gtime_ns());
     c0 = clock64();
   }
+  // "I am running": peers may write into my shared memory once every CTA of the cluster has arrived here
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
 
-  // ---- load phase: cp.async (global -> shared, no register staging): every copy of the CTA's 8-16 KB of
-  // weights and 12-32 KB of activations is in flight at once; one wait.  Weights are issued BEFORE the PDL
-  // wait (they do not depend on the previous kernel).
+  // ---- load phase: cp.async (global -> shared, no register staging): all of the CTA's weights and activations
+  // are in flight at once; one wait.  Weights are issued BEFORE the PDL wait (they do not depend on the
+  // previous kernel).
 #pragma unroll
   for (int i = 0; i < WQ; ++i) {
     const int idx = tid + i * NT;
     const int kr = idx >> 3, nq = idx & 7;
     const bool ok = n0 + nq * 4 < p.N;
     const float* src = p.W + (long long)(kbeg + kr) * p.ldw + (ok ? n0 + nq * 4 : 0);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(&Bs[kr * BN + nq * 4])), "l"(src),
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(&Bs[kr * LDB + nq * 4])), "l"(src),
                  "r"(ok ? 16 : 0) : "memory");
   }
   pdl_wait();
@@ -286,124 +320,182 @@ sgemm_dec_cluster_kernel(const DecGemmArgs p) {
   __syncthreads();
   if (tr0) p.trace[2] = (unsigned long long)(clock64() - c0);      // loads landed
 
-  float acc[4][4];
+  // sum of squares of this CTA's K chunk: thread -> (row tid/2, half of the chunk), fixed order
+  float ss = 0.f;
+  if (p.norm) {
+    const float* ar = As + (tid >> 1) * LDA + (tid & 1) * (KC / 2);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+    for (int k = 0; k < KC / 2; k += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(ar + k);
+      ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    }
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  }
+
+  const uint32_t red_base = tc::smem_u32(Red) + rank * (8 * BN * 4);     // my slot [rank][..] in the owner's Red
+  const uint32_t rss_base = tc::smem_u32(Rss) + rank * (8 * 4);
+  if (MODE == 0) {
+    // ---- exact fp32: thread tile rows ty + 16 i (i < 4), columns tx*4 .. +3; k ascending ----
+    const int tx = tid % 8, ty = tid / 8;
+    float acc[4][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 #pragma unroll 4
-  for (int k = 0; k < KC; k += 4) {
-    float4 a[4], b[4];
+    for (int k = 0; k < KC; k += 4) {
+      float4 a[4], b[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(&As[(ty + 16 * i) * LDA + k]);
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(&As[(ty + 16 * i) * LDA + k]);
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) b[kk] = *reinterpret_cast<const float4*>(&Bs[(k + kk) * BN + tx * 4]);
+      for (int kk = 0; kk < 4; ++kk) b[kk] = *reinterpret_cast<const float4*>(&Bs[(k + kk) * LDB + tx * 4]);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
+      for (int i = 0; i < 4; ++i) {
+        const float av[4] = {a[i].x, a[i].y, a[i].z, a[i].w};
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {                  // k ascending: same summation order as a scalar k-loop
-        acc[i][0] = fmaf(av[kk], b[kk].x, acc[i][0]);
-        acc[i][1] = fmaf(av[kk], b[kk].y, acc[i][1]);
-        acc[i][2] = fmaf(av[kk], b[kk].z, acc[i][2]);
-        acc[i][3] = fmaf(av[kk], b[kk].w, acc[i][3]);
+        for (int kk = 0; kk < 4; ++kk) {
+          acc[i][0] = fmaf(av[kk], b[kk].x, acc[i][0]);
+          acc[i][1] = fmaf(av[kk], b[kk].y, acc[i][1]);
+          acc[i][2] = fmaf(av[kk], b[kk].z, acc[i][2]);
+          acc[i][3] = fmaf(av[kk], b[kk].w, acc[i][3]);
+        }
+      }
+    }
+    if (tr0) p.trace[3] = (unsigned long long)(clock64() - c0);    // FMA loop done
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");    // every peer is running
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                                  // row ty + 16 i -> owner rank, local row
+      const int row = ty + 16 * i;
+      st_cluster_f4(cluster_map(red_base + (uint32_t)(((row & 7) * BN + tx * 4) * 4), (unsigned)(row >> 3)),
+                    make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+    }
+  } else {
+    // ---- tensor cores: warp w owns rows 16w .. 16w+15, all 32 columns (4 n8 tiles) ----
+    const int g = lane >> 2, t = lane & 3;
+    float acc[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
+    const float* a_lo_row = As + (warp * 16 + g) * LDA + t;
+    const float* a_hi_row = a_lo_row + 8 * LDA;
+#pragma unroll 2
+    for (int k = 0; k < KC; k += 8) {
+      const float af[4] = {a_lo_row[k], a_hi_row[k], a_lo_row[k + 4], a_hi_row[k + 4]};   // a0..a3
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float hi, lo;
+        split_tf32(af[e], hi, lo);
+        ah[e] = __float_as_uint(hi);
+        al[e] = __float_as_uint(lo);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float bf[2] = {Bs[(k + t) * LDB + j * 8 + g], Bs[(k + t + 4) * LDB + j * 8 + g]};
+        uint32_t bh[2], bl[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          float hi, lo;
+          split_tf32(bf[e], hi, lo);
+          bh[e] = __float_as_uint(hi);
+          bl[e] = __float_as_uint(lo);
+        }
+        if (MODE == 1) {                       // small terms first
+          mma_tf32_16x8x8(acc[j], al, bh);
+          mma_tf32_16x8x8(acc[j], ah, bl);
+        }
+        mma_tf32_16x8x8(acc[j], ah, bh);
+      }
+    }
+    if (tr0) p.trace[3] = (unsigned long long)(clock64() - c0);    // MMA loop done
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");    // every peer is running
+    // c0,c1: row 16w+g -> rank 2w, local row g;  c2,c3: row 16w+g+8 -> rank 2w+1, local row g
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t off = (uint32_t)((g * BN + j * 8 + 2 * t) * 4);
+      st_cluster_f2(cluster_map(red_base + off, (unsigned)(2 * warp)), acc[j][0], acc[j][1]);
+      st_cluster_f2(cluster_map(red_base + off, (unsigned)(2 * warp + 1)), acc[j][2], acc[j][3]);
+    }
+  }
+  if (p.norm && (tid & 1) == 0) {
+    const int row = tid >> 1;
+    st_cluster_f1(cluster_map(rss_base + (uint32_t)((row & 7) * 4), (unsigned)(row >> 3)), ss);
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (tr0) p.trace[4] = (unsigned long long)(clock64() - c0);      // partials exchanged
+
+  // ---- sum my 8 rows over the 8 source ranks (rank order, local shared memory) + fused epilogue ----
+  {
+    const int rl = tid >> 4, c2 = (tid & 15) * 2;
+    const int m = (int)rank * 8 + rl, n = n0 + c2;
+    float2 v = make_float2(0.f, 0.f);
+    float sst = 0.f;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+      const float2 q = *reinterpret_cast<const float2*>(&Red[(s * 8 + rl) * BN + c2]);
+      v.x += q.x; v.y += q.y;
+      if (p.norm) sst += Rss[s * 8 + rl];
+    }
+    if (m < p.M && n < p.N) {
+      const float rs = p.norm ? 1.0f / sqrtf(sst / (float)p.K + p.eps) : 1.f;
+      v.x *= rs; v.y *= rs;
+      if (p.epi == EPI_GATED_GELU) {
+        p.C[(long long)m * p.ldc + (n >> 1)] = gelu_tanh(v.x) * v.y;
+      } else {
+        if (p.epi == EPI_RESIDUAL) {
+          const float2 q = *reinterpret_cast<const float2*>(p.R + (long long)m * p.ldr + n);
+          v.x += q.x; v.y += q.y;
+        }
+        if (n < p.n_split) {
+          *reinterpret_cast<float2*>(p.C + (long long)m * p.ldc + n) = v;
+        } else {
+          const int pos = p.hm_pos ? *p.hm_pos : 0;
+          *reinterpret_cast<float2*>(p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos)) = v;
+        }
       }
     }
   }
-  // sum of squares of this CTA's K chunk, row tid (sequential over k: deterministic)
-  float ss = 0.f;
-  if (p.norm && tid < BM) {
-#pragma unroll 8
-    for (int k = 0; k < KC; ++k) {
-      const float v = As[tid * LDA + k];
-      ss = fmaf(v, v, ss);
-    }
-  }
-  __syncthreads();                              // everyone is done reading As: recycle it as the partial tile
-  if (tr0) p.trace[3] = (unsigned long long)(clock64() - c0);      // FMA loop done
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<float4*>(&Ps[(ty + 16 * i) * BN + tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-  if (tid < BM) Ss[tid] = ss;
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-  if (tr0) p.trace[4] = (unsigned long long)(clock64() - c0);      // cluster barrier passed
-
-  // ---- reduce my rows across the cluster (rank order) + fused epilogue ----
-  const int rows_per_rank = BM / (int)S;
-  const int c2 = (tid & 15) * 2;
-  const int n = n0 + c2;
-  for (int rl = tid >> 4; rl < rows_per_rank; rl += 8) {
-    const int m = (int)rank * rows_per_rank + rl;
-    float2 v = make_float2(0.f, 0.f);
-    float sst = 0.f;
-    const uint32_t my_p = tc::smem_u32(&Ps[m * BN + c2]);
-    const uint32_t my_s = tc::smem_u32(&Ss[m]);
-    // all 8 remote loads are issued before the first add (one DSMEM latency, not eight); the sum itself
-    // stays in rank order.  The cluster kernel is only ever launched with S == 8.
-    float2 t[8];
-    float tss[8];
-#pragma unroll
-    for (unsigned s = 0; s < 8; ++s) {
-      uint32_t rp, rs_addr;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rp) : "r"(my_p), "r"(s));
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rs_addr) : "r"(my_s), "r"(s));
-      asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(t[s].x), "=f"(t[s].y) : "r"(rp));
-      asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(tss[s]) : "r"(rs_addr));
-    }
-#pragma unroll
-    for (unsigned s = 0; s < 8; ++s) {
-      v.x += t[s].x; v.y += t[s].y; sst += tss[s];
-    }
-    if (m >= p.M || n >= p.N) continue;
-    const float rs = p.norm ? 1.0f / sqrtf(sst / (float)p.K + p.eps) : 1.f;
-    v.x *= rs; v.y *= rs;
-    if (p.epi == EPI_GATED_GELU) {
-      p.C[(long long)m * p.ldc + (n >> 1)] = gelu_tanh(v.x) * v.y;
-      continue;
-    }
-    if (p.epi == EPI_RESIDUAL) {
-      const float2 q = *reinterpret_cast<const float2*>(p.R + (long long)m * p.ldr + n);
-      v.x += q.x; v.y += q.y;
-    }
-    if (n < p.n_split) {
-      *reinterpret_cast<float2*>(p.C + (long long)m * p.ldc + n) = v;
-    } else {
-      const int pos = p.hm_pos ? *p.hm_pos : 0;
-      *reinterpret_cast<float2*>(p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos)) = v;
-    }
-  }
-  if (tr0) p.trace[5] = (unsigned long long)(clock64() - c0);      // DSMEM reduce + epilogue stores issued
-  // nobody may exit (and release its shared memory) while a peer can still be reading it
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (tr) {
-    if (tr0) p.trace[6] = (unsigned long long)(clock64() - c0);
+    if (tr0) p.trace[5] = (unsigned long long)(clock64() - c0);    // reduce + epilogue stores issued
     atomicMax(p.trace + 1, gtime_ns());
   }
 }
 
-template <int KC>
-inline int launch_dec_gemm_cluster_kc(const DecGemmArgs& a, int S, cudaStream_t s, bool pdl) {
-  constexpr size_t smem = (size_t)(kDecBM * (KC + 4) + KC * kDecBN) * sizeof(float);
+template <int KC, int MODE>
+inline int launch_dec_gemm_cluster_kc(const DecGemmArgs& a, cudaStream_t s, bool pdl) {
+  constexpr size_t smem = dec_cluster_smem<KC>();
   static bool attr_done = false;
   if (!attr_done) {
-    MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster_kernel<KC, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster_kernel<KC, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  MT3_CUDA_CHECK(launch_kernel_cluster(sgemm_dec_cluster_kernel<KC>, dim3(cdiv(a.N, kDecBN), S), dim3(128), smem, s, pdl,
-                                       (unsigned)S, a));
+  if (a.trace)
+    MT3_CUDA_CHECK(launch_kernel_cluster(sgemm_dec_cluster_kernel<KC, MODE, true>, dim3(cdiv(a.N, kDecBN), 8), dim3(128), smem, s, pdl, 8u, a));
+  else
+    MT3_CUDA_CHECK(launch_kernel_cluster(sgemm_dec_cluster_kernel<KC, MODE, false>, dim3(cdiv(a.N, kDecBN), 8), dim3(128), smem, s, pdl, 8u, a));
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }
 
-// Returns MT3_ERR_UNSUPPORTED (without launching) when K does not split into 8 chunks of 48/64/128.
-inline int launch_dec_gemm_cluster(const DecGemmArgs& a, cudaStream_t s, bool pdl) {
-  if (a.M > kDecBM || a.N % 4 != 0 || a.lda % 4 != 0 || a.ldw % 4 != 0 || a.n_split % 4 != 0 || a.K % 8 != 0) return MT3_ERR_UNSUPPORTED;
+template <int MODE>
+inline int launch_dec_gemm_cluster_mode(const DecGemmArgs& a, cudaStream_t s, bool pdl) {
   switch (a.K / 8) {
-    case 48: return launch_dec_gemm_cluster_kc<48>(a, 8, s, pdl);
-    case 64: return launch_dec_gemm_cluster_kc<64>(a, 8, s, pdl);
-    case 128: return launch_dec_gemm_cluster_kc<128>(a, 8, s, pdl);
+    case 48: return launch_dec_gemm_cluster_kc<48, MODE>(a, s, pdl);
+    case 64: return launch_dec_gemm_cluster_kc<64, MODE>(a, s, pdl);
+    case 128: return launch_dec_gemm_cluster_kc<128, MODE>(a, s, pdl);
     default: return MT3_ERR_UNSUPPORTED;
   }
+}
+
+// mode: 0 exact fp32 FMA, 1 3xTF32 mma, 2 1xTF32 mma.  Returns MT3_ERR_UNSUPPORTED (without launching) when K
+// does not split into 8 chunks of 48/64/128.
+inline int launch_dec_gemm_cluster(const DecGemmArgs& a, int mode, cudaStream_t s, bool pdl) {
+  if (a.M > kDecBM || a.N % 4 != 0 || a.lda % 4 != 0 || a.ldw % 4 != 0 || a.n_split % 4 != 0 || a.K % 8 != 0) return MT3_ERR_UNSUPPORTED;
+  if (mode == 1) return launch_dec_gemm_cluster_mode<1>(a, s, pdl);
+  if (mode == 2) return launch_dec_gemm_cluster_mode<2>(a, s, pdl);
+  return launch_dec_gemm_cluster_mode<0>(a, s, pdl);
 }
 
 // One CTA per (32-column tile, 64-deep K chunk).
@@ -450,6 +542,7 @@ inline size_t dec_attention_smem(int max_len) {
 
 // q [B, ldq], head h at column q_off + h*64.  kv: head-major [b][2][H][cap][64].  out [B, ldo].
 // len = (len_ptr ? *len_ptr : 0) + len_add.
+template <bool TRACE>
 __global__ void __launch_bounds__(kAttThreads)
 dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const float* __restrict__ kv, int H, int cap,
                           const int* __restrict__ len_ptr, int len_add, int max_len, float* __restrict__ out, int ldo,
@@ -468,7 +561,7 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
   const int nt = (len + kAttKT - 1) / kAttKT;
   const float* kbase = kv + (((long long)b * 2 + 0) * H + h) * (long long)cap * 64;
   const float* vbase = kv + (((long long)b * 2 + 1) * H + h) * (long long)cap * 64;
-  const bool tr = trace != nullptr && tid == 0;
+  const bool tr = TRACE && trace != nullptr && tid == 0;
   const bool tr0 = tr && blockIdx.x == 0 && blockIdx.y == 0;
   long long c0 = 0;
   if (tr) {

@@ -129,12 +129,14 @@ __device__ __forceinline__ void mega_gemm_tile(const DecGemmArgs& p, int tile, u
         }
       }
     }
-    if (p.norm && tid < BM) {
-#pragma unroll 8
-      for (int k = 0; k < KC; ++k) {
-        const float v = As[tid * LDA + k];
-        ss = fmaf(v, v, ss);
+    if (p.norm) {        // same order as sgemm_dec_cluster_kernel: thread -> (row tid/2, half of the chunk)
+      const float* ar = As + (tid >> 1) * LDA + (tid & 1) * (KC / 2);
+#pragma unroll
+      for (int k = 0; k < KC / 2; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(ar + k);
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
       }
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
     }
   }
   __syncthreads();
@@ -142,7 +144,7 @@ __device__ __forceinline__ void mega_gemm_tile(const DecGemmArgs& p, int tile, u
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       *reinterpret_cast<float4*>(&Ps[(ty + 16 * i) * BN + tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-    if (tid < BM) Ss[tid] = ss;
+    if ((tid & 1) == 0) Ss[tid >> 1] = ss;
   }
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (worker) {

@@ -91,6 +91,8 @@ struct Model {
   bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between all decode-step kernels
   bool pdl_attn = false;          // MT3_PDL=2: only the attention launches (K/V prefetch under the preceding GEMM)
   bool pdl_gemm = false;          // MT3_PDL=4: only the GEMM launches; bits combine (6 = attention + GEMM)
+  int dec_gemm_mode = 0;          // decode GEMM arithmetic: 0 fp32 FMA, 1 3xTF32 mma, 2 1xTF32 mma (follows gemm_mode;
+                                  // MT3_DEC_GEMM_MODE overrides)
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
   int dec_streams = 1;            // MT3_DEC_STREAMS=n: decode step runs as n concurrent sub-batches
   // debug timeline (mt3_debug_trace_step): while `tracing` is set every decode GEMM / attention launch gets a slot
@@ -391,7 +393,7 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
     a.partial = m->dpartial + (int64_t)rows.stream_idx * m->dpartial_stride;      // per-stream split-K scratch
     a.counters = m->dcounters + (int64_t)rows.stream_idx * m->dcounters_stride;
     a.trace = trace_slot(m, K == m->F ? "gemm_mlp_out" : (N == 2 * m->F ? "gemm_mlp_in" : (kv ? "gemm_qkv_append" : (N == m->V ? "gemm_logits" : (K == m->Q ? "gemm_attn_out" : "gemm_cross_q")))));
-    int rc = m->dec_cluster ? launch_dec_gemm_cluster(a, s, m->pdl_gemm) : MT3_ERR_UNSUPPORTED;
+    int rc = m->dec_cluster ? launch_dec_gemm_cluster(a, m->dec_gemm_mode, s, m->pdl_gemm) : MT3_ERR_UNSUPPORTED;
     if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, splits, s, m->pdl_gemm);   // shapes the cluster kernel does not tile
     MT3_TRY(rc);
   }
@@ -404,11 +406,13 @@ static int launch_dec_attention(Model* m, const float* q, const float* kv, int c
   const int max_len = std::max(m->L, m->T);
   const size_t smem = dec_attention_smem(max_len);
   if (!attr_done) {
-    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
   MT3_REQUIRE(smem <= 100 * 1024, MT3_ERR_UNSUPPORTED, "decode attention: length %d too long", max_len);
-  MT3_CUDA_CHECK(launch_kernel(dec_attention_bulk_kernel, dim3(m->H, rows.count), dim3(kAttThreads), smem, s, m->pdl_attn,
+  MT3_CUDA_CHECK(launch_kernel(m->tracing ? dec_attention_bulk_kernel<true> : dec_attention_bulk_kernel<false>, dim3(m->H, rows.count),
+                               dim3(kAttThreads), smem, s, m->pdl_attn,
                                q + (int64_t)rows.begin * m->Q, m->Q, 0, kv + (int64_t)rows.begin * 2 * m->H * cap * 64, m->H, cap,
                                len_ptr, len_add, max_len, out + (int64_t)rows.begin * m->Q, m->Q,
                                trace_slot(m, len_ptr ? "attn_self" : "attn_cross")));
@@ -870,6 +874,8 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     if (e_ns && e_ns[0] >= '1' && e_ns[0] <= '4') m->dec_streams = e_ns[0] - '0';
     const char* e_clu = getenv("MT3_DEC_CLUSTER");
     m->dec_cluster = !(e_clu && e_clu[0] == '0');
+    m->dec_gemm_mode = cfg->gemm_mode == MT3_GEMM_TF32X3 ? 1 : (cfg->gemm_mode == MT3_GEMM_TF32 ? 2 : 0);
+    if (const char* e_dgm = getenv("MT3_DEC_GEMM_MODE")) m->dec_gemm_mode = std::max(0, std::min(2, atoi(e_dgm)));
     const char* e_attn = getenv("MT3_TC_ATTENTION");
     m->tc_attn_ok = !(e_attn && e_attn[0] == '0');
   }

@@ -32,7 +32,7 @@ def main():
         t = out[:n.value].astype(np.int64)
         t0 = t[0, 0]
         print(f"\n== decode step at cache position {pos}: {n.value} traced nodes (B={B})")
-        print(f"{'node':18s} {'start':>8s} {'dur':>7s} {'gap':>6s} | CTA(0,0) phases us: " "gemm: loads fma barrier reduce exit | attn: first-K pass1 softmax pass2 exit")
+        print(f"{'node':18s} {'start':>8s} {'dur':>7s} {'gap':>6s} | CTA(0,0) phases us: " "gemm: loads compute exchange reduce - | attn: first-K pass1 softmax pass2 exit")
         prev_end = t0
         agg = {}
         for i in range(n.value):
