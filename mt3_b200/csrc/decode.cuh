@@ -266,6 +266,41 @@ constexpr size_t dec_cluster_smem() {
   return (size_t)(kDecBM * (KC + 4) + KC * kDecLDB + kDecRedFloats + 64) * sizeof(float);
 }
 
+// Sum this rank's 8 rows over the 8 source ranks (rank order, local shared memory) and apply the fused epilogue:
+// RMSNorm row factor, gated-GELU / residual, plain store or head-major KV-cache append.  128 threads.
+__device__ __forceinline__ void dec_reduce_epilogue(const DecGemmArgs& p, const float* Red, const float* Rss, unsigned rank, int n0) {
+  constexpr int BN = kDecBN;
+  const int tid = threadIdx.x;
+  const int rl = tid >> 4, c2 = (tid & 15) * 2;
+  const int m = (int)rank * 8 + rl, n = n0 + c2;
+  float2 v = make_float2(0.f, 0.f);
+  float sst = 0.f;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const float2 q = *reinterpret_cast<const float2*>(&Red[(s * 8 + rl) * BN + c2]);
+    v.x += q.x; v.y += q.y;
+    if (p.norm) sst += Rss[s * 8 + rl];
+  }
+  if (m < p.M && n < p.N) {
+    const float rs = p.norm ? 1.0f / sqrtf(sst / (float)p.K + p.eps) : 1.f;
+    v.x *= rs; v.y *= rs;
+    if (p.epi == EPI_GATED_GELU) {
+      p.C[(long long)m * p.ldc + (n >> 1)] = gelu_tanh(v.x) * v.y;
+    } else {
+      if (p.epi == EPI_RESIDUAL) {
+        const float2 q = *reinterpret_cast<const float2*>(p.R + (long long)m * p.ldr + n);
+        v.x += q.x; v.y += q.y;
+      }
+      if (n < p.n_split) {
+        *reinterpret_cast<float2*>(p.C + (long long)m * p.ldc + n) = v;
+      } else {
+        const int pos = p.hm_pos ? *p.hm_pos : 0;
+        *reinterpret_cast<float2*>(p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos)) = v;
+      }
+    }
+  }
+}
+
 template <int KC, int MODE, bool TRACE>
 __global__ void __launch_bounds__(128)
 sgemm_dec_cluster_kernel(const DecGemmArgs p) {
@@ -425,37 +460,7 @@ sgemm_dec_cluster_kernel(const DecGemmArgs p) {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (tr0) p.trace[4] = (unsigned long long)(clock64() - c0);      // partials exchanged
 
-  // ---- sum my 8 rows over the 8 source ranks (rank order, local shared memory) + fused epilogue ----
-  {
-    const int rl = tid >> 4, c2 = (tid & 15) * 2;
-    const int m = (int)rank * 8 + rl, n = n0 + c2;
-    float2 v = make_float2(0.f, 0.f);
-    float sst = 0.f;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-      const float2 q = *reinterpret_cast<const float2*>(&Red[(s * 8 + rl) * BN + c2]);
-      v.x += q.x; v.y += q.y;
-      if (p.norm) sst += Rss[s * 8 + rl];
-    }
-    if (m < p.M && n < p.N) {
-      const float rs = p.norm ? 1.0f / sqrtf(sst / (float)p.K + p.eps) : 1.f;
-      v.x *= rs; v.y *= rs;
-      if (p.epi == EPI_GATED_GELU) {
-        p.C[(long long)m * p.ldc + (n >> 1)] = gelu_tanh(v.x) * v.y;
-      } else {
-        if (p.epi == EPI_RESIDUAL) {
-          const float2 q = *reinterpret_cast<const float2*>(p.R + (long long)m * p.ldr + n);
-          v.x += q.x; v.y += q.y;
-        }
-        if (n < p.n_split) {
-          *reinterpret_cast<float2*>(p.C + (long long)m * p.ldc + n) = v;
-        } else {
-          const int pos = p.hm_pos ? *p.hm_pos : 0;
-          *reinterpret_cast<float2*>(p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos)) = v;
-        }
-      }
-    }
-  }
+  dec_reduce_epilogue(p, Red, Rss, rank, n0);
   if (tr) {
     if (tr0) p.trace[5] = (unsigned long long)(clock64() - c0);    // reduce + epilogue stores issued
     atomicMax(p.trace + 1, gtime_ns());

@@ -13,12 +13,15 @@
 #include <math.h>
 #include <string>
 #include <vector>
+#include <map>
+#include <tuple>
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "attention_tc.cuh"
 #include "decode.cuh"
+#include "decode_tc.cuh"
 #include "decode_chain.cuh"
 #include "decode_mega.cuh"
 #include "layers.cuh"
@@ -85,6 +88,10 @@ struct Model {
   int D, H, Q, F, V, Le, Ld, L;
   float* slab = nullptr;          // all prepared weights
   float* slab_tc = nullptr;       // K-major (and hi/lo) copies for the tcgen05 path
+  float* slab_dect = nullptr;     // K-major fp32 copies W^T [N, K] of the decoder's step weights (tcgen05 decode GEMM)
+  bool dec_tc = true;             // MT3_DEC_TC=0: tensor-core decode modes use the mma.sync kernel instead of tcgen05
+  std::map<const float*, const float*> dec_wt;                                   // [K, N] weight -> its W^T copy
+  std::map<std::tuple<const void*, int, int, int>, CUtensorMap> dec_maps;       // (ptr, rows, K, ld) -> TMA map
   bool tc = false, split3 = false;
   TcW t_w_in;
   Act a_x, a_h, a_ao, a_g, a_enc, a_qkv, a_vt; // tcgen05-path activation buffers (workspace); a_vt = per-head V^T
@@ -376,6 +383,19 @@ static unsigned long long* trace_slot(Model* m, const char* name) {
   return m->trace + (size_t)(m->trace_names.size() - 1) * kTraceWords;
 }
 
+// TMA map of an [rows, K] fp32 operand (leading dimension ld), box 32 floats x box_rows; built once and cached.
+static int dec_tmap(Model* m, const float* ptr, int rows, int K, int ld, int box_rows, CUtensorMap* out) {
+  const auto key = std::make_tuple((const void*)ptr, rows, K, ld);
+  auto it = m->dec_maps.find(key);
+  if (it == m->dec_maps.end()) {
+    CUtensorMap tm;
+    MT3_TRY(make_tmap_2d(&tm, ptr, (uint64_t)rows, (uint64_t)K, (uint64_t)ld, (uint32_t)box_rows));
+    it = m->dec_maps.emplace(key, tm).first;
+  }
+  *out = it->second;
+  return MT3_OK;
+}
+
 static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, int K, int norm, int epi, float* C, int ldc,
                     int n_split, float* kv, const int* pos, const Rows& rows, cudaStream_t s) {
   const int splits = dec_gemm_splits(N, K, m->sm_count);
@@ -393,7 +413,17 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
     a.partial = m->dpartial + (int64_t)rows.stream_idx * m->dpartial_stride;      // per-stream split-K scratch
     a.counters = m->dcounters + (int64_t)rows.stream_idx * m->dcounters_stride;
     a.trace = trace_slot(m, K == m->F ? "gemm_mlp_out" : (N == 2 * m->F ? "gemm_mlp_in" : (kv ? "gemm_qkv_append" : (N == m->V ? "gemm_logits" : (K == m->Q ? "gemm_attn_out" : "gemm_cross_q")))));
-    int rc = m->dec_cluster ? launch_dec_gemm_cluster(a, m->dec_gemm_mode, s, m->pdl_gemm) : MT3_ERR_UNSUPPORTED;
+    int rc = MT3_ERR_UNSUPPORTED;
+    if (m->dec_cluster && m->dec_gemm_mode >= 1 && m->dec_tc && dec_gemm_tc_supported(a)) {
+      const auto wt = m->dec_wt.find(W);
+      if (wt != m->dec_wt.end()) {
+        DecTcMaps maps;
+        MT3_TRY(dec_tmap(m, a.A, a.M, K, lda, kDecBM, &maps.a));
+        MT3_TRY(dec_tmap(m, wt->second, N, K, K, kDecBN, &maps.b));
+        rc = launch_dec_gemm_tc(maps, a, m->dec_gemm_mode, s, m->pdl_gemm);
+      }
+    }
+    if (rc == MT3_ERR_UNSUPPORTED && m->dec_cluster) rc = launch_dec_gemm_cluster(a, m->dec_gemm_mode, s, m->pdl_gemm);
     if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, splits, s, m->pdl_gemm);   // shapes the cluster kernel does not tile
     MT3_TRY(rc);
   }
@@ -901,6 +931,33 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
       if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: tc weight prep -> %s", cudaGetErrorString(e));
     }
   }
+  {
+    const char* e_dtc = getenv("MT3_DEC_TC");
+    m->dec_tc = !(e_dtc && e_dtc[0] == '0');
+  }
+  if (rc == MT3_OK && m->dec_gemm_mode >= 1 && m->dec_tc) {
+    // K-major copies of the decode-step weights for the tcgen05 decode GEMM (decode_tc.cuh)
+    const int64_t n_dect = (int64_t)m->Ld * ((int64_t)D * 3 * Q + (int64_t)Q * D + (int64_t)D * Q + (int64_t)Q * D + (int64_t)D * 2 * F + (int64_t)F * D) + (int64_t)D * V;
+    e = cudaMalloc((void**)&m->slab_dect, (size_t)n_dect * sizeof(float));
+    if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: cudaMalloc(decode W^T) -> %s", cudaGetErrorString(e));
+    float* cur = m->slab_dect;
+    auto tr = [&](const float* w, int K, int N) {
+      if (rc != MT3_OK) return;
+      transpose_split_kernel<<<dim3(cdiv(N, 32), cdiv(K, 32)), dim3(32, 8), 0, s>>>(w, K, N, cur, nullptr);
+      if (cudaGetLastError() != cudaSuccess) { rc = fail(MT3_ERR_CUDA, "mt3_model_create: decode W^T prep launch failed"); return; }
+      m->dec_wt[w] = cur;
+      cur += (int64_t)K * N;
+    };
+    for (int i = 0; i < m->Ld; ++i) {
+      const DecLayer& L = m->dec[i];
+      tr(L.wqkv, D, 3 * Q); tr(L.wo, Q, D); tr(L.wq_c, D, Q); tr(L.wo_c, Q, D); tr(L.wi, D, 2 * F); tr(L.wo2, F, D);
+    }
+    tr(m->w_logits, D, V);
+    if (rc == MT3_OK) {
+      e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: decode W^T prep -> %s", cudaGetErrorString(e));
+    }
+  }
   if (rc == MT3_OK) {
     e = cudaMallocHost((void**)&m->h_flag, 4 * sizeof(int));
     if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: cudaMallocHost -> %s", cudaGetErrorString(e));
@@ -908,6 +965,7 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
   if (rc != MT3_OK) {
     cudaFree(m->slab);
     cudaFree(m->slab_tc);
+    cudaFree(m->slab_dect);
     delete m;
     return rc;
   }
@@ -928,6 +986,7 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
   if (m->h_flag) cudaFreeHost(m->h_flag);
   cudaFree(m->slab);
   cudaFree(m->slab_tc);
+  cudaFree(m->slab_dect);
   delete m;
   return MT3_OK;
 }
