@@ -904,7 +904,10 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     if (e_ns && e_ns[0] >= '1' && e_ns[0] <= '4') m->dec_streams = e_ns[0] - '0';
     const char* e_clu = getenv("MT3_DEC_CLUSTER");
     m->dec_cluster = !(e_clu && e_clu[0] == '0');
-    m->dec_gemm_mode = cfg->gemm_mode == MT3_GEMM_TF32X3 ? 1 : (cfg->gemm_mode == MT3_GEMM_TF32 ? 2 : 0);
+    // The decode-step GEMMs are latency-bound (0.5 MFLOP per CTA): exact fp32 FMA is as fast as the tensor-core
+    // variants (measured: FMA 526, mma.sync 3xTF32 521, tcgen05 3xTF32 678 ms/step), so every gemm_mode decodes in
+    // exact fp32 unless MT3_DEC_GEMM_MODE asks for 1 (3xTF32) / 2 (1xTF32).
+    m->dec_gemm_mode = 0;
     if (const char* e_dgm = getenv("MT3_DEC_GEMM_MODE")) m->dec_gemm_mode = std::max(0, std::min(2, atoi(e_dgm)));
     const char* e_attn = getenv("MT3_TC_ATTENTION");
     m->tc_attn_ok = !(e_attn && e_attn[0] == '0');

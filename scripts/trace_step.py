@@ -41,7 +41,7 @@ def main():
             dur, gap = (en - st) / 1e3, (st - prev_end) / 1e3
             a = agg.setdefault(nm[i], [0, 0.0, 0.0, np.zeros(5)])
             a[0] += 1; a[1] += dur; a[2] += gap; a[3] += ph
-            if i < 10 or i >= n.value - 3:
+            if i < int(os.environ.get('TRACE_ROWS', '10')) or i >= n.value - 3:
                 print(f"{nm[i]:18s} {(st - t0) / 1e3:8.2f} {dur:7.2f} {gap:6.2f} | " + " ".join(f"{x:6.2f}" for x in ph))
             prev_end = en
         total = (t[-1, 1] - t0) / 1e3
