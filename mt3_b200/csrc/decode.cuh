@@ -38,6 +38,12 @@ struct DecGemmArgs {
   int n_split; float* C1; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;
   float* partial;                 // [splits][n_tiles][64*32 + 64] scratch
   int* counters;                  // [n_tiles], zero on entry, left zero on exit
+  // optional second activation source: columns [K0, K) of the virtual A come from A2[:, k - K0] (fused launches
+  // multiply the concatenation [o | y] by a precomposed weight block); A2 == nullptr -> single source
+  const float* A2; int lda2; int K0;
+  // optional: per (row, 32-column tile) sum of squares of the OUTPUT row slice, [M][ssq_ld]; the consumer of the
+  // output sums the N/32 partials in order and gets the RMSNorm statistic without re-reading the row
+  float* ssq_out; int ssq_ld;
   unsigned long long* trace;      // debug timeline slot (mt3_debug_trace_step) or null: [0] min start, [1] max end (ns,
                                   // %globaltimer); [2..6] clock64 deltas of CTA (0,0) at its phase boundaries
 };
@@ -281,7 +287,8 @@ __device__ __forceinline__ void dec_reduce_epilogue(const DecGemmArgs& p, const 
     v.x += q.x; v.y += q.y;
     if (p.norm) sst += Rss[s * 8 + rl];
   }
-  if (m < p.M && n < p.N) {
+  const bool valid = m < p.M && n < p.N;
+  if (valid) {
     const float rs = p.norm ? 1.0f / sqrtf(sst / (float)p.K + p.eps) : 1.f;
     v.x *= rs; v.y *= rs;
     if (p.epi == EPI_GATED_GELU) {
@@ -299,11 +306,18 @@ __device__ __forceinline__ void dec_reduce_epilogue(const DecGemmArgs& p, const 
       }
     }
   }
+  if (p.ssq_out) {                      // 16 lanes share a row: fixed butterfly order
+    float sq = valid ? fmaf(v.x, v.x, v.y * v.y) : 0.f;
+    sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+    if ((tid & 15) == 0 && m < p.M) p.ssq_out[(long long)m * p.ssq_ld + n0 / BN] = sq;
+  }
 }
 
 template <int KC, int MODE, bool TRACE>
-__global__ void __launch_bounds__(128)
-sgemm_dec_cluster_kernel(const DecGemmArgs p) {
+__device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int tile_x) {
   constexpr int BM = kDecBM, BN = kDecBN, NT = 128, LDA = KC + 4, LDB = kDecLDB;
   constexpr int WQ = KC * 8 / NT;            // weight 16-byte copies per thread
   constexpr int AQ = KC * 16 / NT;           // activation 16-byte copies per thread
@@ -316,10 +330,10 @@ sgemm_dec_cluster_kernel(const DecGemmArgs p) {
   unsigned rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n0 = blockIdx.x * BN;
+  const int n0 = tile_x * BN;
   const int kbeg = blockIdx.y * KC;
   const bool tr = TRACE && p.trace != nullptr && tid == 0;
-  const bool tr0 = tr && blockIdx.x == 0 && blockIdx.y == 0;
+  const bool tr0 = tr && tile_x == 0 && blockIdx.y == 0;
   long long c0 = 0;
   if (tr) {
     atomicMin(p.trace, gtime_ns());
@@ -347,7 +361,9 @@ sgemm_dec_cluster_kernel(const DecGemmArgs p) {
     const int idx = tid + i * NT;
     const int row = idx / (KC / 4), kq = idx % (KC / 4);
     const bool ok = row < p.M;
-    const float* src = p.A + (long long)(ok ? row : 0) * p.lda + kbeg + kq * 4;
+    const int col = kbeg + kq * 4;
+    const float* src = (p.A2 != nullptr && col >= p.K0) ? p.A2 + (long long)(ok ? row : 0) * p.lda2 + (col - p.K0)
+                                                         : p.A + (long long)(ok ? row : 0) * p.lda + col;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(&As[row * LDA + kq * 4])), "l"(src),
                  "r"(ok ? 16 : 0) : "memory");
   }
@@ -467,6 +483,44 @@ sgemm_dec_cluster_kernel(const DecGemmArgs p) {
   }
 }
 
+template <int KC, int MODE, bool TRACE>
+__global__ void __launch_bounds__(128)
+sgemm_dec_cluster_kernel(const DecGemmArgs p) {
+  dec_cluster_body<KC, MODE, TRACE>(p, (int)blockIdx.x);
+}
+
+// Two independent GEMMs that read the same inputs in ONE launch (column tiles [0, tiles0) belong to p0, the rest to
+// p1): used for  y' = y + o.Wo  together with  q_raw = [o | y].[Wo.Wq ; Wq]  (the out-projection folded into the
+// next projection with a precomposed weight block), which removes a kernel from the dependency chain.
+template <int KC0, int KC1, int MODE, bool TRACE>
+__global__ void __launch_bounds__(128)
+sgemm_dec_cluster2_kernel(const DecGemmArgs p0, const DecGemmArgs p1, const int tiles0) {
+  if ((int)blockIdx.x < tiles0) dec_cluster_body<KC0, MODE, TRACE>(p0, (int)blockIdx.x);
+  else dec_cluster_body<KC1, MODE, TRACE>(p1, (int)blockIdx.x - tiles0);
+}
+
+template <int KC0, int KC1, int MODE>
+inline int launch_dec_gemm_cluster2(const DecGemmArgs& a0, const DecGemmArgs& a1, cudaStream_t s, bool pdl) {
+  constexpr size_t smem = dec_cluster_smem<(KC0 > KC1 ? KC0 : KC1)>();
+  if (a0.M > kDecBM || a1.M > kDecBM || a0.K != 8 * KC0 || a1.K != 8 * KC1 || a0.N % kDecBN != 0 || a1.N % kDecBN != 0)
+    return MT3_ERR_UNSUPPORTED;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster2_kernel<KC0, KC1, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster2_kernel<KC0, KC1, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int tiles0 = a0.N / kDecBN, tiles1 = a1.N / kDecBN;
+  if (a0.trace)
+    MT3_CUDA_CHECK(launch_kernel_cluster(sgemm_dec_cluster2_kernel<KC0, KC1, MODE, true>, dim3(tiles0 + tiles1, 8), dim3(128), smem, s,
+                                         pdl, 8u, a0, a1, tiles0));
+  else
+    MT3_CUDA_CHECK(launch_kernel_cluster(sgemm_dec_cluster2_kernel<KC0, KC1, MODE, false>, dim3(tiles0 + tiles1, 8), dim3(128), smem, s,
+                                         pdl, 8u, a0, a1, tiles0));
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
 template <int KC, int MODE>
 inline int launch_dec_gemm_cluster_kc(const DecGemmArgs& a, cudaStream_t s, bool pdl) {
   constexpr size_t smem = dec_cluster_smem<KC>();
@@ -551,6 +605,7 @@ template <bool TRACE>
 __global__ void __launch_bounds__(kAttThreads)
 dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const float* __restrict__ kv, int H, int cap,
                           const int* __restrict__ len_ptr, int len_add, int max_len, float* __restrict__ out, int ldo,
+                          const float* __restrict__ q_ssq, int q_ssq_n, int q_ssq_ld, float q_dim, float q_eps,
                           unsigned long long* trace) {
   extern __shared__ __align__(128) float sm[];
   float* ring = sm;                                              // [stages][32*64]
@@ -617,7 +672,15 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
   pdl_wait();                                                    // q comes from the preceding GEMM
   pdl_trigger();
   const int c = lane & 15, half = lane >> 4;
-  const float4 q4 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + q_off + h * 64 + c * 4);
+  float4 q4 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + q_off + h * 64 + c * 4);
+  if (q_ssq) {
+    // q arrives un-normalised from a fused projection: scale by rsqrt(mean(y^2) + eps) of its input row, whose sum
+    // of squares the producing GEMM left as q_ssq_n per-tile partials (summed in order)
+    float ssq = 0.f;
+    for (int i = 0; i < q_ssq_n; ++i) ssq += __ldg(q_ssq + (long long)b * q_ssq_ld + i);
+    const float rs = 1.0f / sqrtf(ssq / q_dim + q_eps);
+    q4.x *= rs; q4.y *= rs; q4.z *= rs; q4.w *= rs;
+  }
   float lmax = -INFINITY;
   for (int j = 0; j < nt; ++j) {
     const int s = j % kAttStages;

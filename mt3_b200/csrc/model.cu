@@ -81,13 +81,16 @@ struct TcW { float* hi = nullptr; float* lo = nullptr; TcOperand op; int K = 0, 
 struct Act { float* hi = nullptr; float* lo = nullptr; TcOperand op; };
 
 struct EncLayer { float *wqkv, *wo, *wi, *wo2; TcW t_wqkv, t_wo, t_wi, t_wo2; };
-struct DecLayer { float *wqkv, *wo, *wq_c, *wkv_c, *wo_c, *wi, *wo2; TcW t_wkv_c; };
+struct DecLayer { float *wqkv, *wo, *wq_c, *wkv_c, *wo_c, *wi, *wo2; float* wc1 = nullptr; TcW t_wkv_c; };   // wc1: [Q+D, Q] = [Wo.Wq ; Wq]
 
 struct Model {
   mt3_model_config cfg;
   int D, H, Q, F, V, Le, Ld, L;
   float* slab = nullptr;          // all prepared weights
   float* slab_tc = nullptr;       // K-major (and hi/lo) copies for the tcgen05 path
+  bool fuse_q = true;             // MT3_DEC_FUSE=0: keep the self-attention out-projection and the cross-attention query
+                                  // projection as two launches (default: one launch with a precomposed weight block)
+  float *dy2 = nullptr, *dssq = nullptr;   // second residual-stream buffer (ping-pong) and [B][D/32] sum-of-squares partials
   float* slab_dect = nullptr;     // K-major fp32 copies W^T [N, K] of the decoder's step weights (tcgen05 decode GEMM)
   bool dec_tc = true;             // MT3_DEC_TC=0: tensor-core decode modes use the mma.sync kernel instead of tcgen05
   std::map<const float*, const float*> dec_wt;                                   // [K, N] weight -> its W^T copy
@@ -154,8 +157,23 @@ static int64_t prepared_floats(const mt3_model_config& c) {
   n += V * D;      // embedding
   n += (int64_t)c.num_decoder_layers * (D * 3 * Q + Q * D + D * Q + D * 2 * Q + Q * D + D * 2 * F + F * D);
   n += D * V;      // logits
+  n += (int64_t)c.num_decoder_layers * (Q + D) * Q;   // precomposed [Wo.Wq ; Wq] blocks
   n += 2048 * D;   // PE
   return n;
+}
+
+// out [Q + D, Q]: rows [0, Q) = Wo [Q, D] . Wq [D, Q] accumulated in fp64 and rounded once; rows [Q, Q + D) = Wq.
+// (q = rstd . (y + o.Wo) . Wq  =  rstd . ([o | y] . out): the out-projection folded into the query projection.)
+__global__ void compose_out_q_kernel(const float* __restrict__ wo, const float* __restrict__ wq, int Q, int D, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= Q) return;
+  if (i < Q) {
+    double acc = 0.0;
+    for (int k = 0; k < D; ++k) acc += (double)wo[(long long)i * D + k] * (double)wq[(long long)k * Q + j];
+    out[(long long)i * Q + j] = (float)acc;
+  } else {
+    out[(long long)i * Q + j] = wq[(long long)(i - Q) * Q + j];
+  }
 }
 
 static int prep_copy(cudaStream_t s, const float* src, int K, int N, const float* g, float* dst, int ldd, int col_off,
@@ -431,7 +449,7 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
 }
 
 static int launch_dec_attention(Model* m, const float* q, const float* kv, int cap, const int* len_ptr, int len_add,
-                                float* out, const Rows& rows, cudaStream_t s) {
+                                float* out, const Rows& rows, cudaStream_t s, const float* q_ssq = nullptr) {
   static bool attr_done = false;
   const int max_len = std::max(m->L, m->T);
   const size_t smem = dec_attention_smem(max_len);
@@ -445,9 +463,31 @@ static int launch_dec_attention(Model* m, const float* q, const float* kv, int c
                                dim3(kAttThreads), smem, s, m->pdl_attn,
                                q + (int64_t)rows.begin * m->Q, m->Q, 0, kv + (int64_t)rows.begin * 2 * m->H * cap * 64, m->H, cap,
                                len_ptr, len_add, max_len, out + (int64_t)rows.begin * m->Q, m->Q,
-                               trace_slot(m, len_ptr ? "attn_self" : "attn_cross")));
+                               q_ssq ? q_ssq + (int64_t)rows.begin * (m->D / 32) : (const float*)nullptr, m->D / 32, m->D / 32,
+                               (float)m->D, 1e-6f, trace_slot(m, len_ptr ? "attn_self" : "attn_cross")));
   MT3_LAUNCH_CHECK();
   return MT3_OK;
+}
+
+// y_out = y_in + o.Wo  and  q_raw = [o | y_in].[Wo.Wq ; Wq]  in ONE launch; the RMSNorm factor of y_out is applied to
+// q inside the cross-attention kernel from the per-tile sums of squares this launch leaves in m->dssq.
+static int dec_gemm_out_q(Model* m, const DecLayer& w, const float* y_in, float* y_out, const Rows& rows, cudaStream_t s) {
+  const int D = m->D, Q = m->Q;
+  if (rows.count > kDecBM || Q != 384 || D != 512) return MT3_ERR_UNSUPPORTED;
+  const int64_t r0 = rows.begin;
+  DecGemmArgs a0, a1;
+  memset(&a0, 0, sizeof(a0));
+  a0.A = m->dao + r0 * Q; a0.lda = Q; a0.W = w.wo; a0.ldw = D; a0.M = rows.count; a0.N = D; a0.K = Q;
+  a0.eps = 1e-6f; a0.epi = EPI_RESIDUAL; a0.R = y_in + r0 * D; a0.ldr = D; a0.C = y_out + r0 * D; a0.ldc = D; a0.n_split = D;
+  a0.ssq_out = m->dssq + r0 * (D / 32); a0.ssq_ld = D / 32;
+  a0.trace = trace_slot(m, "gemm_out+cross_q");
+  memset(&a1, 0, sizeof(a1));
+  a1.A = m->dao + r0 * Q; a1.lda = Q; a1.A2 = y_in + r0 * D; a1.lda2 = D; a1.K0 = Q;
+  a1.W = w.wc1; a1.ldw = Q; a1.M = rows.count; a1.N = Q; a1.K = Q + D;
+  a1.eps = 1e-6f; a1.epi = EPI_STORE; a1.C = m->dq + r0 * Q; a1.ldc = Q; a1.n_split = Q;
+  a1.R = a1.C; a1.ldr = Q;
+  a1.trace = a0.trace;
+  return launch_dec_gemm_cluster2<48, 112, 0>(a0, a1, s, m->pdl_gemm);
 }
 
 // One decode step (network.py:303-361 -> :196-262 -> :88-155).  tok_in DEV [B]; logits DEV [B,V];
@@ -461,21 +501,31 @@ static int decode_rows(Model* m, const int* tok_in, float* logits, int greedy, i
   MT3_CUDA_CHECK(launch_kernel(embed_kernel, dim3(rows.count), dim3(128), 0, s, m->pdl, tok_in, (const float*)m->emb, D, V,
                                (const float*)m->pe, (const int*)pos, m->dy, rows.begin));
   MT3_LAUNCH_CHECK();
+  float* y = m->dy;                 // residual stream of the step (ping-pongs with m->dy2 across fused launches)
   for (int l = 0; l < m->Ld; ++l) {
     const DecLayer& w = m->dec[l];
     float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
     const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
     // fused RMSNorm + QKV projection + K/V cache append (layers.py:238-240, :272-289)
-    MT3_TRY(dec_gemm(m, m->dy, D, w.wqkv, 3 * Q, D, 1, EPI_STORE, m->dq, Q, Q, skv, pos, rows, s));
+    MT3_TRY(dec_gemm(m, y, D, w.wqkv, 3 * Q, D, 1, EPI_STORE, m->dq, Q, Q, skv, pos, rows, s));
     MT3_TRY(launch_dec_attention(m, m->dq, skv, L, pos, 1, m->dao, rows, s));
-    MT3_TRY(dec_gemm(m, m->dao, Q, w.wo, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, rows, s));
-    MT3_TRY(dec_gemm(m, m->dy, D, w.wq_c, Q, D, 1, EPI_STORE, m->dq, Q, Q, nullptr, nullptr, rows, s));
-    MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, rows, s));
-    MT3_TRY(dec_gemm(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, rows, s));
-    MT3_TRY(dec_gemm(m, m->dy, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr, nullptr, rows, s));
-    MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, m->dy, D, D, nullptr, nullptr, rows, s));
+    int fused = MT3_ERR_UNSUPPORTED;
+    if (m->fuse_q && m->dec_cluster && m->dec_gemm_mode == 0) {
+      float* y_next = (y == m->dy) ? m->dy2 : m->dy;      // the fused launch reads y while other CTAs write y': ping-pong
+      fused = dec_gemm_out_q(m, w, y, y_next, rows, s);
+      if (fused == MT3_OK) y = y_next;
+      else if (fused != MT3_ERR_UNSUPPORTED) return fused;
+    }
+    if (fused != MT3_OK) {
+      MT3_TRY(dec_gemm(m, m->dao, Q, w.wo, D, Q, 0, EPI_RESIDUAL, y, D, D, nullptr, nullptr, rows, s));
+      MT3_TRY(dec_gemm(m, y, D, w.wq_c, Q, D, 1, EPI_STORE, m->dq, Q, Q, nullptr, nullptr, rows, s));
+    }
+    MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, rows, s, fused == MT3_OK ? m->dssq : nullptr));
+    MT3_TRY(dec_gemm(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, y, D, D, nullptr, nullptr, rows, s));
+    MT3_TRY(dec_gemm(m, y, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr, nullptr, rows, s));
+    MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, y, D, D, nullptr, nullptr, rows, s));
   }
-  MT3_TRY(dec_gemm(m, m->dy, D, m->w_logits, V, D, 1, EPI_STORE, logits, V, V, nullptr, nullptr, rows, s));
+  MT3_TRY(dec_gemm(m, y, D, m->w_logits, V, D, 1, EPI_STORE, logits, V, V, nullptr, nullptr, rows, s));
   if (greedy) {
     // B (whole batch) sizes the arrival counter: the LAST CTA over all sub-batches advances the position
     MT3_CUDA_CHECK(launch_kernel(argmax_step_kernel, dim3(rows.count), dim3(256), 0, s, m->pdl, (const float*)logits, V, B,
@@ -855,6 +905,11 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     PREP(W(pre + "self_attention/out/kernel"), Q, D, nullptr, L.wo, D, 0, 1);
     L.wq_c = take((int64_t)D * Q);
     PREP(W(pre + "encoder_decoder_attention/query/kernel"), D, Q, g2, L.wq_c, Q, 0, 1);
+    L.wc1 = take((int64_t)(Q + D) * Q);
+    if (rc == MT3_OK) {
+      compose_out_q_kernel<<<dim3(cdiv(Q, 128), Q + D), 128, 0, s>>>(L.wo, L.wq_c, Q, D, L.wc1);
+      if (cudaGetLastError() != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: compose_out_q launch failed");
+    }
     L.wkv_c = take((int64_t)D * 2 * Q);   // applied to `encoded`, which is already normed: no fold
     PREP(W(pre + "encoder_decoder_attention/key/kernel"), D, Q, nullptr, L.wkv_c, 2 * Q, 0, 1);
     PREP(W(pre + "encoder_decoder_attention/value/kernel"), D, Q, nullptr, L.wkv_c, 2 * Q, Q, 1);
@@ -896,6 +951,8 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     m->pdl = (pdl_bits & 1) != 0;
     m->pdl_attn = (pdl_bits & 3) != 0;
     m->pdl_gemm = (pdl_bits & 5) != 0;
+    const char* e_fuse = getenv("MT3_DEC_FUSE");
+    m->fuse_q = !(e_fuse && e_fuse[0] == '0');
     const char* e_chain = getenv("MT3_DEC_CHAIN");
     m->chain = e_chain && e_chain[0] == '1';
     const char* e_mega = getenv("MT3_DEC_MEGA");
@@ -997,6 +1054,7 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
 namespace {
 struct WsLayout {
   int64_t x_hi, x_lo, h_lo, ao_lo, g_lo, enc_hi, enc_lo, qkv_lo, vt_hi, vt_lo;
+  int64_t dy2, dssq;
   int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, mega_prog, mega_bar, total;
 };
 WsLayout ws_layout(const Model* m, int B, int T) {
@@ -1025,6 +1083,8 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   w.skv = take((int64_t)m->Ld * B * L * 2 * Q * 4);
   w.dy = take((int64_t)B * D * 4);
   w.drstd = take((int64_t)B * 4);
+  w.dy2 = take((int64_t)B * D * 4);
+  w.dssq = take((int64_t)B * (D / 32) * 4);
   w.dq = take((int64_t)B * Q * 4);
   w.dao = take((int64_t)B * Q * 4);
   w.dg = take((int64_t)B * F * 4);
@@ -1061,6 +1121,7 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
   m->ws = b; m->ws_bytes = bytes; m->B = batch; m->T = input_length;
   m->h = (float*)(b + w.h); m->rstd = (float*)(b + w.rstd); m->qkv = (float*)(b + w.qkv); m->ao = (float*)(b + w.ao);
   m->g = (float*)(b + w.g); m->encoded = (float*)(b + w.encoded); m->ckv = (float*)(b + w.ckv); m->skv = (float*)(b + w.skv);
+  m->dy2 = (float*)(b + w.dy2); m->dssq = (float*)(b + w.dssq);
   m->dy = (float*)(b + w.dy); m->drstd = (float*)(b + w.drstd); m->dq = (float*)(b + w.dq); m->dao = (float*)(b + w.dao);
   m->dg = (float*)(b + w.dg); m->dlogits = (float*)(b + w.dlogits); m->tok_cur = (int*)(b + w.tok_cur);
   m->finished = (int*)(b + w.finished); m->tokens = (int*)(b + w.tokens); m->state = (int*)(b + w.state);

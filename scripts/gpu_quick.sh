@@ -1,8 +1,13 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-MT3_DEC_STREAMS=2 TRACE_POS=512 TRACE_ROWS=140 timeout 600 python scripts/trace_step.py 2>&1 | tee gpurun_out/trace_step_streams2.log | awk 'NR<=30 || (NR>=68 && NR<=92)' 
-tail -14 gpurun_out/trace_step_streams2.log
-echo "== bench default"
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench_default.err | tail -1 > gpurun_out/bench_default.json
-grep -E "timed|e2e " gpurun_out/bench_default.err | head -2
+echo "== pytest -m gpu (all)"; timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -12 | tee gpurun_out/pytest_gpu.log
+TRACE_POS=512 timeout 600 python scripts/trace_step.py 2>&1 | tee gpurun_out/trace_step_fused.log | tail -14
+run_bench () {
+  local name=$1; shift
+  echo "== bench $name"
+  timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline "$@" 2> gpurun_out/bench_$name.err | tail -1 > gpurun_out/bench_$name.json
+  grep -E "timed|e2e " gpurun_out/bench_$name.err | head -2; tail -2 gpurun_out/bench_$name.err | grep -i -E "error|Traceback" 
+}
+run_bench default
+MT3_DEC_FUSE=0 run_bench unfused

@@ -269,11 +269,43 @@ def test_decode_variants_bit_identical(streams, pdl, cluster, mega, chain, monke
     monkeypatch.setenv("MT3_DEC_MEGA", mega)      # the whole step as one persistent kernel (generate path)
     monkeypatch.setenv("MT3_DEC_CHAIN", chain)    # cluster-local GEMM chains (full-K sums: other rounding)
     t, l = run()
-    if cluster == "1" and chain == "0":
+    if cluster == "1" and chain == "0" and mega == "0":
         np.testing.assert_array_equal(t, base_t)
         np.testing.assert_array_equal(l, base_l)
-    else:   # the fallback splits K into 64-deep chunks (the cluster kernel into K/8): same math, other rounding
+    else:   # the fallback splits K into 64-deep chunks (the cluster kernel into K/8), the persistent kernels keep the
+            # out-projection and the query projection separate: same math, other rounding
         np.testing.assert_allclose(l, base_l, rtol=0, atol=2e-5 * np.abs(base_l).max())
+
+
+def test_decode_fused_out_q_matches_unfused(monkeypatch):
+    """The default step folds the self-attention out-projection into the cross-attention query projection
+    (precomposed [Wo.Wq ; Wq] block, q scaled inside the attention kernel).  Same math as the two-launch
+    path up to fp32 rounding of the precomposed product: logits agree to 2e-5 of their scale, and both sit
+    within the standard tolerance of the fp64 oracle."""
+    from mt3_b200 import network
+    ocfg = O.T5Config(vocab_size=1536, num_encoder_layers=1, num_decoder_layers=3)
+    params = O.init_params(ocfg, seed=33, norm_scale_jitter=0.05)
+    cfg = network.T5Config(vocab_size=1536, emb_dim=512, num_heads=6, num_encoder_layers=1, num_decoder_layers=3,
+                           head_dim=64, mlp_dim=1024, mlp_activations=('gelu', 'linear'))
+    x_np = _inputs(5, t=64, seed=500)
+    x = torch.from_numpy(x_np).to(DEV)
+    forced = np.random.default_rng(3).integers(3, 1500, size=(5, 6)).astype(np.int32)
+
+    def run():
+        m = network.Transformer(cfg, params, device=DEV, max_batch=8, max_input_length=64, max_decode_length=16)
+        enc = m.encode(x)
+        return m.teacher_forced_logits(enc, torch.from_numpy(forced).to(DEV)).cpu().numpy()
+
+    monkeypatch.setenv("MT3_DEC_FUSE", "0")
+    unfused = run()
+    monkeypatch.setenv("MT3_DEC_FUSE", "1")
+    fused = run()
+    scale = np.abs(unfused).max()
+    assert np.abs(fused - unfused).max() <= 2e-5 * scale
+    assert np.abs(fused - unfused).max() > 0          # the fused path really ran (different rounding)
+    enc64 = O.encode(params, ocfg, x_np, np.float64)
+    ref = O.decode_teacher_forced(params, ocfg, enc64, forced, np.float64)
+    assert np.abs(fused - ref).max() <= 5e-4 * np.abs(ref).max()
 
 
 def test_vocab_decode_kernel_random():
