@@ -116,6 +116,8 @@ struct Model {
   int mega_phases = 0, mega_clusters = 0; bool mega_ready = false;
   cudaStream_t sub_stream[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  int interleave = 0;             // MT3_DEC_INTERLEAVE=n: n blocks of sequences, attention nodes serialised across blocks
+  cudaEvent_t ev_hbm[64] = {};    // one per bandwidth-bound node of a step (n * Ld * 2 <= 64)
   int64_t dpartial_stride = 0, dcounters_stride = 0;
   bool tc_attn_ok = true;         // MT3_TC_ATTENTION=0 in the environment forces the exact-fp32 attention kernel
   float* w_in = nullptr;
@@ -490,48 +492,131 @@ static int dec_gemm_out_q(Model* m, const DecLayer& w, const float* y_in, float*
   return launch_dec_gemm_cluster2<48, 112, 0>(a0, a1, s, m->pdl_gemm);
 }
 
-// One decode step (network.py:303-361 -> :196-262 -> :88-155).  tok_in DEV [B]; logits DEV [B,V];
-// greedy != 0 runs the argmax/bookkeeping kernel (tok_user optional), else only the position advances.
-// 8 launches per layer: [norm+QKV+KV-append] [self-attn] [out+residual] [norm+q] [cross-attn]
-// [out+residual] [norm+gated-GELU MLP in] [MLP out+residual].
-static int decode_rows(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
-                       int* tokens_ws, const Rows& rows, cudaStream_t s) {
-  const int B = m->B, D = m->D, Q = m->Q, F = m->F, V = m->V, L = m->L, T = m->T;
-  int* pos = m->state;
-  MT3_CUDA_CHECK(launch_kernel(embed_kernel, dim3(rows.count), dim3(128), 0, s, m->pdl, tok_in, (const float*)m->emb, D, V,
-                               (const float*)m->pe, (const int*)pos, m->dy, rows.begin));
+constexpr int kHbmEvents = 64;
+
+// A block of sequences walking through the step on its own stream.
+struct DecBranch { Rows rows; cudaStream_t s; float* y; int fused; };
+
+static int dec_embed(Model* m, DecBranch& b, const int* tok_in) {
+  MT3_CUDA_CHECK(launch_kernel(embed_kernel, dim3(b.rows.count), dim3(128), 0, b.s, m->pdl, tok_in, (const float*)m->emb, m->D, m->V,
+                               (const float*)m->pe, (const int*)m->state, m->dy, b.rows.begin));
   MT3_LAUNCH_CHECK();
-  float* y = m->dy;                 // residual stream of the step (ping-pongs with m->dy2 across fused launches)
-  for (int l = 0; l < m->Ld; ++l) {
-    const DecLayer& w = m->dec[l];
-    float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
-    const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
-    // fused RMSNorm + QKV projection + K/V cache append (layers.py:238-240, :272-289)
-    MT3_TRY(dec_gemm(m, y, D, w.wqkv, 3 * Q, D, 1, EPI_STORE, m->dq, Q, Q, skv, pos, rows, s));
-    MT3_TRY(launch_dec_attention(m, m->dq, skv, L, pos, 1, m->dao, rows, s));
-    int fused = MT3_ERR_UNSUPPORTED;
-    if (m->fuse_q && m->dec_cluster && m->dec_gemm_mode == 0) {
-      float* y_next = (y == m->dy) ? m->dy2 : m->dy;      // the fused launch reads y while other CTAs write y': ping-pong
-      fused = dec_gemm_out_q(m, w, y, y_next, rows, s);
-      if (fused == MT3_OK) y = y_next;
-      else if (fused != MT3_ERR_UNSUPPORTED) return fused;
-    }
-    if (fused != MT3_OK) {
-      MT3_TRY(dec_gemm(m, m->dao, Q, w.wo, D, Q, 0, EPI_RESIDUAL, y, D, D, nullptr, nullptr, rows, s));
-      MT3_TRY(dec_gemm(m, y, D, w.wq_c, Q, D, 1, EPI_STORE, m->dq, Q, Q, nullptr, nullptr, rows, s));
-    }
-    MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, rows, s, fused == MT3_OK ? m->dssq : nullptr));
-    MT3_TRY(dec_gemm(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, y, D, D, nullptr, nullptr, rows, s));
-    MT3_TRY(dec_gemm(m, y, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr, nullptr, rows, s));
-    MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, y, D, D, nullptr, nullptr, rows, s));
+  b.y = m->dy;                      // residual stream of the step (ping-pongs with m->dy2 across fused launches)
+  return MT3_OK;
+}
+// fused RMSNorm + QKV projection + K/V cache append (layers.py:238-240, :272-289)
+static int dec_layer_qkv(Model* m, DecBranch& b, int l) {
+  float* skv = m->skv + (int64_t)l * m->B * m->L * 2 * m->Q;
+  return dec_gemm(m, b.y, m->D, m->dec[l].wqkv, 3 * m->Q, m->D, 1, EPI_STORE, m->dq, m->Q, m->Q, skv, m->state, b.rows, b.s);
+}
+static int dec_layer_self(Model* m, DecBranch& b, int l) {
+  float* skv = m->skv + (int64_t)l * m->B * m->L * 2 * m->Q;
+  return launch_dec_attention(m, m->dq, skv, m->L, m->state, 1, m->dao, b.rows, b.s);
+}
+// self-attention out-projection + residual, cross-attention query projection (one launch when fused)
+static int dec_layer_outq(Model* m, DecBranch& b, int l) {
+  const DecLayer& w = m->dec[l];
+  const int D = m->D, Q = m->Q;
+  b.fused = MT3_ERR_UNSUPPORTED;
+  if (m->fuse_q && m->dec_cluster && m->dec_gemm_mode == 0) {
+    float* y_next = (b.y == m->dy) ? m->dy2 : m->dy;    // the fused launch reads y while other CTAs write y': ping-pong
+    b.fused = dec_gemm_out_q(m, w, b.y, y_next, b.rows, b.s);
+    if (b.fused == MT3_OK) b.y = y_next;
+    else if (b.fused != MT3_ERR_UNSUPPORTED) return b.fused;
   }
-  MT3_TRY(dec_gemm(m, y, D, m->w_logits, V, D, 1, EPI_STORE, logits, V, V, nullptr, nullptr, rows, s));
+  if (b.fused != MT3_OK) {
+    MT3_TRY(dec_gemm(m, m->dao, Q, w.wo, D, Q, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s));
+    MT3_TRY(dec_gemm(m, b.y, D, w.wq_c, Q, D, 1, EPI_STORE, m->dq, Q, Q, nullptr, nullptr, b.rows, b.s));
+  }
+  return MT3_OK;
+}
+static int dec_layer_cross(Model* m, DecBranch& b, int l) {
+  const float* ckv = m->ckv + (int64_t)l * m->B * m->T * 2 * m->Q;
+  return launch_dec_attention(m, m->dq, ckv, m->T, nullptr, m->T, m->dao, b.rows, b.s, b.fused == MT3_OK ? m->dssq : nullptr);
+}
+static int dec_layer_mlp(Model* m, DecBranch& b, int l) {
+  const DecLayer& w = m->dec[l];
+  const int D = m->D, Q = m->Q, F = m->F;
+  MT3_TRY(dec_gemm(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s));
+  MT3_TRY(dec_gemm(m, b.y, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr, nullptr, b.rows, b.s));
+  MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s));
+  return MT3_OK;
+}
+static int dec_logits_argmax(Model* m, DecBranch& b, float* logits, int greedy, int* tok_user, int use_finished, int* tokens_ws) {
+  MT3_TRY(dec_gemm(m, b.y, m->D, m->w_logits, m->V, m->D, 1, EPI_STORE, logits, m->V, m->V, nullptr, nullptr, b.rows, b.s));
   if (greedy) {
     // B (whole batch) sizes the arrival counter: the LAST CTA over all sub-batches advances the position
-    MT3_CUDA_CHECK(launch_kernel(argmax_step_kernel, dim3(rows.count), dim3(256), 0, s, m->pdl, (const float*)logits, V, B,
+    MT3_CUDA_CHECK(launch_kernel(argmax_step_kernel, dim3(b.rows.count), dim3(256), 0, b.s, m->pdl, (const float*)logits, m->V, m->B,
                                  use_finished ? m->tok_cur : (int*)nullptr, use_finished ? m->finished : (int*)nullptr,
-                                 tokens_ws, L, tok_user, m->state, 1, rows.begin));
+                                 tokens_ws, m->L, tok_user, m->state, 1, b.rows.begin));
     MT3_LAUNCH_CHECK();
+  }
+  return MT3_OK;
+}
+
+// One decode step (network.py:303-361 -> :196-262 -> :88-155) for one block of sequences.  tok_in DEV [B]; logits
+// DEV [B,V]; greedy != 0 runs the argmax/bookkeeping kernel (tok_user optional), else only the position advances.
+// 7 launches per layer: [norm+QKV+KV-append] [self-attn] [out+residual | norm+q] [cross-attn] [out+residual]
+// [norm+gated-GELU MLP in] [MLP out+residual].
+static int decode_rows(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
+                       int* tokens_ws, const Rows& rows, cudaStream_t s) {
+  DecBranch b{rows, s, nullptr, MT3_ERR_UNSUPPORTED};
+  MT3_TRY(dec_embed(m, b, tok_in));
+  for (int l = 0; l < m->Ld; ++l) {
+    MT3_TRY(dec_layer_qkv(m, b, l));
+    MT3_TRY(dec_layer_self(m, b, l));
+    MT3_TRY(dec_layer_outq(m, b, l));
+    MT3_TRY(dec_layer_cross(m, b, l));
+    MT3_TRY(dec_layer_mlp(m, b, l));
+  }
+  return dec_logits_argmax(m, b, logits, greedy, tok_user, use_finished, tokens_ws);
+}
+
+// The same step for n blocks of sequences on n streams with the bandwidth-bound nodes SERIALISED across the blocks:
+// the attention kernels run one after the other in the fixed order  self(b0,l) self(b1,l) .. cross(b0,l) cross(b1,l) ..
+// (cross-stream events; captured as cross-branch edges of the step graph), so a block's attention never shares HBM
+// with another block's attention and always overlaps the other blocks' latency-bound GEMM chains.  (Plain forked
+// branches run in lockstep -- attention over attention, GEMM over GEMM -- and gain nothing: profiles/r01_call15.)
+static int decode_step_interleaved(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
+                                   int* tokens_ws, cudaStream_t s, int n) {
+  const int B = m->B;
+  DecBranch br[4];
+  const int per = (B + n - 1) / n;
+  MT3_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
+  for (int i = 0; i < n; ++i) {
+    const int b0 = i * per, cnt = std::min(per, B - b0);
+    br[i] = DecBranch{Rows{b0, cnt, i}, i == 0 ? s : m->sub_stream[i], nullptr, MT3_ERR_UNSUPPORTED};
+    if (i > 0) MT3_CUDA_CHECK(cudaStreamWaitEvent(br[i].s, m->ev_fork, 0));
+    MT3_TRY(dec_embed(m, br[i], tok_in));
+  }
+  cudaEvent_t prev = nullptr;       // completion of the previous bandwidth-bound node in the global order
+  int prev_branch = -1, ev_next = 0;
+  auto hbm_node = [&](int i, int l, bool self) -> int {
+    if (prev && prev_branch != i) MT3_CUDA_CHECK(cudaStreamWaitEvent(br[i].s, prev, 0));
+    MT3_TRY(self ? dec_layer_self(m, br[i], l) : dec_layer_cross(m, br[i], l));
+    cudaEvent_t e = m->ev_hbm[ev_next++ % kHbmEvents];
+    MT3_CUDA_CHECK(cudaEventRecord(e, br[i].s));
+    prev = e;
+    prev_branch = i;
+    return MT3_OK;
+  };
+  for (int l = 0; l < m->Ld; ++l) {
+    for (int i = 0; i < n; ++i) MT3_TRY(dec_layer_qkv(m, br[i], l));
+    for (int i = 0; i < n; ++i) {
+      MT3_TRY(hbm_node(i, l, true));
+      MT3_TRY(dec_layer_outq(m, br[i], l));
+    }
+    for (int i = 0; i < n; ++i) {
+      MT3_TRY(hbm_node(i, l, false));
+      MT3_TRY(dec_layer_mlp(m, br[i], l));
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    MT3_TRY(dec_logits_argmax(m, br[i], logits, greedy, tok_user, use_finished, tokens_ws));
+    if (i > 0) {
+      MT3_CUDA_CHECK(cudaEventRecord(m->ev_join[i], br[i].s));
+      MT3_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join[i], 0));
+    }
   }
   return MT3_OK;
 }
@@ -542,9 +627,33 @@ static int decode_step_chain(Model* m, const int* tok_in, float* logits, int gre
 // One decode step for the whole batch.  With MT3_DEC_STREAMS = n > 1 the batch is cut into n blocks of
 // sequences that run on n streams (forked/joined with events; captured as parallel branches of the step
 // graph): one block's latency-bound GEMM chain overlaps another block's bandwidth-bound attention.
+static int ensure_sub_streams(Model* m) {
+  if (m->ev_fork) return MT3_OK;
+  MT3_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+  for (int i = 0; i < 4; ++i) {
+    MT3_CUDA_CHECK(cudaStreamCreateWithFlags(&m->sub_stream[i], cudaStreamNonBlocking));
+    MT3_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < kHbmEvents; ++i) MT3_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_hbm[i], cudaEventDisableTiming));
+  return MT3_OK;
+}
+
 static int decode_step_impl(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
                             int* tokens_ws, cudaStream_t s) {
   const int B = m->B;
+  if (m->interleave > 1 && !(m->chain && m->chain_cluster)) {
+    int n = std::min(m->interleave, 4);
+    while (n > 1 && (B / n < 8 || n * m->Ld * 2 > kHbmEvents)) --n;
+    if (n > 1) {
+      MT3_TRY(ensure_sub_streams(m));
+      MT3_TRY(decode_step_interleaved(m, tok_in, logits, greedy, tok_user, use_finished, tokens_ws, s, n));
+      if (!greedy) {
+        MT3_CUDA_CHECK(launch_kernel(advance_pos_kernel, dim3(1), dim3(1), 0, s, m->pdl, m->state));
+        MT3_LAUNCH_CHECK();
+      }
+      return MT3_OK;
+    }
+  }
   if (m->chain && m->chain_cluster)
     return decode_step_chain(m, tok_in, logits, greedy, tok_user, use_finished, tokens_ws, s);
   int ns = std::max(1, std::min(m->dec_streams, 4));
@@ -552,13 +661,7 @@ static int decode_step_impl(Model* m, const int* tok_in, float* logits, int gree
   if (ns == 1) {
     MT3_TRY(decode_rows(m, tok_in, logits, greedy, tok_user, use_finished, tokens_ws, Rows{0, B, 0}, s));
   } else {
-    if (!m->ev_fork) {
-      MT3_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
-      for (int i = 0; i < 4; ++i) {
-        MT3_CUDA_CHECK(cudaStreamCreateWithFlags(&m->sub_stream[i], cudaStreamNonBlocking));
-        MT3_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
-      }
-    }
+    MT3_TRY(ensure_sub_streams(m));
     MT3_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
     const int per = (B + ns - 1) / ns;
     for (int i = 0; i < ns; ++i) {
@@ -951,6 +1054,8 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     m->pdl = (pdl_bits & 1) != 0;
     m->pdl_attn = (pdl_bits & 3) != 0;
     m->pdl_gemm = (pdl_bits & 5) != 0;
+    const char* e_il = getenv("MT3_DEC_INTERLEAVE");
+    m->interleave = e_il ? atoi(e_il) : 0;
     const char* e_fuse = getenv("MT3_DEC_FUSE");
     m->fuse_q = !(e_fuse && e_fuse[0] == '0');
     const char* e_chain = getenv("MT3_DEC_CHAIN");
@@ -1043,6 +1148,8 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
     if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
   }
   if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+  for (int i = 0; i < kHbmEvents; ++i)
+    if (m->ev_hbm[i]) cudaEventDestroy(m->ev_hbm[i]);
   if (m->h_flag) cudaFreeHost(m->h_flag);
   cudaFree(m->slab);
   cudaFree(m->slab_tc);

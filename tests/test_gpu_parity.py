@@ -240,10 +240,11 @@ def test_generate_eos_semantics_and_graph_equivalence(pdl, monkeypatch):
     np.testing.assert_array_equal(dec, O.vocab_decode(t_plain, 1388))
 
 
-@pytest.mark.parametrize("streams,pdl,cluster,mega,chain", [("2", "0", "1", "0", "0"), ("4", "1", "1", "0", "0"),
-                                                            ("1", "0", "0", "0", "0"), ("1", "0", "1", "1", "0"),
-                                                            ("1", "0", "1", "0", "1"), ("1", "1", "1", "0", "1")])
-def test_decode_variants_bit_identical(streams, pdl, cluster, mega, chain, monkeypatch):
+@pytest.mark.parametrize("streams,pdl,cluster,mega,chain,interleave",
+                         [("2", "0", "1", "0", "0", "0"), ("4", "1", "1", "0", "0", "0"), ("1", "0", "0", "0", "0", "0"),
+                          ("1", "0", "1", "1", "0", "0"), ("1", "0", "1", "0", "1", "0"), ("1", "1", "1", "0", "1", "0"),
+                          ("1", "0", "1", "0", "0", "2"), ("1", "0", "1", "0", "0", "4")])
+def test_decode_variants_bit_identical(streams, pdl, cluster, mega, chain, interleave, monkeypatch):
     """Sub-batch streams, PDL and the global-scratch split-K fallback are scheduling choices only: every
     output element keeps its summation order, so tokens AND logits are bit-identical to the default path."""
     from mt3_b200 import network
@@ -260,14 +261,16 @@ def test_decode_variants_bit_identical(streams, pdl, cluster, mega, chain, monke
         lg = m.teacher_forced_logits(enc, torch.from_numpy(toks[:, :4].astype(np.int32)).to(DEV)).cpu().numpy()
         return toks, lg
 
-    for k in ("MT3_DEC_STREAMS", "MT3_PDL", "MT3_DEC_CLUSTER", "MT3_DEC_MEGA", "MT3_DEC_CHAIN"):
+    for k in ("MT3_DEC_STREAMS", "MT3_PDL", "MT3_DEC_CLUSTER", "MT3_DEC_MEGA", "MT3_DEC_CHAIN", "MT3_DEC_INTERLEAVE"):
         monkeypatch.delenv(k, raising=False)
+    monkeypatch.setenv("MT3_DEC_INTERLEAVE", "0")
     base_t, base_l = run()
     monkeypatch.setenv("MT3_DEC_STREAMS", streams)
     monkeypatch.setenv("MT3_PDL", pdl)
     monkeypatch.setenv("MT3_DEC_CLUSTER", cluster)
     monkeypatch.setenv("MT3_DEC_MEGA", mega)      # the whole step as one persistent kernel (generate path)
     monkeypatch.setenv("MT3_DEC_CHAIN", chain)    # cluster-local GEMM chains (full-K sums: other rounding)
+    monkeypatch.setenv("MT3_DEC_INTERLEAVE", interleave)   # blocks of sequences with serialised attention nodes
     t, l = run()
     if cluster == "1" and chain == "0" and mega == "0":
         np.testing.assert_array_equal(t, base_t)
