@@ -596,7 +596,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 }
 
 inline size_t dec_attention_smem(int max_len) {
-  return (size_t)(kAttStages * kAttTileFloats + ((max_len + 3) & ~3) + 8 * 64) * sizeof(float) + 2 * kAttStages * 8 + 64;
+  return (size_t)(kAttStages * kAttTileFloats + 4 * ((max_len + 3) & ~3) + 8 * 64 + 64) * sizeof(float) + 2 * kAttStages * 8 + 64;
 }
 
 // q [B, ldq], head h at column q_off + h*64.  kv: head-major [b][2][H][cap][64].  out [B, ldo].
@@ -608,10 +608,12 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
                           const float* __restrict__ q_ssq, int q_ssq_n, int q_ssq_ld, float q_dim, float q_eps,
                           unsigned long long* trace) {
   extern __shared__ __align__(128) float sm[];
+  const int ml4 = (max_len + 3) & ~3;
   float* ring = sm;                                              // [stages][32*64]
-  float* sP = ring + kAttStages * kAttTileFloats;                // [max_len4]
-  float* sRed = sP + ((max_len + 3) & ~3);                       // [8][64]
-  uint64_t* full = reinterpret_cast<uint64_t*>(sRed + 8 * 64);   // [stages]
+  float* sP = ring + kAttStages * kAttTileFloats;                // [4][ml4]: per-warp partial scores; row 0 becomes P
+  float* sRed = sP + 4 * ml4;                                    // [8][64]
+  float* sQ = sRed + 8 * 64;                                     // [64] the (scaled) query
+  uint64_t* full = reinterpret_cast<uint64_t*>(sQ + 64);         // [stages]
   uint64_t* empty = full + kAttStages;
   __shared__ float s_stat[8];
 
@@ -668,47 +670,55 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
   }
 
   // ---- consumers (128 threads) ----
-  // pass 1: scores.  16 lanes cover one key row (conflict-free 256-byte read), 2 keys per warp instruction.
   pdl_wait();                                                    // q comes from the preceding GEMM
   pdl_trigger();
-  const int c = lane & 15, half = lane >> 4;
-  float4 q4 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + q_off + h * 64 + c * 4);
-  if (q_ssq) {
-    // q arrives un-normalised from a fused projection: scale by rsqrt(mean(y^2) + eps) of its input row, whose sum
-    // of squares the producing GEMM left as q_ssq_n per-tile partials (summed in order)
-    float ssq = 0.f;
-    for (int i = 0; i < q_ssq_n; ++i) ssq += __ldg(q_ssq + (long long)b * q_ssq_ld + i);
-    const float rs = 1.0f / sqrtf(ssq / q_dim + q_eps);
-    q4.x *= rs; q4.y *= rs; q4.z *= rs; q4.w *= rs;
-  }
-  float lmax = -INFINITY;
-  for (int j = 0; j < nt; ++j) {
-    const int s = j % kAttStages;
-    tc::mbar_wait(&full[s], (j / kAttStages) & 1);
-    if (tr0 && j == 0) trace[2] = (unsigned long long)(clock64() - c0);      // first K tile landed
-    const float* tile = ring + s * kAttTileFloats;
-    const int k0 = j * kAttKT;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int kk = warp * 8 + i * 2 + half;                    // key inside the tile
-      float d = 0.f;
-      if (k0 + kk < len) {
-        const float4 kx = *reinterpret_cast<const float4*>(tile + kk * 64 + c * 4);
-        d = q4.x * kx.x + q4.y * kx.y + q4.z * kx.z + q4.w * kx.w;
-      }
-      d += __shfl_xor_sync(0xffffffffu, d, 1);
-      d += __shfl_xor_sync(0xffffffffu, d, 2);
-      d += __shfl_xor_sync(0xffffffffu, d, 4);
-      d += __shfl_xor_sync(0xffffffffu, d, 8);
-      if (k0 + kk < len) {
-        if (c == 0) sP[k0 + kk] = d;
-        lmax = fmaxf(lmax, d);
-      }
+  if (tid < 16) {
+    float4 q4 = *reinterpret_cast<const float4*>(q + (long long)b * ldq + q_off + h * 64 + tid * 4);
+    if (q_ssq) {
+      // q arrives un-normalised from a fused projection: scale by rsqrt(mean(y^2) + eps) of its input row, whose sum
+      // of squares the producing GEMM left as q_ssq_n per-tile partials (summed in order)
+      float ssq = 0.f;
+      for (int i = 0; i < q_ssq_n; ++i) ssq += __ldg(q_ssq + (long long)b * q_ssq_ld + i);
+      const float rs = 1.0f / sqrtf(ssq / q_dim + q_eps);
+      q4.x *= rs; q4.y *= rs; q4.z *= rs; q4.w *= rs;
     }
-    __syncwarp();
-    if (lane == 0) tc::mbar_arrive(&empty[s]);
+    reinterpret_cast<float4*>(sQ)[tid] = q4;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  // pass 1: scores, no cross-lane traffic.  Lane <-> key of the tile (a 256-byte row); warp w covers four of the
+  // row's sixteen 16-byte chunks, rotated by the lane so that the eight lanes of a quarter-warp hit eight distinct
+  // bank groups (rows are 64 words apart, i.e. bank-aligned); the four per-warp partial dot products of a key are
+  // added in warp order by the softmax pass.
+  {
+    const float4* q4s = reinterpret_cast<const float4*>(sQ);
+    float* part = sP + warp * ml4;
+    for (int j = 0; j < nt; ++j) {
+      const int s = j % kAttStages;
+      tc::mbar_wait(&full[s], (j / kAttStages) & 1);
+      if (tr0 && j == 0) trace[2] = (unsigned long long)(clock64() - c0);      // first K tile landed
+      const float4* row = reinterpret_cast<const float4*>(ring + s * kAttTileFloats + lane * 64);
+      const int k0 = j * kAttKT;
+      float d = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int c = (4 * warp + jj + (lane & 7)) & 15;
+        const float4 kx = row[c];
+        const float4 qx = q4s[c];
+        d = fmaf(qx.x, kx.x, d); d = fmaf(qx.y, kx.y, d); d = fmaf(qx.z, kx.z, d); d = fmaf(qx.w, kx.w, d);
+      }
+      if (k0 + lane < len) part[k0 + lane] = d;
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&empty[s]);
+    }
   }
   if (tr0) trace[3] = (unsigned long long)(clock64() - c0);       // pass 1 (K tiles) consumed
+  asm volatile("bar.sync 1, 128;" ::: "memory");                // all four partial rows are complete
+  float lmax = -INFINITY;
+  for (int k = tid; k < len; k += 128) {
+    const float sc = ((sP[k] + sP[ml4 + k]) + sP[2 * ml4 + k]) + sP[3 * ml4 + k];
+    sP[k] = sc;
+    lmax = fmaxf(lmax, sc);
+  }
   lmax = warp_max(lmax);
   if (lane == 0) s_stat[warp] = lmax;
   asm volatile("bar.sync 1, 128;" ::: "memory");
