@@ -421,14 +421,19 @@ __device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int
                     make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
     }
   } else {
-    // ---- tensor cores: warp w owns rows 16w .. 16w+15, all 32 columns (4 n8 tiles) ----
+    // ---- tensor cores: a warp owns a 16-row group and nj of the four n8 column tiles.  With M <= 32 (<= 16) live
+    // rows the four warps regroup as 2 row groups x 2 column halves (1 x 4), so the multiply time scales with M.
     const int g = lane >> 2, t = lane & 3;
+    int rg, j0, nj;
+    if (p.M > 32) { rg = warp; j0 = 0; nj = 4; }
+    else if (p.M > 16) { rg = warp & 1; j0 = (warp >> 1) * 2; nj = 2; }
+    else { rg = 0; j0 = warp; nj = 1; }
     float acc[4][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-    const float* a_lo_row = As + (warp * 16 + g) * LDA + t;
+    const float* a_lo_row = As + (rg * 16 + g) * LDA + t;
     const float* a_hi_row = a_lo_row + 8 * LDA;
 #pragma unroll 2
     for (int k = 0; k < KC; k += 8) {
@@ -443,30 +448,35 @@ __device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float bf[2] = {Bs[(k + t) * LDB + j * 8 + g], Bs[(k + t + 4) * LDB + j * 8 + g]};
-        uint32_t bh[2], bl[2];
+        if (j < nj) {
+          const int col = (j0 + j) * 8 + g;
+          const float bf[2] = {Bs[(k + t) * LDB + col], Bs[(k + t + 4) * LDB + col]};
+          uint32_t bh[2], bl[2];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          float hi, lo;
-          split_tf32(bf[e], hi, lo);
-          bh[e] = __float_as_uint(hi);
-          bl[e] = __float_as_uint(lo);
+          for (int e = 0; e < 2; ++e) {
+            float hi, lo;
+            split_tf32(bf[e], hi, lo);
+            bh[e] = __float_as_uint(hi);
+            bl[e] = __float_as_uint(lo);
+          }
+          if (MODE == 1) {                     // small terms first
+            mma_tf32_16x8x8(acc[j], al, bh);
+            mma_tf32_16x8x8(acc[j], ah, bl);
+          }
+          mma_tf32_16x8x8(acc[j], ah, bh);
         }
-        if (MODE == 1) {                       // small terms first
-          mma_tf32_16x8x8(acc[j], al, bh);
-          mma_tf32_16x8x8(acc[j], ah, bl);
-        }
-        mma_tf32_16x8x8(acc[j], ah, bh);
       }
     }
     if (tr0) p.trace[3] = (unsigned long long)(clock64() - c0);    // MMA loop done
     asm volatile("barrier.cluster.wait.aligned;" ::: "memory");    // every peer is running
-    // c0,c1: row 16w+g -> rank 2w, local row g;  c2,c3: row 16w+g+8 -> rank 2w+1, local row g
+    // c0,c1: row 16 rg + g -> rank 2 rg, local row g;  c2,c3: row 16 rg + g + 8 -> rank 2 rg + 1, local row g
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t off = (uint32_t)((g * BN + j * 8 + 2 * t) * 4);
-      st_cluster_f2(cluster_map(red_base + off, (unsigned)(2 * warp)), acc[j][0], acc[j][1]);
-      st_cluster_f2(cluster_map(red_base + off, (unsigned)(2 * warp + 1)), acc[j][2], acc[j][3]);
+      if (j < nj) {
+        const uint32_t off = (uint32_t)((g * BN + (j0 + j) * 8 + 2 * t) * 4);
+        st_cluster_f2(cluster_map(red_base + off, (unsigned)(2 * rg)), acc[j][0], acc[j][1]);
+        st_cluster_f2(cluster_map(red_base + off, (unsigned)(2 * rg + 1)), acc[j][2], acc[j][3]);
+      }
     }
   }
   if (p.norm && (tid & 1) == 0) {
@@ -519,6 +529,12 @@ inline int launch_dec_gemm_cluster2(const DecGemmArgs& a0, const DecGemmArgs& a1
                                          pdl, 8u, a0, a1, tiles0));
   MT3_LAUNCH_CHECK();
   return MT3_OK;
+}
+
+inline int launch_dec_gemm_out_q(const DecGemmArgs& a0, const DecGemmArgs& a1, int mode, cudaStream_t s, bool pdl) {
+  if (mode == 1) return launch_dec_gemm_cluster2<48, 112, 1>(a0, a1, s, pdl);
+  if (mode == 2) return launch_dec_gemm_cluster2<48, 112, 2>(a0, a1, s, pdl);
+  return launch_dec_gemm_cluster2<48, 112, 0>(a0, a1, s, pdl);
 }
 
 template <int KC, int MODE>

@@ -489,7 +489,7 @@ static int dec_gemm_out_q(Model* m, const DecLayer& w, const float* y_in, float*
   a1.eps = 1e-6f; a1.epi = EPI_STORE; a1.C = m->dq + r0 * Q; a1.ldc = Q; a1.n_split = Q;
   a1.R = a1.C; a1.ldr = Q;
   a1.trace = a0.trace;
-  return launch_dec_gemm_cluster2<48, 112, 0>(a0, a1, s, m->pdl_gemm);
+  return launch_dec_gemm_out_q(a0, a1, m->dec_gemm_mode, s, m->pdl_gemm);
 }
 
 constexpr int kHbmEvents = 64;
@@ -518,7 +518,7 @@ static int dec_layer_outq(Model* m, DecBranch& b, int l) {
   const DecLayer& w = m->dec[l];
   const int D = m->D, Q = m->Q;
   b.fused = MT3_ERR_UNSUPPORTED;
-  if (m->fuse_q && m->dec_cluster && m->dec_gemm_mode == 0) {
+  if (m->fuse_q && m->dec_cluster && !(m->dec_gemm_mode >= 1 && m->dec_tc && m->slab_dect)) {
     float* y_next = (b.y == m->dy) ? m->dy2 : m->dy;    // the fused launch reads y while other CTAs write y': ping-pong
     b.fused = dec_gemm_out_q(m, w, b.y, y_next, b.rows, b.s);
     if (b.fused == MT3_OK) b.y = y_next;

@@ -311,6 +311,34 @@ def test_decode_fused_out_q_matches_unfused(monkeypatch):
     assert np.abs(fused - ref).max() <= 5e-4 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("batch", [5, 20, 40])
+@pytest.mark.parametrize("mode,tc,tol", [("1", "0", 3e-5), ("1", "1", 3e-5), ("2", "0", 5e-3)])
+def test_decode_gemm_tensor_core_variants(mode, tc, tol, batch, monkeypatch):
+    """Opt-in tensor-core decode GEMMs (mma.sync with row-scaled warp tiling for M <= 16 / 32 / 64, tcgen05) against
+    the default exact-fp32 decode: 3xTF32 agrees to ~1e-5 of the logit scale, 1xTF32 to tf32 precision."""
+    from mt3_b200 import network
+    ocfg = O.T5Config(vocab_size=1536, num_encoder_layers=1, num_decoder_layers=2)
+    params = O.init_params(ocfg, seed=44, norm_scale_jitter=0.05)
+    cfg = network.T5Config(vocab_size=1536, emb_dim=512, num_heads=6, num_encoder_layers=1, num_decoder_layers=2,
+                           head_dim=64, mlp_dim=1024, mlp_activations=('gelu', 'linear'))
+    x = torch.from_numpy(_inputs(batch, t=32, seed=700)).to(DEV)
+    forced = np.random.default_rng(5).integers(3, 1500, size=(batch, 4)).astype(np.int32)
+
+    def run():
+        m = network.Transformer(cfg, params, device=DEV, max_batch=batch, max_input_length=32, max_decode_length=8)
+        enc = m.encode(x)
+        return m.teacher_forced_logits(enc, torch.from_numpy(forced).to(DEV)).cpu().numpy()
+
+    for k in ("MT3_DEC_GEMM_MODE", "MT3_DEC_TC"):
+        monkeypatch.delenv(k, raising=False)
+    base = run()
+    monkeypatch.setenv("MT3_DEC_GEMM_MODE", mode)
+    monkeypatch.setenv("MT3_DEC_TC", tc)
+    got = run()
+    err = np.abs(got - base).max() / np.abs(base).max()
+    assert 0 < err <= tol, err
+
+
 def test_vocab_decode_kernel_random():
     from mt3_b200 import vocabularies
     rng = np.random.default_rng(0)
