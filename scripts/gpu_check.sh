@@ -29,4 +29,6 @@ prof () {  # name, kernel regex, launch-skip, count
 prof enc_attention enc_attention_tc 9 2
 prof logmel logmel2048 1 1
 prof dec_attention dec_attention_bulk 262 2   # the roofline leg's launches at cache length 512
+prof dec_gemm sgemm_dec_cluster 60 4           # decode-step GEMMs (single and fused dual launch)
+echo "== decode-step timeline"; TRACE_POS=512 timeout 300 python scripts/trace_step.py > gpurun_out/trace_step.log 2>&1; tail -12 gpurun_out/trace_step.log
 ls -la gpurun_out/*.ncu-rep 2>/dev/null
