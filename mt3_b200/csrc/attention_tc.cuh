@@ -48,16 +48,24 @@ constexpr int kAtQ = 128;                 // query rows per CTA
 constexpr int kAtKC = 128;                // keys per chunk
 constexpr int kAtSub = 128 * 32 * 4;      // one [128 x 32] fp32 sub-tile = 16 KB
 constexpr int kVSub = 64 * 32 * 4;        // one [64 d x 32 keys] V^T sub-tile = 8 KB
-constexpr int kAtSmem = 3 * 4 * kAtSub + 1024 + 256;
+constexpr int kAtSmem = 3 * 4 * kAtSub + 1024 + 256 + 2 * 2 * 128 * 4;
+constexpr int kAtThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / epilogue (two per TMEM lane group)
+constexpr int kAtStageLd = 68;            // padded row of the O staging tile (floats)
 
 template <bool SPLIT3>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kAtThreads, 1)
 enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                         const __grid_constant__ CUtensorMap tv_hi, const __grid_constant__ CUtensorMap tv_lo, int T, int H,
                         float* __restrict__ out_hi, float* __restrict__ out_lo, int ldo, float* __restrict__ dbg_S,
-                        int variant) {
-  // dbg_S (bring-up tool only): raw S rows [B][H][T][T].
+                        int variant, unsigned long long* __restrict__ dbg_t) {
+  // dbg_S (bring-up tool only): raw S rows [B][H][T][T].  dbg_t (tool only): SM-clock stamps of CTA (0,0,0) -> [0..31]
+  // and of the CTA (0,0,gridDim.z/2) -> [32..63]: MMA thread in slots 0.., first softmax thread in slots 16..
   (void)variant;
+  const long long t_start = clock64();
+  unsigned long long* tslot = nullptr;
+  if (dbg_t && blockIdx.x == 0 && blockIdx.y == 0 && (blockIdx.z == 0 || blockIdx.z == gridDim.z / 2))
+    tslot = dbg_t + (blockIdx.z == 0 ? 0 : 32);
+#define AT_STAMP(i) do { if (tslot) tslot[i] = (unsigned long long)(clock64() - t_start); } while (0)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                       // Q hi: 2 sub-tiles, Q lo: 2 sub-tiles (64 KB); later the P chunk (4 sub-tiles)
@@ -70,6 +78,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
   uint64_t* p_full = bars + 6;              // [2] P chunk written (128 arrivals)
   uint64_t* pv_done = bars + 8;             // [2] PV MMAs of chunk c complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  float* s_max = reinterpret_cast<float*>(bars + 16);      // [2 halves][128 rows] partial row maxima
+  float* s_sum = s_max + 256;                              // [2 halves][128 rows] partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAtQ;
@@ -86,7 +96,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
     for (int c = 0; c < 2; ++c) {
       tc::mbar_init(&k_full[c], 1);
       tc::mbar_init(&v_full[c], 1);
-      tc::mbar_init(&p_full[c], 128);
+      tc::mbar_init(&p_full[c], 256);
       tc::mbar_init(&pv_done[c], 1);
     }
     tc::mbar_init(s_done, 1);
@@ -135,9 +145,11 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
       // ---- S = Q K^T ----
       constexpr uint32_t idesc_s = tc::make_idesc(tc::kFmtTF32, 128, kAtKC, 0, 0);
       tc::mbar_wait(q_full, 0);
+      AT_STAMP(0);
       const uint32_t q_addr = tc::smem_u32(sQ);
       for (int c = 0; c < nchunk; ++c) {
         tc::mbar_wait(&k_full[c], 0);
+        AT_STAMP(1 + c);
         tc::tc_fence_after();
         const uint32_t k_addr = tc::smem_u32(slot[c]);
         uint32_t acc = 0;
@@ -159,12 +171,15 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
         }
       }
       tc::mma_commit(s_done);
+      AT_STAMP(3);
       // ---- O = P V ----  A = P chunk in the Q region (K-major, 4 sub-tiles of 32 keys), B = V chunk (MN-major)
       constexpr uint32_t idesc_o = tc::make_idesc(tc::kFmtTF32, 128, 64, 0, 0);
       uint32_t acc = 0;
       for (int c = 0; c < nchunk; ++c) {
         tc::mbar_wait(&v_full[c], 0);
+        AT_STAMP(4 + 3 * c);
         tc::mbar_wait(&p_full[c], 0);
+        AT_STAMP(5 + 3 * c);
         tc::tc_fence_after();
         const uint32_t p_addr = tc::smem_u32(sQ);
         const uint32_t v_addr = tc::smem_u32(slot[c]);
@@ -177,36 +192,49 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
           if (SPLIT3) tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + 4 * kVSub + voff), idesc_o, 1u);
         }
         tc::mma_commit(&pv_done[c]);
+        AT_STAMP(6 + 3 * c);
       }
     }
   } else {
-    // ---- softmax + epilogue: thread owns query row q0 + 32*(warp%4) + lane ----
+    // ---- softmax + epilogue: 8 warps; warp w reads TMEM lanes [32 (w % 4), +32), the two warps of a lane group split
+    // the columns: of every 128-key chunk half 0 takes keys [0, 64), half 1 keys [64, 128); of O 32 columns each ----
     const int wq = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = wq * 32 + lane;                            // row inside the tile
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
     tc::mbar_wait(s_done, 0);
     tc::tc_fence_after();
+    if (threadIdx.x != 64) tslot = nullptr;                  // one stamping thread among the softmax warps
+    AT_STAMP(16);
     float mx = -INFINITY;
-    for (int c0 = 0; c0 < T; c0 += 32) {
-      uint32_t v[32];
-      tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
-      tc::tmem_ld_wait();
+    for (int c = 0; c < nchunk; ++c)
+      for (int cc = half * 64; cc < half * 64 + 64; cc += 32) {
+        const int c0 = c * kAtKC + cc;
+        if (c0 >= T) continue;
+        uint32_t v[32];
+        tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
+        tc::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
-      if (dbg_S && q0 + r < T) {
-        float* drow = dbg_S + (((long long)b * H + h) * T + q0 + r) * T + c0;
         for (int j = 0; j < 32; ++j)
-          if (c0 + j < T) drow[j] = __uint_as_float(v[j]);
+          if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+        if (dbg_S && q0 + r < T) {
+          float* drow = dbg_S + (((long long)b * H + h) * T + q0 + r) * T + c0;
+          for (int j = 0; j < 32; ++j)
+            if (c0 + j < T) drow[j] = __uint_as_float(v[j]);
+        }
       }
-    }
+    s_max[half * 128 + r] = mx;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    mx = fmaxf(s_max[r], s_max[128 + r]);
+    AT_STAMP(17);
     float sum = 0.f;
     for (int c = 0; c < nchunk; ++c) {
       if (c > 0) {                                           // P buffer is recycled: wait for chunk c-1's MMAs
         tc::mbar_wait(&pv_done[c - 1], 0);
         tc::tc_fence_after();
       }
-      for (int cc = 0; cc < kAtKC; cc += 32) {
+      AT_STAMP(18 + 2 * c);
+      for (int cc = half * 64; cc < half * 64 + 64; cc += 32) {
         const int c0 = c * kAtKC + cc;
         uint32_t v[32];
         tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
@@ -228,35 +256,49 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
       }
       tc::fence_proxy_async();                               // generic-proxy writes -> visible to the MMA (async proxy)
       tc::mbar_arrive(&p_full[c]);
+      AT_STAMP(19 + 2 * c);
     }
+    s_sum[half * 128 + r] = sum;
     tc::mbar_wait(&pv_done[nchunk - 1], 0);
     tc::tc_fence_after();
-    const float inv = 1.0f / sum;
-    const int q = q0 + r;
-    for (int c0 = 0; c0 < 64; c0 += 32) {
+    AT_STAMP(22);
+    asm volatile("bar.sync 1, 256;" ::: "memory");           // partial sums visible
+    const float inv = 1.0f / (s_sum[r] + s_sum[128 + r]);
+    // O row -> padded staging tile in slot 0 (every MMA that read the slots has completed), then coalesced stores
+    float* stage = reinterpret_cast<float*>(slot[0]);
+    {
       uint32_t v[32];
-      tc::tmem_ld_32x32(tmem_O + lane_base + c0, v);
+      tc::tmem_ld_32x32(tmem_O + lane_base + half * 32, v);
       tc::tmem_ld_wait();
+      float* srow = stage + r * kAtStageLd + half * 32;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4)
+        *reinterpret_cast<float4*>(srow + 4 * j4) = make_float4(__uint_as_float(v[4 * j4]) * inv, __uint_as_float(v[4 * j4 + 1]) * inv,
+                                                                 __uint_as_float(v[4 * j4 + 2]) * inv, __uint_as_float(v[4 * j4 + 3]) * inv);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int st = (int)threadIdx.x - 64;                     // 0..255
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int idx = it * 256 + st;
+      const int row = idx >> 4, c4 = idx & 15;
+      const int q = q0 + row;
       if (q < T) {
-        const long long off = (long long)(row0 + q) * ldo + h * 64 + c0;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          float o[4], oh[4], ol[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            o[j] = __uint_as_float(v[4 * j4 + j]) * inv;
-            split_tf32(o[j], oh[j], ol[j]);
-          }
-          if (out_lo) {
-            *reinterpret_cast<float4*>(out_hi + off + 4 * j4) = make_float4(oh[0], oh[1], oh[2], oh[3]);
-            *reinterpret_cast<float4*>(out_lo + off + 4 * j4) = make_float4(ol[0], ol[1], ol[2], ol[3]);
-          } else {
-            *reinterpret_cast<float4*>(out_hi + off + 4 * j4) = make_float4(o[0], o[1], o[2], o[3]);
-          }
+        const float4 o = *reinterpret_cast<const float4*>(stage + row * kAtStageLd + c4 * 4);
+        const long long off = (long long)(row0 + q) * ldo + h * 64 + c4 * 4;
+        if (out_lo) {
+          float4 oh, ol;
+          split_tf32(o.x, oh.x, ol.x); split_tf32(o.y, oh.y, ol.y); split_tf32(o.z, oh.z, ol.z); split_tf32(o.w, oh.w, ol.w);
+          *reinterpret_cast<float4*>(out_hi + off) = oh;
+          *reinterpret_cast<float4*>(out_lo + off) = ol;
+        } else {
+          *reinterpret_cast<float4*>(out_hi + off) = o;
         }
       }
     }
   }
+  if (threadIdx.x == 64) AT_STAMP(23);
+#undef AT_STAMP
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_S, 512);
@@ -265,7 +307,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
 // qkv_hi / qkv_lo: [B*T, 3*H*64] (q and k are read); vt: V^T [B*H*64, T] (box rows 64); out: [B*T, H*64]
 // (out_lo optional).  T <= 256, T % 8 == 0.
 inline int launch_enc_attention_tc(const TcOperand& qkv, const TcOperand& vt, int B, int T, int H, float* out_hi, float* out_lo,
-                                   bool split3, cudaStream_t s, float* dbg_S = nullptr, int variant = 0) {
+                                   bool split3, cudaStream_t s, float* dbg_S = nullptr, int variant = 0,
+                                   unsigned long long* dbg_t = nullptr) {
   MT3_REQUIRE(T <= 2 * kAtKC && T % 8 == 0, MT3_ERR_UNSUPPORTED, "tc attention: T=%d (needs T <= 256, multiple of 8)", T);
   MT3_REQUIRE(!split3 || qkv.has_lo, MT3_ERR_BAD_ARG, "tc attention: TF32X3 needs hi/lo qkv");
   static bool attr_done = false;
@@ -276,9 +319,9 @@ inline int launch_enc_attention_tc(const TcOperand& qkv, const TcOperand& vt, in
   }
   dim3 grid(cdiv(T, kAtQ), H, B);
   if (split3)
-    enc_attention_tc_kernel<true><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.lo, vt.hi, vt.lo, T, H, out_hi, out_lo, H * 64, dbg_S, variant);
+    enc_attention_tc_kernel<true><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.lo, vt.hi, vt.lo, T, H, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t);
   else
-    enc_attention_tc_kernel<false><<<grid, 192, kAtSmem, s>>>(qkv.hi, qkv.hi, vt.hi, vt.hi, T, H, out_hi, out_lo, H * 64, dbg_S, variant);
+    enc_attention_tc_kernel<false><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.hi, vt.hi, vt.hi, T, H, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t);
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }

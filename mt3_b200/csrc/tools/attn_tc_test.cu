@@ -64,6 +64,27 @@ static int run(int B, int T, int H, int mode, bool split3, int variant) {
   if (launch_enc_attention_tc(op, opv, B, T, H, d_o, split3 ? d_ol : nullptr, split3, 0, d_S, variant) != MT3_OK) return 1;
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("  kernel error: %s\n", cudaGetErrorString(e)); return 2; }
+  if (B == 64 && split3) {   // phase timeline of the production launch (no S dump): CTA (0,0,0) and a mid-grid CTA
+    unsigned long long* d_t;
+    CK(cudaMalloc(&d_t, 64 * 8));
+    for (int rep = 0; rep < 2; ++rep) {
+      CK(cudaMemset(d_t, 0, 64 * 8));
+      if (launch_enc_attention_tc(op, opv, B, T, H, d_o, d_ol, split3, 0, nullptr, 0, d_t) != MT3_OK) return 1;
+      CK(cudaDeviceSynchronize());
+    }
+    unsigned long long t[64];
+    CK(cudaMemcpy(t, d_t, sizeof(t), cudaMemcpyDeviceToHost));
+    const char* mma_names[10] = {"Q landed", "K0 landed", "K1 landed", "S issued", "V0 landed", "P0 ready", "PV0 issued", "V1 landed", "P1 ready", "PV1 issued"};
+    const char* sm_names[8] = {"S done", "row max done", "P0 start", "P0 written", "P1 start (PV0 done)", "P1 written", "PV1 done", "epilogue done"};
+    for (int c = 0; c < 2; ++c) {
+      printf("  timeline CTA %s (us @1.965 GHz): MMA thread:", c == 0 ? "(0,0,0)" : "(0,0,B/2)");
+      for (int i = 0; i < 10; ++i) printf(" %s %.2f |", mma_names[i], t[c * 32 + i] / 1965.0);
+      printf("\n      softmax thread:");
+      for (int i = 0; i < 8; ++i) printf(" %s %.2f |", sm_names[i], t[c * 32 + 16 + i] / 1965.0);
+      printf("\n");
+    }
+    cudaFree(d_t);
+  }
   std::vector<float> o((size_t)M * Q), ol((size_t)M * Q), S((size_t)B * H * T * T);
   CK(cudaMemcpy(o.data(), d_o, o.size() * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(ol.data(), d_ol, o.size() * 4, cudaMemcpyDeviceToHost));
