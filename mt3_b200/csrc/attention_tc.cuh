@@ -48,7 +48,7 @@ constexpr int kAtQ = 128;                 // query rows per CTA
 constexpr int kAtKC = 128;                // keys per chunk
 constexpr int kAtSub = 128 * 32 * 4;      // one [128 x 32] fp32 sub-tile = 16 KB
 constexpr int kVSub = 64 * 32 * 4;        // one [64 d x 32 keys] V^T sub-tile = 8 KB
-constexpr int kAtSmem = 3 * 4 * kAtSub + 1024 + 256 + 2 * 2 * 128 * 4;
+constexpr int kAtSmem = 3 * 4 * kAtSub + 1024 + 512 + 2 * 2 * 128 * 4;
 constexpr int kAtThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / epilogue (two per TMEM lane group)
 constexpr int kAtStageLd = 68;            // padded row of the O staging tile (floats)
 
@@ -75,10 +75,10 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
   uint64_t* k_full = bars + 1;              // [2] K chunk landed
   uint64_t* v_full = bars + 3;              // [2] V chunk landed
   uint64_t* s_done = bars + 5;              // all S MMAs complete
-  uint64_t* p_full = bars + 6;              // [2] P chunk written (128 arrivals)
-  uint64_t* pv_done = bars + 8;             // [2] PV MMAs of chunk c complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  float* s_max = reinterpret_cast<float*>(bars + 16);      // [2 halves][128 rows] partial row maxima
+  uint64_t* p_full = bars + 6;              // [8] P quarter-chunk (32 keys) written (128 arrivals: the 4 warps of one half)
+  uint64_t* pv_done = bars + 14;            // [8] PV MMAs of quarter-chunk complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  float* s_max = reinterpret_cast<float*>(bars + 24);      // [2 halves][128 rows] partial row maxima
   float* s_sum = s_max + 256;                              // [2 halves][128 rows] partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,7 +96,9 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
     for (int c = 0; c < 2; ++c) {
       tc::mbar_init(&k_full[c], 1);
       tc::mbar_init(&v_full[c], 1);
-      tc::mbar_init(&p_full[c], 256);
+    }
+    for (int c = 0; c < 8; ++c) {
+      tc::mbar_init(&p_full[c], 128);
       tc::mbar_init(&pv_done[c], 1);
     }
     tc::mbar_init(s_done, 1);
@@ -172,27 +174,33 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
       }
       tc::mma_commit(s_done);
       AT_STAMP(3);
-      // ---- O = P V ----  A = P chunk in the Q region (K-major, 4 sub-tiles of 32 keys), B = V chunk (MN-major)
+      // ---- O = P V ----  quarter-chunks of 32 keys: A = P sub-tile (K-major, one of the 4 sub-tile buffers in the Q
+      // region), B = V^T sub-tile [64 d x 32 keys].  The two softmax halves fill their buffers concurrently, so the
+      // quarter-chunks become ready in the order 0,2,1,3 (chunk 0) 4,6,5,7 (chunk 1); issue in that order.
       constexpr uint32_t idesc_o = tc::make_idesc(tc::kFmtTF32, 128, 64, 0, 0);
       uint32_t acc = 0;
-      for (int c = 0; c < nchunk; ++c) {
-        tc::mbar_wait(&v_full[c], 0);
-        AT_STAMP(4 + 3 * c);
-        tc::mbar_wait(&p_full[c], 0);
-        AT_STAMP(5 + 3 * c);
-        tc::tc_fence_after();
-        const uint32_t p_addr = tc::smem_u32(sQ);
-        const uint32_t v_addr = tc::smem_u32(slot[c]);
-#pragma unroll
-        for (int ks = 0; ks < kAtKC / 8; ++ks) {             // 128 keys = 16 k-steps of 8
-          const uint64_t a = tc::smem_desc_k_sw128(p_addr + (ks >> 2) * kSubBytes + (ks & 3) * 32);
-          const uint32_t voff = (ks >> 2) * kVSub + (ks & 3) * 32;
-          tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + voff), idesc_o, acc);
-          acc = 1u;
-          if (SPLIT3) tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + 4 * kVSub + voff), idesc_o, 1u);
+      const int nq = nchunk * 4;
+      for (int i = 0; i < nq; ++i) {
+        const int qc = (i & ~3) | ((i & 1) << 1) | ((i >> 1) & 1);      // 0,2,1,3,4,6,5,7
+        const int c = qc >> 2, sub = qc & 3;
+        if (sub == 0 || i == (c << 2)) {
+          tc::mbar_wait(&v_full[c], 0);
+          AT_STAMP(4 + 3 * c);
         }
-        tc::mma_commit(&pv_done[c]);
-        AT_STAMP(6 + 3 * c);
+        tc::mbar_wait(&p_full[qc], 0);
+        if (i == (c << 2)) AT_STAMP(5 + 3 * c);
+        tc::tc_fence_after();
+        const uint32_t p_addr = tc::smem_u32(sQ) + sub * kSubBytes;
+        const uint32_t v_addr = tc::smem_u32(slot[c]) + sub * kVSub;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {                       // 32 keys = 4 k-steps of 8
+          const uint64_t a = tc::smem_desc_k_sw128(p_addr + ks * 32);
+          tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + ks * 32), idesc_o, acc);
+          acc = 1u;
+          if (SPLIT3) tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + 4 * kVSub + ks * 32), idesc_o, 1u);
+        }
+        tc::mma_commit(&pv_done[qc]);
+        if ((i & 3) == 3) AT_STAMP(6 + 3 * c);
       }
     }
   } else {
@@ -228,14 +236,16 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
     mx = fmaxf(s_max[r], s_max[128 + r]);
     AT_STAMP(17);
     float sum = 0.f;
+    int last_qc = 0;
     for (int c = 0; c < nchunk; ++c) {
-      if (c > 0) {                                           // P buffer is recycled: wait for chunk c-1's MMAs
-        tc::mbar_wait(&pv_done[c - 1], 0);
-        tc::tc_fence_after();
-      }
       AT_STAMP(18 + 2 * c);
-      for (int cc = half * 64; cc < half * 64 + 64; cc += 32) {
-        const int c0 = c * kAtKC + cc;
+      for (int sub = half * 2; sub < half * 2 + 2; ++sub) {  // this half's two quarter-chunks of chunk c -> P buffers `sub`
+        const int qc = c * 4 + sub;
+        const int c0 = c * kAtKC + sub * 32;
+        if (c > 0) {                                         // the buffer was read by quarter-chunk qc - 4's MMAs
+          tc::mbar_wait(&pv_done[qc - 4], 0);
+          tc::tc_fence_after();
+        }
         uint32_t v[32];
         tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
         tc::tmem_ld_wait();
@@ -248,18 +258,20 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
           p[j] = e;
           sum += e;
         }
-        // sub-tile (cc/32) of the P chunk, row r, 8 x 16-byte pieces XOR-swizzled by (r % 8)
-        uint8_t* rowp = sQ + (cc >> 5) * kAtSub + r * 128;
+        // P sub-tile buffer `sub`, row r, 8 x 16-byte pieces XOR-swizzled by (r % 8)
+        uint8_t* rowp = sQ + sub * kAtSub + r * 128;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4)
           *reinterpret_cast<float4*>(rowp + ((j4 ^ (r & 7)) << 4)) = make_float4(p[4 * j4], p[4 * j4 + 1], p[4 * j4 + 2], p[4 * j4 + 3]);
+        tc::fence_proxy_async();                             // generic-proxy writes -> visible to the MMA (async proxy)
+        tc::mbar_arrive(&p_full[qc]);
+        last_qc = qc;
       }
-      tc::fence_proxy_async();                               // generic-proxy writes -> visible to the MMA (async proxy)
-      tc::mbar_arrive(&p_full[c]);
       AT_STAMP(19 + 2 * c);
     }
+    (void)last_qc;
     s_sum[half * 128 + r] = sum;
-    tc::mbar_wait(&pv_done[nchunk - 1], 0);
+    tc::mbar_wait(&pv_done[nchunk * 4 - 1], 0);               // issued last (order .. 5,7): covers every earlier MMA
     tc::tc_fence_after();
     AT_STAMP(22);
     asm volatile("bar.sync 1, 256;" ::: "memory");           // partial sums visible
