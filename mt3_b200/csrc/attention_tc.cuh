@@ -38,10 +38,19 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
+// Round a non-negative finite float to tf32 (10 explicit mantissa bits), ties away from zero, on the integer pipe:
+// cvt.rna.tf32.f32 runs on the same quarter-rate unit as ex2 and doubled the cost of the exp pass.
+#ifndef MT3_AT_INT_ROUND
+#define MT3_AT_INT_ROUND 0
+#endif
 __device__ __forceinline__ float round_tf32(float x) {
+#if MT3_AT_INT_ROUND
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+#else
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+#endif
 }
 
 constexpr int kAtQ = 128;                 // query rows per CTA
@@ -50,6 +59,7 @@ constexpr int kAtSub = 128 * 32 * 4;      // one [128 x 32] fp32 sub-tile = 16 K
 constexpr int kVSub = 64 * 32 * 4;        // one [64 d x 32 keys] V^T sub-tile = 8 KB
 constexpr int kAtSmem = 3 * 4 * kAtSub + 1024 + 512 + 2 * 2 * 128 * 4;
 constexpr int kAtThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / epilogue (two per TMEM lane group)
+constexpr int kAtSplitAcc = 0;             // 1: P.Vhi and P.Vlo into separate TMEM accumulators (measured slower)
 constexpr int kAtStageLd = 68;            // padded row of the O staging tile (floats)
 
 template <bool SPLIT3>
@@ -112,7 +122,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_S = *tmem_slot;            // columns [0, 256)
-  const uint32_t tmem_O = tmem_S + 256;          // columns [256, 320)
+  const uint32_t tmem_O = tmem_S + 256;          // columns [256, 512): four 64-column partial accumulators (see P.V)
 
   if (warp == 0) {
     if (tc::elect_one()) {
@@ -177,8 +187,11 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
       // ---- O = P V ----  quarter-chunks of 32 keys: A = P sub-tile (K-major, one of the 4 sub-tile buffers in the Q
       // region), B = V^T sub-tile [64 d x 32 keys].  The two softmax halves fill their buffers concurrently, so the
       // quarter-chunks become ready in the order 0,2,1,3 (chunk 0) 4,6,5,7 (chunk 1); issue in that order.
+      // Back-to-back MMAs into ONE small accumulator serialise on its ~100-cycle read-modify-write latency (N = 64 is
+      // 16 cycles of math), so the products go round-robin into four accumulators (hi/lo term x k-step parity) that
+      // the epilogue adds.
       constexpr uint32_t idesc_o = tc::make_idesc(tc::kFmtTF32, 128, 64, 0, 0);
-      uint32_t acc = 0;
+      uint32_t acc_used = 0;                   // bit a set: accumulator a has been written
       const int nq = nchunk * 4;
       for (int i = 0; i < nq; ++i) {
         const int qc = (i & ~3) | ((i & 1) << 1) | ((i >> 1) & 1);      // 0,2,1,3,4,6,5,7
@@ -195,9 +208,13 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {                       // 32 keys = 4 k-steps of 8
           const uint64_t a = tc::smem_desc_k_sw128(p_addr + ks * 32);
-          tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + ks * 32), idesc_o, acc);
-          acc = 1u;
-          if (SPLIT3) tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + 4 * kVSub + ks * 32), idesc_o, 1u);
+          const uint32_t a0 = 0u, a1 = kAtSplitAcc ? 2u : 0u;    // one accumulator (or hi / lo terms apart)
+          tc::mma_tf32(tmem_O + 64 * a0, a, tc::smem_desc_k_sw128(v_addr + ks * 32), idesc_o, (acc_used >> a0) & 1u);
+          acc_used |= 1u << a0;
+          if (SPLIT3) {
+            tc::mma_tf32(tmem_O + 64 * a1, a, tc::smem_desc_k_sw128(v_addr + 4 * kVSub + ks * 32), idesc_o, (acc_used >> a1) & 1u);
+            acc_used |= 1u << a1;
+          }
         }
         tc::mma_commit(&pv_done[qc]);
         if ((i & 3) == 3) AT_STAMP(6 + 3 * c);
@@ -215,22 +232,26 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
     if (threadIdx.x != 64) tslot = nullptr;                  // one stamping thread among the softmax warps
     AT_STAMP(16);
     float mx = -INFINITY;
-    for (int c = 0; c < nchunk; ++c)
-      for (int cc = half * 64; cc < half * 64 + 64; cc += 32) {
-        const int c0 = c * kAtKC + cc;
-        if (c0 >= T) continue;
-        uint32_t v[32];
-        tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
-        tc::tmem_ld_wait();
+    for (int c = 0; c < nchunk; ++c) {
+      const int c0 = c * kAtKC + half * 64;                  // this half's 64 columns of the chunk: both loads in flight
+      if (c0 >= T) continue;
+      uint32_t v[32], w[32];
+      tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
+      tc::tmem_ld_32x32(tmem_S + lane_base + c0 + 32, w);
+      tc::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
-        if (dbg_S && q0 + r < T) {
-          float* drow = dbg_S + (((long long)b * H + h) * T + q0 + r) * T + c0;
-          for (int j = 0; j < 32; ++j)
-            if (c0 + j < T) drow[j] = __uint_as_float(v[j]);
+      for (int j = 0; j < 32; ++j) {
+        if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+        if (c0 + 32 + j < T) mx = fmaxf(mx, __uint_as_float(w[j]));
+      }
+      if (dbg_S && q0 + r < T) {
+        float* drow = dbg_S + (((long long)b * H + h) * T + q0 + r) * T + c0;
+        for (int j = 0; j < 32; ++j) {
+          if (c0 + j < T) drow[j] = __uint_as_float(v[j]);
+          if (c0 + 32 + j < T) drow[32 + j] = __uint_as_float(w[j]);
         }
       }
+    }
     s_max[half * 128 + r] = mx;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     mx = fmaxf(s_max[r], s_max[128 + r]);
@@ -282,11 +303,19 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
       uint32_t v[32];
       tc::tmem_ld_32x32(tmem_O + lane_base + half * 32, v);
       tc::tmem_ld_wait();
+      float o[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
+      if (SPLIT3 && kAtSplitAcc) {                            // the lo-term accumulator
+        tc::tmem_ld_32x32(tmem_O + lane_base + 128 + half * 32, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] += __uint_as_float(v[j]);
+      }
       float* srow = stage + r * kAtStageLd + half * 32;
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4)
-        *reinterpret_cast<float4*>(srow + 4 * j4) = make_float4(__uint_as_float(v[4 * j4]) * inv, __uint_as_float(v[4 * j4 + 1]) * inv,
-                                                                 __uint_as_float(v[4 * j4 + 2]) * inv, __uint_as_float(v[4 * j4 + 3]) * inv);
+        *reinterpret_cast<float4*>(srow + 4 * j4) = make_float4(o[4 * j4] * inv, o[4 * j4 + 1] * inv, o[4 * j4 + 2] * inv, o[4 * j4 + 3] * inv);
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const int st = (int)threadIdx.x - 64;                     // 0..255
