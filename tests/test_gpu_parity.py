@@ -439,6 +439,64 @@ def test_inference_model_api_end_to_end():
     np.testing.assert_array_equal(out[:, :6][safe], O.vocab_decode(ref[:, :6], 1514)[safe])
 
 
+def test_baseline_config4_ten_minute_stream_logmel(spec_cfg):
+    """BASELINE configs[3]: log-mel of a 10 min / 16 kHz stream (9.6 M samples -> 75 001 frames -> 293 segments, the
+    last one short).  Segment-wise GPU frames == one-shot GPU frames (segments are independent, spectral_ops.py:35-48
+    frames never cross a segment), and sampled segments == the float64 oracle."""
+    from mt3_b200 import spectrograms
+    n = 10 * 60 * 16000
+    rng = np.random.default_rng(11)
+    t = np.arange(n, dtype=np.float64) / 16000.0
+    audio = (0.3 * np.sin(2 * np.pi * (220.0 + 40.0 * np.sin(0.05 * t)) * t) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    padded = np.pad(audio, [0, 128 - n % 128])
+    frames = padded.reshape(-1, 128)
+    assert frames.shape[0] == 75001
+    S = -(-frames.shape[0] // 256)
+    assert S == 293
+    segs = np.zeros((S, 256 * 128), np.float32)
+    flat = frames.reshape(-1)
+    segs.reshape(-1)[:flat.size] = flat
+    n_valid = np.full((S,), 256, np.int32)
+    n_valid[-1] = frames.shape[0] - 292 * 256
+    lm = spectrograms.compute_spectrogram(torch.from_numpy(segs).to(DEV), spec_cfg,
+                                          n_valid_frames=torch.from_numpy(n_valid).to(DEV)).cpu().numpy()
+    assert lm.shape == (293, 256, 512)
+    assert (lm[-1, n_valid[-1]:] == 0).all()                     # feature-converter zero rows
+    for i in (0, 146, 291):
+        _mel_close(lm[i], O.compute_spectrogram(segs[i].astype(np.float64), np.float64))
+    last = O.compute_spectrogram(segs[-1, :n_valid[-1] * 128].astype(np.float64), np.float64)
+    _mel_close(lm[-1, :n_valid[-1]], last)
+    # batch composition does not matter: a segment alone == the same segment inside the 293-segment launch
+    solo = spectrograms.compute_spectrogram(torch.from_numpy(segs[146]).to(DEV), spec_cfg).cpu().numpy()
+    np.testing.assert_array_equal(solo, lm[146])
+
+
+def test_baseline_config5_long_form_three_minutes():
+    """BASELINE configs[4]: 3 min of audio -> 88 non-overlapping segments (87 full + one of 229 frames) -> tokens ->
+    stitched NoteSequence, in two GPU batches of 64 + 24; batch composition must not change any token stream."""
+    from mt3_b200 import inference, note_decoding
+    im = inference.InferenceModel('synthetic:0', 'mt3', device=DEV, batch_size=64)
+    n = 3 * 60 * 16000
+    audio = np.concatenate([O.sine_mix(32768, 100 + i) for i in range(-(-n // 32768))])[:n]
+    ds = im.preprocess(im.audio_to_dataset(audio))
+    assert len(ds) == 88 and ds[-1]['inputs'].shape[0] == 229
+    im.outputs_length = 1024
+    preds = im.predict_segments(audio)
+    assert len(preds) == 88
+    assert round(preds[1]['start_time'], 3) == 2.04 and round(preds[87]['start_time'], 2) == round(int(87 * 2.048 * 100) / 100, 2)
+    ns = note_decoding.event_predictions_to_ns(preds, im.codec, im.encoding_spec)['est_ns']
+    assert isinstance(ns, note_decoding.NoteSequence)
+    # the same segments one at a time (batch of 1) give the same decoded token streams
+    hop = im.spectrogram_config.hop_width
+    for i in (0, 63, 64, 87):
+        flat = np.asarray(ds[i]['inputs'], np.float32).reshape(-1)
+        seg = np.zeros((1, 256 * hop), np.float32)
+        seg[0, :flat.size] = flat
+        one = im.transcribe_segments(seg, n_valid_frames=np.array([flat.size // hop], np.int32))
+        trimmed = one[0][:len(preds[i]['est_tokens'])]
+        np.testing.assert_array_equal(trimmed, preds[i]['est_tokens'])
+
+
 # ------------------------------------------------------------------------------------------------
 # tcgen05 GEMM modes (encoder + cross-K/V on the tensor cores)
 # ------------------------------------------------------------------------------------------------
