@@ -231,6 +231,76 @@ logmel2048_kernel(const float* __restrict__ audio, long long audio_stride, int n
   }
 }
 
+// Any power-of-two FFT size other than the reference's 2048 (BASELINE configs[3] sweeps 1024 / 2048 / 4096; the reference
+// itself only ever uses 2048, spectrograms.py:27-28).  Same arithmetic contract, plain structure: one CTA per frame,
+// real FFT of size N as a complex radix-2 DIF FFT of size N/2 in shared memory (output bit-reversed, read back through
+// the bit-reversed index), untangle, magnitude, banded mel, safe log.  Tables (window, W_N^k) come from global memory.
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR)
+logmel_pow2_kernel(const float* __restrict__ audio, long long audio_stride, int n_samples, int hop, int fft, int log2_nc,
+                   const int* __restrict__ n_valid_frames, int T, const float* __restrict__ window,
+                   const float2* __restrict__ rtw, const int* __restrict__ mel_bin0, const float* __restrict__ mel_wpad,
+                   int mel_taps, int n_mel, float log_eps, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  const int nc = fft >> 1;
+  float2* z = reinterpret_cast<float2*>(smem);             // [nc]
+  float* mag = smem + 2 * nc;                              // [nc + 1]
+  const int seg = blockIdx.y, t = blockIdx.x, tid = threadIdx.x;
+  float* orow = out + ((long long)seg * T + t) * n_mel;
+  const int n_valid = n_valid_frames ? n_valid_frames[seg] : T;
+  if (t >= n_valid) {                                      // feature-converter zero padding
+    for (int m = tid; m < n_mel; m += NTHR) orow[m] = 0.f;
+    return;
+  }
+  const float* a = audio + (long long)seg * audio_stride;
+  const long long s0 = (long long)t * hop;
+  for (int n = tid; n < nc; n += NTHR) {
+    const long long g = s0 + 2 * n;
+    const float x0 = (g < n_samples) ? __ldg(a + g) : 0.f;             // pad_end=True zeros
+    const float x1 = (g + 1 < n_samples) ? __ldg(a + g + 1) : 0.f;
+    z[n] = make_float2(x0 * __ldg(window + 2 * n), x1 * __ldg(window + 2 * n + 1));
+  }
+  __syncthreads();
+  // radix-2 decimation in frequency: stage with half-span h: (a, b) -> (a + b, (a - b) W_nc^(j * nc / (2h)))
+  for (int h = nc >> 1; h >= 1; h >>= 1) {
+    const int tw_step = (nc / (2 * h)) * 2;                // W_nc^m = W_fft^(2m): index into rtw (W_fft^k, k < fft/2)
+    for (int i = tid; i < (nc >> 1); i += NTHR) {
+      const int j = i & (h - 1);
+      const int ia = ((i - j) << 1) + j, ib = ia + h;
+      const float2 va = z[ia], vb = z[ib];
+      const float dr = va.x - vb.x, di = va.y - vb.y;
+      const float2 w = __ldg(rtw + j * tw_step);
+      z[ia] = make_float2(va.x + vb.x, va.y + vb.y);
+      z[ib] = make_float2(dr * w.x - di * w.y, dr * w.y + di * w.x);
+    }
+    __syncthreads();
+  }
+  // untangle: X[k] = E[k] + W_fft^k O[k], E = (Z[k] + conj Z[nc-k]) / 2, O = (Z[k] - conj Z[nc-k]) / (2i); Z[k] = z[brev(k)]
+  const int shift = 32 - log2_nc;
+  for (int k = tid; k <= nc; k += NTHR) {
+    if (k == 0 || k == nc) {
+      const float2 z0 = z[0];
+      mag[k] = (k == 0) ? fabsf(z0.x + z0.y) : fabsf(z0.x - z0.y);
+      continue;
+    }
+    const float2 zk = z[__brev((unsigned)k) >> shift];
+    const float2 zq = z[__brev((unsigned)(nc - k)) >> shift];
+    const float er = 0.5f * (zk.x + zq.x), ei = 0.5f * (zk.y - zq.y);
+    const float orr = 0.5f * (zk.y + zq.y), oi = -0.5f * (zk.x - zq.x);
+    const float2 w = __ldg(rtw + k);
+    const float Xr = er + (w.x * orr - w.y * oi);
+    const float Xi = ei + (w.x * oi + w.y * orr);
+    mag[k] = sqrtf(Xr * Xr + Xi * Xi);
+  }
+  __syncthreads();
+  for (int m = tid; m < n_mel; m += NTHR) {
+    const float* mg = mag + __ldg(mel_bin0 + m);
+    float acc = 0.f;
+    for (int j = 0; j < mel_taps; ++j) acc = fmaf(mg[j], __ldg(mel_wpad + j * n_mel + m), acc);
+    orow[m] = logf(acc <= 0.f ? log_eps : acc);            // safe_log: replace, not add
+  }
+}
+
 }  // namespace
 
 }  // namespace mt3
@@ -239,27 +309,28 @@ using namespace mt3;
 
 extern "C" int mt3_frontend_create(const mt3_frontend_config* cfg, const float* mel_matrix, mt3_frontend** out) {
   MT3_REQUIRE(cfg && mel_matrix && out, MT3_ERR_BAD_ARG, "mt3_frontend_create: null argument");
-  MT3_REQUIRE(cfg->fft_size == kFft, MT3_ERR_UNSUPPORTED,
-              "mt3_frontend_create: fft_size %d unsupported (the reference fixes FFT_SIZE=2048, spectrograms.py:27-28)",
-              cfg->fft_size);
-  MT3_REQUIRE(cfg->hop_width > 0 && cfg->hop_width % 2 == 0 && cfg->hop_width <= kFft, MT3_ERR_BAD_ARG,
-              "mt3_frontend_create: hop_width %d must be even and in (0, %d]", cfg->hop_width, kFft);
+  const int fft = cfg->fft_size;
+  MT3_REQUIRE(fft >= 64 && fft <= 16384 && (fft & (fft - 1)) == 0, MT3_ERR_UNSUPPORTED,
+              "mt3_frontend_create: fft_size %d unsupported (power of two in [64, 16384]; the reference fixes 2048, "
+              "spectrograms.py:27-28)", fft);
+  MT3_REQUIRE(cfg->hop_width > 0 && cfg->hop_width % 2 == 0 && cfg->hop_width <= fft, MT3_ERR_BAD_ARG,
+              "mt3_frontend_create: hop_width %d must be even and in (0, %d]", cfg->hop_width, fft);
   MT3_REQUIRE(cfg->num_mel_bins > 0 && cfg->sample_rate > 0, MT3_ERR_BAD_ARG, "mt3_frontend_create: bad sizes");
   Frontend* fe = new Frontend();
   fe->cfg = *cfg;
   fe->n_bins = cfg->fft_size / 2 + 1;
   const int n_mel = cfg->num_mel_bins;
 
-  std::vector<float> win(kFft);
-  for (int i = 0; i < kFft; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / kFft));  // periodic Hann
-  std::vector<float2> tw(32 * 32), rt(kHalf);
+  std::vector<float> win(fft);
+  for (int i = 0; i < fft; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / fft));  // periodic Hann
+  std::vector<float2> tw(32 * 32), rt(fft / 2);
   for (int k1 = 0; k1 < 32; ++k1)
     for (int l = 0; l < 32; ++l) {
       const double th = -2.0 * M_PI * (double)(k1 * l) / 1024.0;
       tw[k1 * 32 + l] = make_float2((float)cos(th), (float)sin(th));
     }
-  for (int k = 0; k < kHalf; ++k) {
-    const double th = -2.0 * M_PI * (double)k / 2048.0;
+  for (int k = 0; k < fft / 2; ++k) {                       // W_fft^k
+    const double th = -2.0 * M_PI * (double)k / (double)fft;
     rt[k] = make_float2((float)cos(th), (float)sin(th));
   }
   // banded form of the [n_bins, n_mel] matrix: per mel bin the contiguous span of non-zero FFT bins, padded
@@ -327,6 +398,24 @@ extern "C" int mt3_logmel_f32(const mt3_frontend* h, const float* audio, int64_t
   const Frontend* fe = reinterpret_cast<const Frontend*>(h);
   const int hop = fe->cfg.hop_width;
   const int T = (n_samples + hop - 1) / hop;
+  if (fe->cfg.fft_size != kFft) {
+    const int fft = fe->cfg.fft_size, nc = fft / 2;
+    int log2_nc = 0;
+    while ((1 << log2_nc) < nc) ++log2_nc;
+    constexpr int NT = 256;
+    const size_t smem_g = (size_t)(2 * nc + nc + 4) * sizeof(float);
+    static bool attr_g = false;
+    if (!attr_g) {
+      MT3_CUDA_CHECK(cudaFuncSetAttribute(logmel_pow2_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_g = true;
+    }
+    MT3_REQUIRE(T <= 2147483647 / 2 && smem_g <= 200 * 1024, MT3_ERR_UNSUPPORTED, "mt3_logmel_f32: fft %d too large", fft);
+    logmel_pow2_kernel<NT><<<dim3(T, num_segments), NT, smem_g, (cudaStream_t)stream>>>(
+        audio, audio_stride, n_samples, hop, fft, log2_nc, n_valid_frames, T, fe->d_window, fe->d_rtw, fe->d_mel_bin0, fe->d_mel_w,
+        fe->taps, fe->cfg.num_mel_bins, fe->cfg.log_eps, out);
+    MT3_LAUNCH_CHECK();
+    return MT3_OK;
+  }
   constexpr int F = 16, W = 4;   // 16 frames per CTA, 4 warps: ~96 KB of smem incl. all tables -> two CTAs per SM
   const int chunk = (F - 1) * hop + kFft;
   const int n_mel = fe->cfg.num_mel_bins;

@@ -471,6 +471,25 @@ def test_baseline_config4_ten_minute_stream_logmel(spec_cfg):
     np.testing.assert_array_equal(solo, lm[146])
 
 
+@pytest.mark.parametrize("fft", [512, 1024, 4096])
+def test_logmel_other_fft_sizes(fft):
+    """BASELINE configs[3] sweeps FFT sizes 1024 / 2048 / 4096 at hop 128 and 512 mel bins.  Only 2048 exists in the
+    reference (spectrograms.py:27-28); the other sizes go through the generic power-of-two kernel and are checked
+    against the same restated pipeline (spectral_ops.py:29-88) in float64."""
+    from mt3_b200 import spectral_ops
+    bins, hop = (512 if fft >= 1024 else 128), 128
+    audio = np.stack([O.sine_mix(8 * 1024 + 77, 900 + i) for i in range(3)]).astype(np.float32)
+    audio[2] = np.random.default_rng(9).uniform(-1, 1, audio.shape[1]).astype(np.float32)
+    got = spectral_ops.compute_logmel(torch.from_numpy(audio).to(DEV), lo_hz=20.0, hi_hz=7600.0, bins=bins, fft_size=fft,
+                                      overlap=1.0 - hop / fft).cpu().numpy()
+    want = O.compute_logmel(audio.astype(np.float64), bins=bins, lo_hz=20.0, hi_hz=7600.0, fft_size=fft, hop=hop, dtype=np.float64)
+    assert got.shape == want.shape == (3, -(-audio.shape[1] // hop), bins)
+    _mel_close(got, want)
+    z = spectral_ops.compute_logmel(torch.zeros(1000, device=DEV), lo_hz=20.0, hi_hz=7600.0, bins=bins, fft_size=fft,
+                                    overlap=1.0 - hop / fft).cpu().numpy()
+    np.testing.assert_allclose(z, np.log(np.float32(1e-5)), rtol=1e-6)
+
+
 def test_baseline_config5_long_form_three_minutes():
     """BASELINE configs[4]: 3 min of audio -> 88 non-overlapping segments (87 full + one of 229 frames) -> tokens ->
     stitched NoteSequence, in two GPU batches of 64 + 24; batch composition must not change any token stream."""
