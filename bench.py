@@ -346,6 +346,28 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize(dev)
             kernels_us[name] = 1000.0 * e0.elapsed_time(e1) / it_
+        # K1 at the bench shape (64 segments) and BASELINE configs[3]: 10 min stream, FFT 1024 / 2048 / 4096 at hop 128
+        from mt3_b200 import spectral_ops
+        def time_logmel(a, fft, iters=5):
+            kw = dict(lo_hz=20.0, hi_hz=7600.0, bins=512, fft_size=fft, overlap=1.0 - 128.0 / fft)
+            spectral_ops.compute_logmel(a, **kw)
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                spectral_ops.compute_logmel(a, **kw)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return 1000.0 * e0.elapsed_time(e1) / iters
+        kernels_us["logmel_fft2048_64x2.048s"] = time_logmel(audio_dev, 2048, 20)
+        stream10 = torch.from_numpy(synth_audio(293, 99)).to(dev)          # 293 x 32768 samples = 10 min
+        sweep = {}
+        for fft in (1024, 2048, 4096):
+            us = time_logmel(stream10, fft, 3)
+            alg = 293 * (32768 * 4 + 256 * 512 * 4)
+            sweep[f"fft{fft}"] = {"us": us, "algorithmic_GBps": alg / (us * 1e-6) / 1e9, "frac_of_hbm_peak": alg / (us * 1e-6) / 1e9 / peak}
+        del stream10
+        roofline["logmel_10min_stream_sweep"] = sweep
         roofline["other_kernels_us_per_launch"] = kernels_us
         log("kernel microbench: " + ", ".join(f"{k}={v:.1f}us" for k, v in kernels_us.items()))
         if world == 1 and not args.no_cpu_baseline:

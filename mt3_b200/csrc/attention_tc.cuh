@@ -15,7 +15,8 @@
 //                               in bring-up, so V is transposed once at its producer instead.)
 // TMEM: S = 256 columns, O = 64 columns (512 allocated).  Shared memory (192 KB):
 //   [ Q hi/lo 64 KB | slot0 64 KB | slot1 64 KB ]   slots hold K chunk c (hi/lo) and later V chunk c (hi/lo);
-//   the Q region is recycled as the P chunk buffer once the S MMAs have completed.
+//   the Q region is recycled as four 32-key P sub-tile buffers once the S MMAs have completed; slot 0 stages O.
+// 320 threads: warp 0 TMA, warp 1 MMA issue, warps 2..9 softmax / epilogue (two warps per TMEM lane group).
 // Operands come straight from the qkv buffers the QKV GEMM epilogue wrote ([B*T, 3*H*64] hi and lo)
 // through two TMA tensor maps; output is [B*T, H*64] (hi/lo split for the out-projection GEMM).
 #pragma once
@@ -26,20 +27,6 @@
 
 namespace mt3 {
 
-// MN-major operand, 128B swizzle: rows are K (128 B = 32 MN elements each), 8-row atoms 1024 B apart
-// (stride byte offset), the next 32 MN elements `lbo_bytes` away (leading byte offset).
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// Round a non-negative finite float to tf32 (10 explicit mantissa bits), ties away from zero, on the integer pipe:
-// cvt.rna.tf32.f32 runs on the same quarter-rate unit as ex2 and doubled the cost of the exp pass.
 #ifndef MT3_AT_INT_ROUND
 #define MT3_AT_INT_ROUND 0
 #endif
