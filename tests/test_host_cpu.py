@@ -217,11 +217,13 @@ def test_abi_library_exports_every_declared_symbol():
     # argument validation happens before any CUDA call -> testable without a GPU
     assert lib.mt3_frontend_create(None, None, None) == -1
     assert b"null" in lib.mt3_last_error()
-    cfg = _lib.FrontendConfig(16000, 128, 1024, 512, 1e-5)
+    cfg = _lib.FrontendConfig(16000, 128, 1000, 512, 1e-5)       # FFT sizes must be powers of two
     h = C.c_void_p()
-    mel = np.zeros((513, 512), np.float32)
+    mel = np.zeros((501, 512), np.float32)
     assert lib.mt3_frontend_create(C.byref(cfg), mel.ctypes.data_as(C.c_void_p), C.byref(h)) == -3
-    assert b"2048" in lib.mt3_last_error()
+    assert b"power of two" in lib.mt3_last_error() and b"2048" in lib.mt3_last_error()
+    cfg = _lib.FrontendConfig(16000, 127, 2048, 512, 1e-5)       # odd hop
+    assert lib.mt3_frontend_create(C.byref(cfg), mel.ctypes.data_as(C.c_void_p), C.byref(h)) == -1
     assert lib.mt3_workspace_bytes(None, 1, 1) == -1
     assert lib.mt3_encode(None, None, None, None) == -1
 
