@@ -40,55 +40,67 @@ __device__ __forceinline__ float round_tf32(float x) {
 #endif
 }
 
-constexpr int kAtQ = 128;                 // query rows per CTA
+constexpr int kAtQ = 128;                 // query rows per work item
 constexpr int kAtKC = 128;                // keys per chunk
 constexpr int kAtSub = 128 * 32 * 4;      // one [128 x 32] fp32 sub-tile = 16 KB
 constexpr int kVSub = 64 * 32 * 4;        // one [64 d x 32 keys] V^T sub-tile = 8 KB
-constexpr int kAtSmem = 3 * 4 * kAtSub + 1024 + 512 + 2 * 2 * 128 * 4;
+constexpr int kAtStage = 128 * 64 * 4;    // O staging tile (XOR-swizzled rows of 256 B) = 32 KB
+constexpr int kAtSmem = 3 * 4 * kAtSub + kAtStage + 256 + 2 * 2 * 128 * 4;   // 231 680 B of the 232 448 a CTA may have: no
+                                                                              // slack, the dynamic window must be 1024-aligned
 constexpr int kAtThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / epilogue (two per TMEM lane group)
-constexpr int kAtSplitAcc = 0;             // 1: P.Vhi and P.Vlo into separate TMEM accumulators (measured slower)
-constexpr int kAtStageLd = 68;            // padded row of the O staging tile (floats)
 
+// PERSISTENT: one CTA per SM walks over work items (sequence b, head h, 128-query tile) with stride gridDim.x.  All
+// mbarriers complete exactly once per item, so the wait parity is (item counter & 1).  While the softmax warps are
+// still in item i, the TMA thread already streams item i+1: K chunk 0 as soon as the P.V MMAs that read V chunk 0 are
+// done, Q and K chunk 1 as soon as the last P.V MMA is done (the Q region doubles as the P buffers); the MMA thread
+// issues S(i+1) as soon as the softmax warps have finished reading S(i) out of TMEM, i.e. under the epilogue of i.
 template <bool SPLIT3>
 __global__ void __launch_bounds__(kAtThreads, 1)
 enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
-                        const __grid_constant__ CUtensorMap tv_hi, const __grid_constant__ CUtensorMap tv_lo, int T, int H,
+                        const __grid_constant__ CUtensorMap tv_hi, const __grid_constant__ CUtensorMap tv_lo, int T, int H, int B,
                         float* __restrict__ out_hi, float* __restrict__ out_lo, int ldo, float* __restrict__ dbg_S,
                         int variant, unsigned long long* __restrict__ dbg_t) {
-  // dbg_S (bring-up tool only): raw S rows [B][H][T][T].  dbg_t (tool only): SM-clock stamps of CTA (0,0,0) -> [0..31]
-  // and of the CTA (0,0,gridDim.z/2) -> [32..63]: MMA thread in slots 0.., first softmax thread in slots 16..
+  // dbg_S (bring-up tool only): raw S rows [B][H][T][T].  dbg_t (tool only): SM-clock stamps of CTA 0's first item ->
+  // [0..31] and third item -> [32..63]: MMA thread in slots 0.., first softmax thread in slots 16..
   (void)variant;
   const long long t_start = clock64();
   unsigned long long* tslot = nullptr;
-  if (dbg_t && blockIdx.x == 0 && blockIdx.y == 0 && (blockIdx.z == 0 || blockIdx.z == gridDim.z / 2))
-    tslot = dbg_t + (blockIdx.z == 0 ? 0 : 32);
 #define AT_STAMP(i) do { if (tslot) tslot[i] = (unsigned long long)(clock64() - t_start); } while (0)
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sQ = smem;                       // Q hi: 2 sub-tiles, Q lo: 2 sub-tiles (64 KB); later the P chunk (4 sub-tiles)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((tc::smem_u32(smem) & 1023u) != 0) __trap();          // the swizzled tiles need 1024-byte alignment
+  uint8_t* sQ = smem;                       // Q hi: 2 sub-tiles, Q lo: 2 sub-tiles (64 KB); later four P sub-tile buffers
   uint8_t* slot[2] = {smem + 4 * kAtSub, smem + 8 * kAtSub};
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 12 * kAtSub);
+  float* stage = reinterpret_cast<float*>(smem + 12 * kAtSub);   // O tile on its way to global memory
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 12 * kAtSub + kAtStage);
   uint64_t* q_full = bars;                  // Q landed
   uint64_t* k_full = bars + 1;              // [2] K chunk landed
   uint64_t* v_full = bars + 3;              // [2] V chunk landed
   uint64_t* s_done = bars + 5;              // all S MMAs complete
   uint64_t* p_full = bars + 6;              // [8] P quarter-chunk (32 keys) written (128 arrivals: the 4 warps of one half)
   uint64_t* pv_done = bars + 14;            // [8] PV MMAs of quarter-chunk complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
-  float* s_max = reinterpret_cast<float*>(bars + 24);      // [2 halves][128 rows] partial row maxima
+  uint64_t* s_free = bars + 22;             // softmax warps are done reading S (256 arrivals)
+  uint64_t* o_free = bars + 23;             // epilogue has read O out of TMEM (256 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float* s_max = reinterpret_cast<float*>(bars + 26);      // [2 halves][128 rows] partial row maxima
   float* s_sum = s_max + 256;                              // [2 halves][128 rows] partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * kAtQ;
   const int Q = H * 64;
   const int nchunk = (T + kAtKC - 1) / kAtKC;              // 1 or 2
-  const int row0 = b * T;
+  const int ntile = (T + kAtQ - 1) / kAtQ;
+  const int n_items = B * H * ntile;
+  const int last_qc = nchunk * 4 - 1;                       // the quarter-chunk whose P.V MMAs are issued last
   constexpr uint32_t kSubBytes = kAtSub;
   const uint32_t lo_tiles = SPLIT3 ? 2u : 1u;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tm_hi);
-    if (SPLIT3) tc::prefetch_tmap(&tm_lo);
+    tc::prefetch_tmap(&tv_hi);
+    if (SPLIT3) {
+      tc::prefetch_tmap(&tm_lo);
+      tc::prefetch_tmap(&tv_lo);
+    }
     tc::mbar_init(q_full, 1);
     for (int c = 0; c < 2; ++c) {
       tc::mbar_init(&k_full[c], 1);
@@ -99,6 +111,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
       tc::mbar_init(&pv_done[c], 1);
     }
     tc::mbar_init(s_done, 1);
+    tc::mbar_init(s_free, 256);
+    tc::mbar_init(o_free, 256);
     tc::fence_barrier_init();
   }
   if (warp == 1) {
@@ -109,102 +123,118 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_S = *tmem_slot;            // columns [0, 256)
-  const uint32_t tmem_O = tmem_S + 256;          // columns [256, 512): four 64-column partial accumulators (see P.V)
+  const uint32_t tmem_O = tmem_S + 256;          // columns [256, 320)
 
   if (warp == 0) {
     if (tc::elect_one()) {
-      // Q: columns h*64 (+32), rows row0+q0 ..
-      tc::mbar_arrive_expect_tx(q_full, 2 * lo_tiles * kSubBytes);
-      for (int sub = 0; sub < 2; ++sub) {
-        tc::tma_load_2d(sQ + sub * kAtSub, &tm_hi, q_full, h * 64 + sub * 32, row0 + q0);
-        if (SPLIT3) tc::tma_load_2d(sQ + (2 + sub) * kAtSub, &tm_lo, q_full, h * 64 + sub * 32, row0 + q0);
-      }
-      // K chunks into slot c: [hi sub0 | hi sub1 | lo sub0 | lo sub1]
-      for (int c = 0; c < nchunk; ++c) {
-        tc::mbar_arrive_expect_tx(&k_full[c], 2 * lo_tiles * kSubBytes);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1, pph = ph ^ 1;
+        const int qt = item % ntile, h = (item / ntile) % H, b = item / (ntile * H);
+        const int row0 = b * T, q0 = qt * kAtQ;
+        // K chunk 0 -> slot 0: free once the previous item's P.V MMAs over V chunk 0 are done
+        if (it > 0) tc::mbar_wait(&pv_done[3], pph);
+        tc::mbar_arrive_expect_tx(&k_full[0], 2 * lo_tiles * kSubBytes);
         for (int sub = 0; sub < 2; ++sub) {
-          tc::tma_load_2d(slot[c] + sub * kAtSub, &tm_hi, &k_full[c], Q + h * 64 + sub * 32, row0 + c * kAtKC);
-          if (SPLIT3) tc::tma_load_2d(slot[c] + (2 + sub) * kAtSub, &tm_lo, &k_full[c], Q + h * 64 + sub * 32, row0 + c * kAtKC);
+          tc::tma_load_2d(slot[0] + sub * kAtSub, &tm_hi, &k_full[0], Q + h * 64 + sub * 32, row0);
+          if (SPLIT3) tc::tma_load_2d(slot[0] + (2 + sub) * kAtSub, &tm_lo, &k_full[0], Q + h * 64 + sub * 32, row0);
         }
-      }
-      // V^T chunks reuse the slots once every S MMA has read K
-      tc::mbar_wait(s_done, 0);
-      // V^T chunk c: 4 sub-tiles [64 d x 32 keys] (8 KB each) hi, then 4 lo
-      const int vrow = (b * H + h) * 64;
-      for (int c = 0; c < nchunk; ++c) {
-        tc::mbar_arrive_expect_tx(&v_full[c], 4 * lo_tiles * kVSub);
-        for (int sub = 0; sub < 4; ++sub) {
-          tc::tma_load_2d(slot[c] + sub * kVSub, &tv_hi, &v_full[c], c * kAtKC + sub * 32, vrow);
-          if (SPLIT3) tc::tma_load_2d(slot[c] + (4 + sub) * kVSub, &tv_lo, &v_full[c], c * kAtKC + sub * 32, vrow);
+        // Q -> Q region (= the previous item's P buffers) and K chunk 1 -> slot 1: free once its last P.V MMA is done
+        if (it > 0) tc::mbar_wait(&pv_done[last_qc], pph);
+        tc::mbar_arrive_expect_tx(q_full, 2 * lo_tiles * kSubBytes);
+        for (int sub = 0; sub < 2; ++sub) {
+          tc::tma_load_2d(sQ + sub * kAtSub, &tm_hi, q_full, h * 64 + sub * 32, row0 + q0);
+          if (SPLIT3) tc::tma_load_2d(sQ + (2 + sub) * kAtSub, &tm_lo, q_full, h * 64 + sub * 32, row0 + q0);
+        }
+        if (nchunk > 1) {
+          tc::mbar_arrive_expect_tx(&k_full[1], 2 * lo_tiles * kSubBytes);
+          for (int sub = 0; sub < 2; ++sub) {
+            tc::tma_load_2d(slot[1] + sub * kAtSub, &tm_hi, &k_full[1], Q + h * 64 + sub * 32, row0 + kAtKC);
+            if (SPLIT3) tc::tma_load_2d(slot[1] + (2 + sub) * kAtSub, &tm_lo, &k_full[1], Q + h * 64 + sub * 32, row0 + kAtKC);
+          }
+        }
+        // V^T chunks reuse the slots once every S MMA of THIS item has read K
+        tc::mbar_wait(s_done, ph);
+        const int vrow = (b * H + h) * 64;
+        for (int c = 0; c < nchunk; ++c) {
+          tc::mbar_arrive_expect_tx(&v_full[c], 4 * lo_tiles * kVSub);
+          for (int sub = 0; sub < 4; ++sub) {
+            tc::tma_load_2d(slot[c] + sub * kVSub, &tv_hi, &v_full[c], c * kAtKC + sub * 32, vrow);
+            if (SPLIT3) tc::tma_load_2d(slot[c] + (4 + sub) * kVSub, &tv_lo, &v_full[c], c * kAtKC + sub * 32, vrow);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (tc::elect_one()) {
-      // ---- S = Q K^T ----
       constexpr uint32_t idesc_s = tc::make_idesc(tc::kFmtTF32, 128, kAtKC, 0, 0);
-      tc::mbar_wait(q_full, 0);
-      AT_STAMP(0);
-      const uint32_t q_addr = tc::smem_u32(sQ);
-      for (int c = 0; c < nchunk; ++c) {
-        tc::mbar_wait(&k_full[c], 0);
-        AT_STAMP(1 + c);
-        tc::tc_fence_after();
-        const uint32_t k_addr = tc::smem_u32(slot[c]);
-        uint32_t acc = 0;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {                     // 64 d = 2 sub-tiles x 4 k-steps of 8
-          const uint32_t off = (ks >> 2) * kSubBytes + (ks & 3) * 32;
-          const uint64_t a_hi = tc::smem_desc_k_sw128(q_addr + off);
-          const uint64_t b_hi = tc::smem_desc_k_sw128(k_addr + off);
-          if (SPLIT3) {
-            const uint64_t a_lo = tc::smem_desc_k_sw128(q_addr + 2 * kSubBytes + off);
-            const uint64_t b_lo = tc::smem_desc_k_sw128(k_addr + 2 * kSubBytes + off);
-            tc::mma_tf32(tmem_S + c * kAtKC, a_lo, b_hi, idesc_s, acc);
-            tc::mma_tf32(tmem_S + c * kAtKC, a_hi, b_lo, idesc_s, 1u);
-            tc::mma_tf32(tmem_S + c * kAtKC, a_hi, b_hi, idesc_s, 1u);
-          } else {
-            tc::mma_tf32(tmem_S + c * kAtKC, a_hi, b_hi, idesc_s, acc);
-          }
-          acc = 1u;
-        }
-      }
-      tc::mma_commit(s_done);
-      AT_STAMP(3);
-      // ---- O = P V ----  quarter-chunks of 32 keys: A = P sub-tile (K-major, one of the 4 sub-tile buffers in the Q
-      // region), B = V^T sub-tile [64 d x 32 keys].  The two softmax halves fill their buffers concurrently, so the
-      // quarter-chunks become ready in the order 0,2,1,3 (chunk 0) 4,6,5,7 (chunk 1); issue in that order.
-      // Back-to-back MMAs into ONE small accumulator serialise on its ~100-cycle read-modify-write latency (N = 64 is
-      // 16 cycles of math), so the products go round-robin into four accumulators (hi/lo term x k-step parity) that
-      // the epilogue adds.
       constexpr uint32_t idesc_o = tc::make_idesc(tc::kFmtTF32, 128, 64, 0, 0);
-      uint32_t acc_used = 0;                   // bit a set: accumulator a has been written
-      const int nq = nchunk * 4;
-      for (int i = 0; i < nq; ++i) {
-        const int qc = (i & ~3) | ((i & 1) << 1) | ((i >> 1) & 1);      // 0,2,1,3,4,6,5,7
-        const int c = qc >> 2, sub = qc & 3;
-        if (sub == 0 || i == (c << 2)) {
-          tc::mbar_wait(&v_full[c], 0);
-          AT_STAMP(4 + 3 * c);
-        }
-        tc::mbar_wait(&p_full[qc], 0);
-        if (i == (c << 2)) AT_STAMP(5 + 3 * c);
+      int it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t ph = it & 1, pph = ph ^ 1;
+        tslot = (dbg_t && blockIdx.x == 0 && (it == 0 || it == 2)) ? dbg_t + (it == 0 ? 0 : 32) : nullptr;
+        // ---- S = Q K^T ----
+        tc::mbar_wait(q_full, ph);
+        AT_STAMP(0);
+        if (it > 0) tc::mbar_wait(s_free, pph);              // the softmax warps no longer read the previous S
         tc::tc_fence_after();
-        const uint32_t p_addr = tc::smem_u32(sQ) + sub * kSubBytes;
-        const uint32_t v_addr = tc::smem_u32(slot[c]) + sub * kVSub;
+        const uint32_t q_addr = tc::smem_u32(sQ);
+        for (int c = 0; c < nchunk; ++c) {
+          tc::mbar_wait(&k_full[c], ph);
+          AT_STAMP(1 + c);
+          tc::tc_fence_after();
+          const uint32_t k_addr = tc::smem_u32(slot[c]);
+          uint32_t acc = 0;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {                       // 32 keys = 4 k-steps of 8
-          const uint64_t a = tc::smem_desc_k_sw128(p_addr + ks * 32);
-          const uint32_t a0 = 0u, a1 = kAtSplitAcc ? 2u : 0u;    // one accumulator (or hi / lo terms apart)
-          tc::mma_tf32(tmem_O + 64 * a0, a, tc::smem_desc_k_sw128(v_addr + ks * 32), idesc_o, (acc_used >> a0) & 1u);
-          acc_used |= 1u << a0;
-          if (SPLIT3) {
-            tc::mma_tf32(tmem_O + 64 * a1, a, tc::smem_desc_k_sw128(v_addr + 4 * kVSub + ks * 32), idesc_o, (acc_used >> a1) & 1u);
-            acc_used |= 1u << a1;
+          for (int ks = 0; ks < 8; ++ks) {                   // 64 d = 2 sub-tiles x 4 k-steps of 8
+            const uint32_t off = (ks >> 2) * kSubBytes + (ks & 3) * 32;
+            const uint64_t a_hi = tc::smem_desc_k_sw128(q_addr + off);
+            const uint64_t b_hi = tc::smem_desc_k_sw128(k_addr + off);
+            if (SPLIT3) {
+              const uint64_t a_lo = tc::smem_desc_k_sw128(q_addr + 2 * kSubBytes + off);
+              const uint64_t b_lo = tc::smem_desc_k_sw128(k_addr + 2 * kSubBytes + off);
+              tc::mma_tf32(tmem_S + c * kAtKC, a_lo, b_hi, idesc_s, acc);
+              tc::mma_tf32(tmem_S + c * kAtKC, a_hi, b_lo, idesc_s, 1u);
+              tc::mma_tf32(tmem_S + c * kAtKC, a_hi, b_hi, idesc_s, 1u);
+            } else {
+              tc::mma_tf32(tmem_S + c * kAtKC, a_hi, b_hi, idesc_s, acc);
+            }
+            acc = 1u;
           }
         }
-        tc::mma_commit(&pv_done[qc]);
-        if ((i & 3) == 3) AT_STAMP(6 + 3 * c);
+        tc::mma_commit(s_done);
+        AT_STAMP(3);
+        // ---- O = P V ----  quarter-chunks of 32 keys: A = P sub-tile (K-major, one of the 4 sub-tile buffers in the Q
+        // region), B = V^T sub-tile [64 d x 32 keys].  The two softmax halves fill their buffers concurrently, so the
+        // quarter-chunks become ready in the order 0,2,1,3 (chunk 0) 4,6,5,7 (chunk 1); issue in that order.
+        if (it > 0) {
+          tc::mbar_wait(o_free, pph);                        // the previous O has been read out of TMEM
+          tc::tc_fence_after();
+        }
+        uint32_t acc = 0;
+        const int nq = nchunk * 4;
+        for (int i = 0; i < nq; ++i) {
+          const int qc = (i & ~3) | ((i & 1) << 1) | ((i >> 1) & 1);      // 0,2,1,3,4,6,5,7
+          const int c = qc >> 2, sub = qc & 3;
+          if (i == (c << 2)) {
+            tc::mbar_wait(&v_full[c], ph);
+            AT_STAMP(4 + 3 * c);
+          }
+          tc::mbar_wait(&p_full[qc], ph);
+          if (i == (c << 2)) AT_STAMP(5 + 3 * c);
+          tc::tc_fence_after();
+          const uint32_t p_addr = tc::smem_u32(sQ) + sub * kSubBytes;
+          const uint32_t v_addr = tc::smem_u32(slot[c]) + sub * kVSub;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {                   // 32 keys = 4 k-steps of 8
+            const uint64_t a = tc::smem_desc_k_sw128(p_addr + ks * 32);
+            tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + ks * 32), idesc_o, acc);
+            acc = 1u;
+            if (SPLIT3) tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + 4 * kVSub + ks * 32), idesc_o, 1u);
+          }
+          tc::mma_commit(&pv_done[qc]);
+          if ((i & 3) == 3) AT_STAMP(6 + 3 * c);
+        }
       }
     }
   } else {
@@ -214,118 +244,119 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
     const int half = (warp - 2) >> 2;
     const int r = wq * 32 + lane;                            // row inside the tile
     const uint32_t lane_base = (uint32_t)(wq * 32) << 16;
-    tc::mbar_wait(s_done, 0);
-    tc::tc_fence_after();
-    if (threadIdx.x != 64) tslot = nullptr;                  // one stamping thread among the softmax warps
-    AT_STAMP(16);
-    float mx = -INFINITY;
-    for (int c = 0; c < nchunk; ++c) {
-      const int c0 = c * kAtKC + half * 64;                  // this half's 64 columns of the chunk: both loads in flight
-      if (c0 >= T) continue;
-      uint32_t v[32], w[32];
-      tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
-      tc::tmem_ld_32x32(tmem_S + lane_base + c0 + 32, w);
-      tc::tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
-        if (c0 + 32 + j < T) mx = fmaxf(mx, __uint_as_float(w[j]));
-      }
-      if (dbg_S && q0 + r < T) {
-        float* drow = dbg_S + (((long long)b * H + h) * T + q0 + r) * T + c0;
-        for (int j = 0; j < 32; ++j) {
-          if (c0 + j < T) drow[j] = __uint_as_float(v[j]);
-          if (c0 + 32 + j < T) drow[32 + j] = __uint_as_float(w[j]);
-        }
-      }
-    }
-    s_max[half * 128 + r] = mx;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    mx = fmaxf(s_max[r], s_max[128 + r]);
-    AT_STAMP(17);
-    float sum = 0.f;
-    int last_qc = 0;
-    for (int c = 0; c < nchunk; ++c) {
-      AT_STAMP(18 + 2 * c);
-      for (int sub = half * 2; sub < half * 2 + 2; ++sub) {  // this half's two quarter-chunks of chunk c -> P buffers `sub`
-        const int qc = c * 4 + sub;
-        const int c0 = c * kAtKC + sub * 32;
-        if (c > 0) {                                         // the buffer was read by quarter-chunk qc - 4's MMAs
-          tc::mbar_wait(&pv_done[qc - 4], 0);
-          tc::tc_fence_after();
-        }
-        uint32_t v[32];
+    const int st = (int)threadIdx.x - 64;                    // 0..255
+    int it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t ph = it & 1;
+      const int qt = item % ntile, h = (item / ntile) % H, b = item / (ntile * H);
+      const int row0 = b * T, q0 = qt * kAtQ;
+      tslot = (dbg_t && blockIdx.x == 0 && threadIdx.x == 64 && (it == 0 || it == 2)) ? dbg_t + (it == 0 ? 0 : 32) : nullptr;
+      tc::mbar_wait(s_done, ph);
+      tc::tc_fence_after();
+      AT_STAMP(16);
+      float mx = -INFINITY;
+      for (int c = 0; c < nchunk; ++c) {
+        const int c0 = c * kAtKC + half * 64;                // this half's 64 columns of the chunk: both loads in flight
+        if (c0 >= T) continue;
+        uint32_t v[32], w[32];
         tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
+        tc::tmem_ld_32x32(tmem_S + lane_base + c0 + 32, w);
         tc::tmem_ld_wait();
-        float p[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          // ex2.approx (2 ulp) is ample: the value is rounded to tf32 (2^-11) on the next line
-          float e = (c0 + j < T) ? exp2f((__uint_as_float(v[j]) - mx) * 1.4426950408889634f) : 0.f;
-          e = round_tf32(e);                                // exactly what the tensor core will read
-          p[j] = e;
-          sum += e;
+          if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
+          if (c0 + 32 + j < T) mx = fmaxf(mx, __uint_as_float(w[j]));
         }
-        // P sub-tile buffer `sub`, row r, 8 x 16-byte pieces XOR-swizzled by (r % 8)
-        uint8_t* rowp = sQ + sub * kAtSub + r * 128;
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          *reinterpret_cast<float4*>(rowp + ((j4 ^ (r & 7)) << 4)) = make_float4(p[4 * j4], p[4 * j4 + 1], p[4 * j4 + 2], p[4 * j4 + 3]);
-        tc::fence_proxy_async();                             // generic-proxy writes -> visible to the MMA (async proxy)
-        tc::mbar_arrive(&p_full[qc]);
-        last_qc = qc;
+        if (dbg_S && q0 + r < T) {
+          float* drow = dbg_S + (((long long)b * H + h) * T + q0 + r) * T + c0;
+          for (int j = 0; j < 32; ++j) {
+            if (c0 + j < T) drow[j] = __uint_as_float(v[j]);
+            if (c0 + 32 + j < T) drow[32 + j] = __uint_as_float(w[j]);
+          }
+        }
       }
-      AT_STAMP(19 + 2 * c);
-    }
-    (void)last_qc;
-    s_sum[half * 128 + r] = sum;
-    tc::mbar_wait(&pv_done[nchunk * 4 - 1], 0);               // issued last (order .. 5,7): covers every earlier MMA
-    tc::tc_fence_after();
-    AT_STAMP(22);
-    asm volatile("bar.sync 1, 256;" ::: "memory");           // partial sums visible
-    const float inv = 1.0f / (s_sum[r] + s_sum[128 + r]);
-    // O row -> padded staging tile in slot 0 (every MMA that read the slots has completed), then coalesced stores
-    float* stage = reinterpret_cast<float*>(slot[0]);
-    {
+      s_max[half * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(s_max[r], s_max[128 + r]);
+      AT_STAMP(17);
+      float sum = 0.f;
+      for (int c = 0; c < nchunk; ++c) {
+        AT_STAMP(18 + 2 * c);
+        for (int sub = half * 2; sub < half * 2 + 2; ++sub) {  // this half's two quarter-chunks of chunk c -> P buffers `sub`
+          const int qc = c * 4 + sub;
+          const int c0 = c * kAtKC + sub * 32;
+          if (c > 0) {                                       // the buffer was read by quarter-chunk qc - 4's MMAs
+            tc::mbar_wait(&pv_done[qc - 4], ph);
+            tc::tc_fence_after();
+          }
+          uint32_t v[32];
+          tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
+          tc::tmem_ld_wait();
+          float p[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            // ex2.approx (2 ulp) is ample: the value is rounded to tf32 (2^-11) on the next line
+            float e = (c0 + j < T) ? exp2f((__uint_as_float(v[j]) - mx) * 1.4426950408889634f) : 0.f;
+            e = round_tf32(e);                              // exactly what the tensor core will read
+            p[j] = e;
+            sum += e;
+          }
+          // P sub-tile buffer `sub`, row r, 8 x 16-byte pieces XOR-swizzled by (r % 8)
+          uint8_t* rowp = sQ + sub * kAtSub + r * 128;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(rowp + ((j4 ^ (r & 7)) << 4)) = make_float4(p[4 * j4], p[4 * j4 + 1], p[4 * j4 + 2], p[4 * j4 + 3]);
+          tc::fence_proxy_async();                           // generic-proxy writes -> visible to the MMA (async proxy)
+          tc::mbar_arrive(&p_full[qc]);
+        }
+        AT_STAMP(19 + 2 * c);
+      }
+      tc::tc_fence_before();
+      tc::mbar_arrive(s_free);                               // this thread is done reading S: the next S may be issued
+      s_sum[half * 128 + r] = sum;
+      tc::mbar_wait(&pv_done[last_qc], ph);                  // issued last: covers every earlier MMA of the item
+      tc::tc_fence_after();
+      AT_STAMP(22);
       uint32_t v[32];
       tc::tmem_ld_32x32(tmem_O + lane_base + half * 32, v);
       tc::tmem_ld_wait();
-      float o[32];
+      tc::tc_fence_before();
+      tc::mbar_arrive(o_free);                               // O is in registers: the next item may overwrite it
+      asm volatile("bar.sync 1, 256;" ::: "memory");         // partial sums visible; previous item's staging reads done
+      const float inv = 1.0f / (s_sum[r] + s_sum[128 + r]);
+      // O row -> staging tile (rows of 256 B, 16-byte chunk c4 of row r stored at chunk c4 ^ (r & 7)), then coalesced stores
+      {
+        uint8_t* srow = reinterpret_cast<uint8_t*>(stage) + r * 256;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(v[j]);
-      if (SPLIT3 && kAtSplitAcc) {                            // the lo-term accumulator
-        tc::tmem_ld_32x32(tmem_O + lane_base + 128 + half * 32, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] += __uint_as_float(v[j]);
-      }
-      float* srow = stage + r * kAtStageLd + half * 32;
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4)
-        *reinterpret_cast<float4*>(srow + 4 * j4) = make_float4(o[4 * j4] * inv, o[4 * j4 + 1] * inv, o[4 * j4 + 2] * inv, o[4 * j4 + 3] * inv);
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const int st = (int)threadIdx.x - 64;                     // 0..255
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int idx = it * 256 + st;
-      const int row = idx >> 4, c4 = idx & 15;
-      const int q = q0 + row;
-      if (q < T) {
-        const float4 o = *reinterpret_cast<const float4*>(stage + row * kAtStageLd + c4 * 4);
-        const long long off = (long long)(row0 + q) * ldo + h * 64 + c4 * 4;
-        if (out_lo) {
-          float4 oh, ol;
-          split_tf32(o.x, oh.x, ol.x); split_tf32(o.y, oh.y, ol.y); split_tf32(o.z, oh.z, ol.z); split_tf32(o.w, oh.w, ol.w);
-          *reinterpret_cast<float4*>(out_hi + off) = oh;
-          *reinterpret_cast<float4*>(out_lo + off) = ol;
-        } else {
-          *reinterpret_cast<float4*>(out_hi + off) = o;
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int c4 = half * 8 + j4;
+          *reinterpret_cast<float4*>(srow + ((c4 ^ (r & 7)) << 4)) =
+              make_float4(__uint_as_float(v[4 * j4]) * inv, __uint_as_float(v[4 * j4 + 1]) * inv,
+                          __uint_as_float(v[4 * j4 + 2]) * inv, __uint_as_float(v[4 * j4 + 3]) * inv);
         }
       }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+      for (int i8 = 0; i8 < 8; ++i8) {
+        const int idx = i8 * 256 + st;
+        const int row = idx >> 4, c4 = idx & 15;
+        const int q = q0 + row;
+        if (q < T) {
+          const float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stage) + row * 256 + ((c4 ^ (row & 7)) << 4));
+          const long long off = (long long)(row0 + q) * ldo + h * 64 + c4 * 4;
+          if (out_lo) {
+            float4 oh, ol;
+            split_tf32(o.x, oh.x, ol.x); split_tf32(o.y, oh.y, ol.y); split_tf32(o.z, oh.z, ol.z); split_tf32(o.w, oh.w, ol.w);
+            *reinterpret_cast<float4*>(out_hi + off) = oh;
+            *reinterpret_cast<float4*>(out_lo + off) = ol;
+          } else {
+            *reinterpret_cast<float4*>(out_hi + off) = o;
+          }
+        }
+      }
+      AT_STAMP(23);
     }
   }
-  if (threadIdx.x == 64) AT_STAMP(23);
 #undef AT_STAMP
   tc::tc_fence_before();
   __syncthreads();
@@ -345,11 +376,18 @@ inline int launch_enc_attention_tc(const TcOperand& qkv, const TcOperand& vt, in
     MT3_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     attr_done = true;
   }
-  dim3 grid(cdiv(T, kAtQ), H, B);
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    MT3_CUDA_CHECK(cudaGetDevice(&dev));
+    MT3_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int n_items = B * H * cdiv(T, kAtQ);
+  dim3 grid(n_items < sm_count ? n_items : sm_count);       // one persistent CTA per SM (198 KB of shared memory each)
   if (split3)
-    enc_attention_tc_kernel<true><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.lo, vt.hi, vt.lo, T, H, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t);
+    enc_attention_tc_kernel<true><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.lo, vt.hi, vt.lo, T, H, B, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t);
   else
-    enc_attention_tc_kernel<false><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.hi, vt.hi, vt.hi, T, H, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t);
+    enc_attention_tc_kernel<false><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.hi, vt.hi, vt.hi, T, H, B, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t);
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }

@@ -77,7 +77,7 @@ static int run(int B, int T, int H, int mode, bool split3, int variant) {
     const char* mma_names[10] = {"Q landed", "K0 landed", "K1 landed", "S issued", "V0 landed", "P0 ready", "PV0 issued", "V1 landed", "P1 ready", "PV1 issued"};
     const char* sm_names[8] = {"S done", "row max done", "P0 start", "P0 written", "P1 start (PV0 done)", "P1 written", "PV1 done", "epilogue done"};
     for (int c = 0; c < 2; ++c) {
-      printf("  timeline CTA %s (us @1.965 GHz): MMA thread:", c == 0 ? "(0,0,0)" : "(0,0,B/2)");
+      printf("  timeline CTA 0 %s item (us since kernel start @1.965 GHz): MMA thread:", c == 0 ? "first" : "third");
       for (int i = 0; i < 10; ++i) printf(" %s %.2f |", mma_names[i], t[c * 32 + i] / 1965.0);
       printf("\n      softmax thread:");
       for (int i = 0; i < 8; ++i) printf(" %s %.2f |", sm_names[i], t[c * 32 + 16 + i] / 1965.0);
