@@ -416,25 +416,31 @@ extern "C" int mt3_logmel_f32(const mt3_frontend* h, const float* audio, int64_t
     MT3_LAUNCH_CHECK();
     return MT3_OK;
   }
-  constexpr int F = 16, W = 4;   // 16 frames per CTA, 4 warps: ~96 KB of smem incl. all tables -> two CTAs per SM
-  const int chunk = (F - 1) * hop + kFft;
+  // 12 frames per CTA on 6 warps (~111 KB of smem incl. all tables, two CTAs per SM = 12 warps per SM, 168 registers per
+  // thread): 137 us per 64 segments; MT3_LOGMEL_CFG=0 selects the earlier 16 frames on 4 warps (8 warps per SM, 175 us)
+  static const int cfg_sel = [] { const char* e = getenv("MT3_LOGMEL_CFG"); return e ? atoi(e) : 1; }();
+  static bool attr_set[2] = {false, false};
   const int n_mel = fe->cfg.num_mel_bins;
-  const size_t base = (size_t)(((chunk + 3) & ~3) + kFft) * sizeof(float) + 2 * 1024 * sizeof(float2) +
-                      (size_t)W * kScratchF2 * sizeof(float2) + (size_t)((n_mel + 3) & ~3) * sizeof(int);
-  const size_t mel_bytes = (size_t)fe->taps * n_mel * sizeof(float);
-  const int mel_in_smem = base + mel_bytes <= 110 * 1024;
-  const size_t smem = base + (mel_in_smem ? mel_bytes : 0);
-  MT3_REQUIRE(smem <= 227 * 1024, MT3_ERR_UNSUPPORTED, "mt3_logmel_f32: hop %d needs %zu B of shared memory", hop, smem);
-  auto kern = logmel2048_kernel<F, W>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MT3_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
-  dim3 grid((T + F - 1) / F, num_segments);
-  kern<<<grid, W * 32, smem, (cudaStream_t)stream>>>(audio, audio_stride, n_samples, hop, n_valid_frames, T, fe->d_window,
-                                                     fe->d_tw1024, fe->d_rtw, fe->d_mel_bin0, fe->d_mel_w, fe->taps,
-                                                     mel_in_smem, n_mel, fe->cfg.log_eps, out);
+  auto launch = [&](auto kern, int F, int W) -> int {
+    const int chunk = (F - 1) * hop + kFft;
+    const size_t base = (size_t)(((chunk + 3) & ~3) + kFft) * sizeof(float) + 2 * 1024 * sizeof(float2) +
+                        (size_t)W * kScratchF2 * sizeof(float2) + (size_t)((n_mel + 3) & ~3) * sizeof(int);
+    const size_t mel_bytes = (size_t)fe->taps * n_mel * sizeof(float);
+    const int mel_in_smem = base + mel_bytes <= 113 * 1024;
+    const size_t smem = base + (mel_in_smem ? mel_bytes : 0);
+    MT3_REQUIRE(smem <= 227 * 1024, MT3_ERR_UNSUPPORTED, "mt3_logmel_f32: hop %d needs %zu B of shared memory", hop, smem);
+    if (!attr_set[W == 6]) {
+      MT3_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set[W == 6] = true;
+    }
+    dim3 grid((T + F - 1) / F, num_segments);
+    kern<<<grid, W * 32, smem, (cudaStream_t)stream>>>(audio, audio_stride, n_samples, hop, n_valid_frames, T, fe->d_window,
+                                                       fe->d_tw1024, fe->d_rtw, fe->d_mel_bin0, fe->d_mel_w, fe->taps,
+                                                       mel_in_smem, n_mel, fe->cfg.log_eps, out);
+    return MT3_OK;
+  };
+  const int rc = cfg_sel == 1 ? launch(logmel2048_kernel<12, 6>, 12, 6) : launch(logmel2048_kernel<16, 4>, 16, 4);
+  if (rc != MT3_OK) return rc;
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }
