@@ -180,7 +180,7 @@ int mt3_debug_launch(mt3_model* m, int32_t kind, int32_t pos, int32_t iters, voi
 
 /* Measurement hook: device timeline of ONE greedy decode step at cache position `pos` (>= 2), replayed as a
  * CUDA graph exactly like mt3_generate's step.  Every decode GEMM / attention node records into its slot of
- * `out` (host, [max_slots][8] u64): [0] earliest CTA start, [1] latest CTA end (ns, %globaltimer),
+ * `out` (host, [max_slots][16] u64): [0] earliest CTA start, [1] latest CTA end (ns, %globaltimer),
  * [2..6] SM-clock deltas of CTA (0,0) at its internal phase boundaries.  `names` receives the slot names,
  * newline separated.  Clobbers the decode state (position, tokens); call mt3_encode/mt3_cross_kv first. */
 int mt3_debug_trace_step(mt3_model* m, int32_t pos, uint64_t* out, int32_t max_slots, char* names,

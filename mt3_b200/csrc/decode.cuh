@@ -338,6 +338,11 @@ __device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int
   if (tr) {
     atomicMin(p.trace, gtime_ns());
     c0 = clock64();
+    if (tile_x == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      p.trace[8 + blockIdx.y] = smid;
+    }
   }
   // "I am running": peers may write into my shared memory once every CTA of the cluster has arrived here
   asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");

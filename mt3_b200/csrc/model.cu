@@ -396,7 +396,7 @@ static int cross_kv_impl(Model* m, const float* encoded, cudaStream_t s) {
 // A contiguous block of sequences decoded on one stream (MT3_DEC_STREAMS sub-batches per step).
 struct Rows { int begin, count, stream_idx; };
 
-constexpr int kTraceSlots = 256, kTraceWords = 8;
+constexpr int kTraceSlots = 256, kTraceWords = 16;   // words 8..15: %smid of the 8 CTAs of tile 0's cluster
 static unsigned long long* trace_slot(Model* m, const char* name) {
   if (!m->tracing || (int)m->trace_names.size() >= kTraceSlots) return nullptr;
   m->trace_names.push_back(name);

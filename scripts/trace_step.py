@@ -23,7 +23,7 @@ def main():
     lib = _lib.load()
     h = im.model._h
     stream = torch.cuda.current_stream(dev).cuda_stream
-    out = np.zeros((256, 8), np.uint64)
+    out = np.zeros((256, 16), np.uint64)
     names = C.create_string_buffer(16384)
     n = C.c_int32(0)
     for pos in [int(p) for p in os.environ.get("TRACE_POS", "32,512,1000").split(",")]:
@@ -41,6 +41,8 @@ def main():
             dur, gap = (en - st) / 1e3, (st - prev_end) / 1e3
             a = agg.setdefault(nm[i], [0, 0.0, 0.0, np.zeros(5)])
             a[0] += 1; a[1] += dur; a[2] += gap; a[3] += ph
+            if i < 8 and nm[i].startswith('gemm'):
+                print(f"{'':18s} SMs of tile 0's cluster (rank 0..7): " + ' '.join(str(int(x)) for x in t[i, 8:16]))
             if i < int(os.environ.get('TRACE_ROWS', '10')) or i >= n.value - 3:
                 print(f"{nm[i]:18s} {(st - t0) / 1e3:8.2f} {dur:7.2f} {gap:6.2f} | " + " ".join(f"{x:6.2f}" for x in ph))
             prev_end = en
