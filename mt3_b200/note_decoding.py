@@ -261,3 +261,57 @@ def note_sequence_to_midi_bytes(ns: NoteSequence, qpm: float = 120.0) -> bytes:
 def note_sequence_to_midi_file(ns: NoteSequence, path: str, qpm: float = 120.0) -> None:
     with open(path, 'wb') as f:
         f.write(note_sequence_to_midi_bytes(ns, qpm))
+
+
+# ---------------------------------------------------------------------------------------------
+# Offline-eval surface: combine per-segment predictions by example id and write the
+# T5X-`infer`-compatible JSON lines file (reference inference.py:34-138, metrics_utils.py:38-56).
+# ---------------------------------------------------------------------------------------------
+def combine_predictions_by_id(predictions: Sequence[Mapping[str, Any]], combine_predictions_fn) -> Mapping[str, Any]:
+    """Concatenate predicted examples, grouping by 'unique_id' (metrics_utils.py:38-56)."""
+    by_id: dict = {}
+    for pred in predictions:
+        by_id.setdefault(pred['unique_id'], []).append(pred)
+    return {uid: combine_predictions_fn(preds) for uid, preds in by_id.items()}
+
+
+def note_to_dict(note: Note) -> Mapping[str, Any]:
+    return {'start_time': note.start_time, 'end_time': note.end_time, 'pitch': note.pitch, 'velocity': note.velocity,
+            'program': note.program, 'is_drum': note.is_drum}
+
+
+def write_inferences_to_file(path: str, inferences: Sequence[Any], task_ds: Sequence[Mapping[str, Any]], mode: str,
+                             vocabulary=None, vocab_config=None, onsets_only: bool = False, use_ties: bool = True) -> None:
+    """Writes model predictions as JSON lines {'id', 'est_notes': [...]}, one line per full example
+    (reference inference.py:34-138).  `inferences`: RAW model ids per segment (the output of predict_batch,
+    decoded here with `vocabulary.decode_tf` + trim at EOS); `task_ds`: per-segment dicts with 'unique_id' [1],
+    'input_times', 'raw_inputs' and 'sequence' [1] (the example id stands in for the serialized reference
+    NoteSequence, which needs note_seq: only the first segment of an example carries it, as in the reference)."""
+    from . import vocabularies
+    if mode == 'score':
+        raise ValueError('`score` mode currently not supported in MT3')
+    if not vocabulary:
+        raise ValueError('`vocabulary` parameter required in `predict` mode')
+    if onsets_only and use_ties:
+        raise ValueError('ties not compatible with onset-only transcription')
+    encoding_spec = 'NoteOnsetEncodingSpec' if onsets_only else ('NoteEncodingWithTiesSpec' if use_ties else 'NoteEncodingSpec')
+    codec = vocabularies.build_codec(vocab_config)
+    targets, predictions = [], []
+    for inp, output in zip(task_ds, inferences):
+        tokens = np.asarray(vocabulary.decode_tf(np.asarray(output, np.int32)))
+        if vocabularies.DECODED_EOS_ID in tokens:
+            tokens = tokens[:np.argmax(tokens == vocabularies.DECODED_EOS_ID)]
+        start_time = inp['input_times'][0]
+        start_time -= start_time % (1 / codec.steps_per_second)      # round down to the symbolic token step
+        uid = inp['unique_id'][0]
+        targets.append({'unique_id': uid, 'ref_id': inp['sequence'][0] if inp['sequence'][0] else None})
+        predictions.append({'unique_id': uid, 'est_tokens': tokens, 'start_time': start_time, 'raw_inputs': inp['raw_inputs']})
+    full_targets = {t['unique_id']: t['ref_id'] for t in targets if t['ref_id']}
+    full_predictions = combine_predictions_by_id(
+        predictions, lambda preds: event_predictions_to_ns(preds, codec=codec, encoding_spec=encoding_spec))
+    assert sorted(full_targets.keys()) == sorted(full_predictions.keys())
+    import json
+    with open(path, 'w') as f:
+        for uid in sorted(full_targets.keys()):
+            f.write(json.dumps({'id': str(full_targets[uid]),
+                                'est_notes': [note_to_dict(n) for n in full_predictions[uid]['est_ns'].notes]}) + '\n')

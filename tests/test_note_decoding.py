@@ -131,3 +131,39 @@ def test_midi_writer_roundtrip_header(tmp_path):
 def test_unknown_spec():
     with pytest.raises(ValueError):
         nd.NoteDecoder(FULL, 'NoSuchSpec')
+
+
+def test_write_inferences_to_file(tmp_path):
+    """Offline-eval surface (reference inference.py:34-138): raw model ids per segment -> JSON lines of notes per example."""
+    import json
+    from mt3_b200 import vocabularies
+    vc = vocabularies.VocabularyConfig(num_velocity_bins=1)
+    codec = vocabularies.build_codec(vc)
+    vocab = vocabularies.vocabulary_from_codec(codec)
+
+    def ids(*events):           # event -> raw model id (3 special ids first, vocabularies.py:241-271)
+        return [codec.encode_event(ec.Event(t, v)) + 3 for t, v in events]
+
+    seg0 = ids(('tie', 0), ('shift', 10), ('program', 0), ('velocity', 1), ('pitch', 60)) + [1, 0, 0]    # EOS = 1, then padding
+    seg1 = ids(('program', 0), ('pitch', 60), ('tie', 0), ('shift', 50), ('program', 0), ('velocity', 0), ('pitch', 60)) + [1]
+    other = ids(('tie', 0), ('shift', 20), ('program', 40), ('velocity', 1), ('pitch', 72),
+                ('shift', 30), ('program', 40), ('velocity', 0), ('pitch', 72)) + [1]
+    task_ds = [
+        {'unique_id': ['b'], 'input_times': [0.0], 'raw_inputs': [], 'sequence': ['song-b']},
+        {'unique_id': ['a'], 'input_times': [0.0], 'raw_inputs': [], 'sequence': ['song-a']},
+        {'unique_id': ['a'], 'input_times': [2.048], 'raw_inputs': [], 'sequence': ['']},
+    ]
+    path = tmp_path / 'inferences.jsonl'
+    nd.write_inferences_to_file(str(path), [other, seg0, seg1], task_ds, 'predict', vocabulary=vocab, vocab_config=vc,
+                                onsets_only=False, use_ties=True)
+    lines = [json.loads(l) for l in path.read_text().splitlines()]
+    assert [l['id'] for l in lines] == ['song-a', 'song-b']
+    a, b = lines[0]['est_notes'], lines[1]['est_notes']
+    # example a: note-on at 0.10 s in segment 0, tied into segment 1 (starts at 2.04 s), released 0.50 s into it
+    assert len(a) == 1 and a[0]['pitch'] == 60 and a[0]['start_time'] == pytest.approx(0.10) and a[0]['end_time'] == pytest.approx(2.54)
+    assert len(b) == 1 and (b[0]['pitch'], b[0]['program']) == (72, 40)
+    assert b[0]['start_time'] == pytest.approx(0.20) and b[0]['end_time'] == pytest.approx(0.30)
+    with pytest.raises(ValueError):
+        nd.write_inferences_to_file(str(path), [], [], 'score', vocabulary=vocab, vocab_config=vc)
+    with pytest.raises(ValueError):
+        nd.write_inferences_to_file(str(path), [], [], 'predict', vocabulary=vocab, vocab_config=vc, onsets_only=True, use_ties=True)
