@@ -272,53 +272,58 @@ constexpr size_t dec_cluster_smem() {
   return (size_t)(kDecBM * (KC + 4) + KC * kDecLDB + kDecRedFloats + 64) * sizeof(float);
 }
 
-// Sum this rank's 8 rows over the 8 source ranks (rank order, local shared memory) and apply the fused epilogue:
-// RMSNorm row factor, gated-GELU / residual, plain store or head-major KV-cache append.  128 threads.
+// Sum this rank's 64/S rows over the S source ranks (rank order, local shared memory) and apply the fused epilogue:
+// RMSNorm row factor, gated-GELU / residual, plain store or head-major KV-cache append.  128 threads; S = 8: 8 rows x
+// 16 column pairs, S = 16: 4 rows x 32 single columns (no gated-GELU, whose inputs are column pairs).
+template <int S>
 __device__ __forceinline__ void dec_reduce_epilogue(const DecGemmArgs& p, const float* Red, const float* Rss, unsigned rank, int n0) {
-  constexpr int BN = kDecBN;
+  constexpr int BN = kDecBN, R = kDecBM / S, CPT = (R * BN) / 128, LPR = BN / CPT;   // rows per rank, columns per thread, lanes per row
+  static_assert(CPT == 1 || CPT == 2, "cluster size must be 8 or 16");
   const int tid = threadIdx.x;
-  const int rl = tid >> 4, c2 = (tid & 15) * 2;
-  const int m = (int)rank * 8 + rl, n = n0 + c2;
-  float2 v = make_float2(0.f, 0.f);
+  const int rl = tid / LPR, c0 = (tid % LPR) * CPT;
+  const int m = (int)rank * R + rl, n = n0 + c0;
+  float v[2] = {0.f, 0.f};
   float sst = 0.f;
 #pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const float2 q = *reinterpret_cast<const float2*>(&Red[(s * 8 + rl) * BN + c2]);
-    v.x += q.x; v.y += q.y;
-    if (p.norm) sst += Rss[s * 8 + rl];
+  for (int s = 0; s < S; ++s) {
+    if (CPT == 2) {
+      const float2 q = *reinterpret_cast<const float2*>(&Red[(s * R + rl) * BN + c0]);
+      v[0] += q.x; v[1] += q.y;
+    } else {
+      v[0] += Red[(s * R + rl) * BN + c0];
+    }
+    if (p.norm) sst += Rss[s * R + rl];
   }
   const bool valid = m < p.M && n < p.N;
   if (valid) {
     const float rs = p.norm ? 1.0f / sqrtf(sst / (float)p.K + p.eps) : 1.f;
-    v.x *= rs; v.y *= rs;
-    if (p.epi == EPI_GATED_GELU) {
-      p.C[(long long)m * p.ldc + (n >> 1)] = gelu_tanh(v.x) * v.y;
+    v[0] *= rs; v[1] *= rs;
+    if (CPT == 2 && p.epi == EPI_GATED_GELU) {
+      p.C[(long long)m * p.ldc + (n >> 1)] = gelu_tanh(v[0]) * v[1];
     } else {
       if (p.epi == EPI_RESIDUAL) {
-        const float2 q = *reinterpret_cast<const float2*>(p.R + (long long)m * p.ldr + n);
-        v.x += q.x; v.y += q.y;
+        const float* r = p.R + (long long)m * p.ldr + n;
+        v[0] += r[0];
+        if (CPT == 2) v[1] += r[1];
       }
-      if (n < p.n_split) {
-        *reinterpret_cast<float2*>(p.C + (long long)m * p.ldc + n) = v;
-      } else {
-        const int pos = p.hm_pos ? *p.hm_pos : 0;
-        *reinterpret_cast<float2*>(p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos)) = v;
-      }
+      float* dst = n < p.n_split ? p.C + (long long)m * p.ldc + n
+                                 : p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, p.hm_pos ? *p.hm_pos : 0);
+      if (CPT == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+      else dst[0] = v[0];
     }
   }
-  if (p.ssq_out) {                      // 16 lanes share a row: fixed butterfly order
-    float sq = valid ? fmaf(v.x, v.x, v.y * v.y) : 0.f;
-    sq += __shfl_xor_sync(0xffffffffu, sq, 8);
-    sq += __shfl_xor_sync(0xffffffffu, sq, 4);
-    sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-    sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-    if ((tid & 15) == 0 && m < p.M) p.ssq_out[(long long)m * p.ssq_ld + n0 / BN] = sq;
+  if (p.ssq_out) {                      // LPR lanes share a row: fixed butterfly order
+    float sq = valid ? fmaf(v[0], v[0], CPT == 2 ? v[1] * v[1] : 0.f) : 0.f;
+#pragma unroll
+    for (int o = LPR / 2; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((tid % LPR) == 0 && m < p.M) p.ssq_out[(long long)m * p.ssq_ld + n0 / BN] = sq;
   }
 }
 
-template <int KC, int MODE, bool TRACE>
+template <int KC, int MODE, bool TRACE, int S = 8>
 __device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int tile_x) {
   constexpr int BM = kDecBM, BN = kDecBN, NT = 128, LDA = KC + 4, LDB = kDecLDB;
+  constexpr int R = BM / S;                   // rows of the tile each rank owns (8 for clusters of 8, 4 for clusters of 16)
   constexpr int WQ = KC * 8 / NT;            // weight 16-byte copies per thread
   constexpr int AQ = KC * 16 / NT;           // activation 16-byte copies per thread
   extern __shared__ __align__(16) float dsm[];
@@ -341,7 +346,7 @@ __device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int
     if (tile_x == 0) {
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      p.trace[8 + blockIdx.y] = smid;
+      if (blockIdx.y < 8) p.trace[8 + blockIdx.y] = smid;
     }
   }
   // "I am running": peers may write into my shared memory once every CTA of the cluster has arrived here
@@ -388,8 +393,8 @@ __device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int
     ss += __shfl_xor_sync(0xffffffffu, ss, 1);
   }
 
-  const uint32_t red_base = tc::smem_u32(Red) + rank * (8 * BN * 4);     // my slot [rank][..] in the owner's Red
-  const uint32_t rss_base = tc::smem_u32(Rss) + rank * (8 * 4);
+  const uint32_t red_base = tc::smem_u32(Red) + rank * (R * BN * 4);     // my slot [rank][..] in the owner's Red
+  const uint32_t rss_base = tc::smem_u32(Rss) + rank * (R * 4);
   if (MODE == 0) {
     // ---- exact fp32: thread tile rows ty + 16 i (i < 4), columns tx*4 .. +3; k ascending ----
     const int tx = tid % 8, ty = tid / 8;
@@ -422,7 +427,7 @@ __device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int
 #pragma unroll
     for (int i = 0; i < 4; ++i) {                                  // row ty + 16 i -> owner rank, local row
       const int row = ty + 16 * i;
-      st_cluster_f4(cluster_map(red_base + (uint32_t)(((row & 7) * BN + tx * 4) * 4), (unsigned)(row >> 3)),
+      st_cluster_f4(cluster_map(red_base + (uint32_t)(((row % R) * BN + tx * 4) * 4), (unsigned)(row / R)),
                     make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
     }
   } else {
@@ -478,30 +483,31 @@ __device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (j < nj) {
-        const uint32_t off = (uint32_t)((g * BN + (j0 + j) * 8 + 2 * t) * 4);
-        st_cluster_f2(cluster_map(red_base + off, (unsigned)(2 * rg)), acc[j][0], acc[j][1]);
-        st_cluster_f2(cluster_map(red_base + off, (unsigned)(2 * rg + 1)), acc[j][2], acc[j][3]);
+        const int ra = rg * 16 + g, rb = ra + 8;                   // rows of c0,c1 and of c2,c3
+        const uint32_t col = (uint32_t)(((j0 + j) * 8 + 2 * t) * 4);
+        st_cluster_f2(cluster_map(red_base + (uint32_t)((ra % R) * BN * 4) + col, (unsigned)(ra / R)), acc[j][0], acc[j][1]);
+        st_cluster_f2(cluster_map(red_base + (uint32_t)((rb % R) * BN * 4) + col, (unsigned)(rb / R)), acc[j][2], acc[j][3]);
       }
     }
   }
   if (p.norm && (tid & 1) == 0) {
     const int row = tid >> 1;
-    st_cluster_f1(cluster_map(rss_base + (uint32_t)((row & 7) * 4), (unsigned)(row >> 3)), ss);
+    st_cluster_f1(cluster_map(rss_base + (uint32_t)((row % R) * 4), (unsigned)(row / R)), ss);
   }
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (tr0) p.trace[4] = (unsigned long long)(clock64() - c0);      // partials exchanged
 
-  dec_reduce_epilogue(p, Red, Rss, rank, n0);
+  dec_reduce_epilogue<S>(p, Red, Rss, rank, n0);
   if (tr) {
     if (tr0) p.trace[5] = (unsigned long long)(clock64() - c0);    // reduce + epilogue stores issued
     atomicMax(p.trace + 1, gtime_ns());
   }
 }
 
-template <int KC, int MODE, bool TRACE>
+template <int KC, int MODE, bool TRACE, int S = 8>
 __global__ void __launch_bounds__(128)
 sgemm_dec_cluster_kernel(const DecGemmArgs p) {
-  dec_cluster_body<KC, MODE, TRACE>(p, (int)blockIdx.x);
+  dec_cluster_body<KC, MODE, TRACE, S>(p, (int)blockIdx.x);
 }
 
 // Two independent GEMMs that read the same inputs in ONE launch (column tiles [0, tiles0) belong to p0, the rest to
@@ -542,25 +548,33 @@ inline int launch_dec_gemm_out_q(const DecGemmArgs& a0, const DecGemmArgs& a1, i
   return launch_dec_gemm_cluster2<48, 112, 0>(a0, a1, s, pdl);
 }
 
-template <int KC, int MODE>
+template <int KC, int MODE, int S = 8>
 inline int launch_dec_gemm_cluster_kc(const DecGemmArgs& a, cudaStream_t s, bool pdl) {
   constexpr size_t smem = dec_cluster_smem<KC>();
   static bool attr_done = false;
   if (!attr_done) {
-    MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster_kernel<KC, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster_kernel<KC, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster_kernel<KC, MODE, false, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster_kernel<KC, MODE, true, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (S > 8) {
+      MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster_kernel<KC, MODE, false, S>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      MT3_CUDA_CHECK(cudaFuncSetAttribute(sgemm_dec_cluster_kernel<KC, MODE, true, S>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    }
     attr_done = true;
   }
   if (a.trace)
-    MT3_CUDA_CHECK(launch_kernel_cluster(sgemm_dec_cluster_kernel<KC, MODE, true>, dim3(cdiv(a.N, kDecBN), 8), dim3(128), smem, s, pdl, 8u, a));
+    MT3_CUDA_CHECK(launch_kernel_cluster(sgemm_dec_cluster_kernel<KC, MODE, true, S>, dim3(cdiv(a.N, kDecBN), S), dim3(128), smem, s, pdl, (unsigned)S, a));
   else
-    MT3_CUDA_CHECK(launch_kernel_cluster(sgemm_dec_cluster_kernel<KC, MODE, false>, dim3(cdiv(a.N, kDecBN), 8), dim3(128), smem, s, pdl, 8u, a));
+    MT3_CUDA_CHECK(launch_kernel_cluster(sgemm_dec_cluster_kernel<KC, MODE, false, S>, dim3(cdiv(a.N, kDecBN), S), dim3(128), smem, s, pdl, (unsigned)S, a));
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }
 
 template <int MODE>
 inline int launch_dec_gemm_cluster_mode(const DecGemmArgs& a, cudaStream_t s, bool pdl) {
+  // the long-K, narrow-N GEMM (MLP out: K = 1024, N = 512) has only N/32 x 8 = 128 CTAs of 4 warps at cluster size 8: a
+  // cluster of 16 halves every CTA's K chunk and fills the machine (MT3_DEC_CLUSTER16=0 keeps clusters of 8)
+  static const bool c16 = [] { const char* e = getenv("MT3_DEC_CLUSTER16"); return !(e && e[0] == '0'); }();
+  if (c16 && a.K == 1024 && a.epi != EPI_GATED_GELU && a.N <= 512) return launch_dec_gemm_cluster_kc<64, MODE, 16>(a, s, pdl);
   switch (a.K / 8) {
     case 48: return launch_dec_gemm_cluster_kc<48, MODE>(a, s, pdl);
     case 64: return launch_dec_gemm_cluster_kc<64, MODE>(a, s, pdl);

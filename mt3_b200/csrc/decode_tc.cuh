@@ -178,7 +178,7 @@ dec_gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (tr0) p.trace[4] = (unsigned long long)(clock64() - c0);      // partials exchanged
   if (warp == 1) tc::tmem_dealloc(tmem_base, 32);
 
-  dec_reduce_epilogue(p, Red, Rss, rank, n0);
+  dec_reduce_epilogue<8>(p, Red, Rss, rank, n0);
   if (tr) {
     if (tr0) p.trace[5] = (unsigned long long)(clock64() - c0);
     atomicMax(p.trace + 1, gtime_ns());
