@@ -1,9 +1,7 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-echo "== pytest decode"; timeout 900 python -m pytest tests -q -m gpu -x -k "variants or fused or decoder_teacher or graph_equivalence or tiny_golden or tensor_core_variants" 2>&1 | tail -4
-TRACE_POS=512 timeout 600 python scripts/trace_step.py 2>&1 | tee gpurun_out/trace_step_c16.log | tail -12
-for c in 1 0; do
-MT3_DEC_CLUSTER16=$c timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2> gpurun_out/bench_c16_$c.err | tail -1 > gpurun_out/bench_c16_$c.json
-echo "cluster16=$c: $(grep -E 'timed' gpurun_out/bench_c16_$c.err)"
-done
+echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -4 | tee gpurun_out/pytest_gpu.log
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/smoke.log
+echo "== bench"; timeout 600 python bench.py 2> gpurun_out/bench_default.err | tail -1 > gpurun_out/bench_default.json
+grep -E "timed|e2e |cpu port" gpurun_out/bench_default.err; cut -c1-260 gpurun_out/bench_default.json
