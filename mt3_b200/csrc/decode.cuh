@@ -1,17 +1,20 @@
 // Decode-step kernels (one new token per sequence, M = batch rows), sm_100a.
 //
-// The decode step is bandwidth/latency bound (DESIGN.md "decode step"): per layer it streams
-// 11.8 MB of fp32 weights and, per sequence, the self-attention K/V rows written so far plus
-// the 256 hoisted cross-attention K/V rows.  Two kernels carry it:
+// The decode step is bandwidth/latency bound (DESIGN.md "decode step"): per layer it streams 11.8 MB of fp32 weights
+// (L2-resident across steps) and, per sequence, the self-attention K/V rows written so far plus the 256 hoisted
+// cross-attention K/V rows (HBM).  The kernels:
 //
-//  sgemm_dec_kernel    exact-fp32 GEMM for M <= 64 rows.  A 64 x 32 output tile per CTA gives only
-//                      N/32 CTAs, so K is split across gridDim.y CTAs; each writes its partial tile
-//                      to an L2-resident scratch and the LAST CTA to arrive for that tile (atomic
-//                      ticket) sums the partials IN FIXED ORDER (deterministic) and runs the fused
-//                      epilogue.  The RMSNorm statistic of the input rows (layers.py:613-616) is
-//                      computed from the A tiles the GEMM loads anyway (no separate pass), and the
-//                      epilogues are those of gemm_simt.cuh incl. the head-major KV-cache append.
-//
+//  sgemm_dec_cluster_kernel   exact-fp32 GEMM for M <= 64 rows, the default.  One thread-block CLUSTER (8 CTAs; 16 for
+//                      the long-K MLP-out projection) per 64 x 32 output tile splits K; every CTA pushes the rows
+//                      owned by rank r into rank r's shared memory and, after one cluster barrier, each rank sums its
+//                      rows in rank order (deterministic) and runs the fused epilogue: RMSNorm factor (statistic
+//                      computed from the A tiles the GEMM loads anyway, layers.py:613-616), residual, gated GELU,
+//                      head-major KV-cache append, per-tile sums of squares of the output.
+//  sgemm_dec_cluster2_kernel  two such GEMMs that read the same inputs in one launch (out-projection + the
+//                      cross-attention query projection through a precomposed weight block).
+//  sgemm_dec_kernel    the same GEMM without clusters (MT3_DEC_CLUSTER=0 / shapes the cluster kernel does not
+//                      tile): K split over gridDim.y CTAs, partial tiles through an L2-resident scratch, the LAST
+//                      CTA to arrive for a tile (atomic ticket) sums them in fixed order.
 //  dec_attention_bulk_kernel  one query per (sequence, head) over contiguous head-major K/V rows
 //                      (kv[b][K|V][head][cap][64]).  A producer warp streams 32-key tiles (8 KB) with
 //                      cp.async.bulk (TMA 1-D) into a 6-stage shared-memory ring, signalled through

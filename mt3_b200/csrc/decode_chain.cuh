@@ -1,4 +1,6 @@
-// Cluster-local GEMM chains for the decode step (sm_100a).
+// Cluster-local GEMM chains for the decode step (sm_100a).  MEASURED ALTERNATIVE, not the default (MT3_DEC_CHAIN=1):
+// parity-green but 1199 vs 566 ms per batch -- every cluster re-reads all weights (8x the L2 traffic) with ~54 KB
+// in flight per SM, ~15 us per stage.
 //
 // Sequences are independent through the whole decoder, so the grid-wide dependency between two consecutive
 // small GEMMs (every output column of GEMM i feeds every output of GEMM i+1) is only grid-wide because the

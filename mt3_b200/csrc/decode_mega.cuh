@@ -1,4 +1,7 @@
-// The whole decode step as ONE persistent kernel (sm_100a).
+// The whole decode step as ONE persistent kernel (sm_100a).  MEASURED ALTERNATIVE, not the default (MT3_DEC_MEGA=1):
+// parity-green but 773 vs 563 ms per batch when it was written -- a software grid barrier costs ~5 us against the
+// ~0.8 us gap between graph nodes, and one attention CTA per SM holds too few bytes in flight.
+// It still uses the unfused 8-GEMM layer and the pull-style cluster reduction of that time.
 //
 // A greedy decode step is a chain of 67 small, strictly dependent operations (embed, 8 x [QKV GEMM,
 // self-attention, out GEMM, q GEMM, cross-attention, out GEMM, MLP-in GEMM, MLP-out GEMM], logits GEMM,

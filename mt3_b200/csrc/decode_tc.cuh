@@ -1,3 +1,7 @@
+// MEASURED ALTERNATIVE, not the default (MT3_DEC_GEMM_MODE=1 with MT3_DEC_TC=1): parity-green (logits within 5e-6 of
+// the fp64 oracle) but 678 vs 521 ms per batch -- 24-48 DEPENDENT N=32 MMAs per CTA cost ~90 cycles each, more than
+// the FMA loop they replace.
+//
 // Decode-step GEMM on the 5th-generation tensor cores (sm_100a): M = B <= 64 sequences, one 8-CTA cluster per
 // 64 x 32 output tile, split-K across the cluster, push-style DSMEM reduction (see sgemm_dec_cluster_kernel in
 // decode.cuh for the reduction / epilogue contract -- this kernel only replaces the load and multiply phases).
@@ -14,7 +18,7 @@
 //   drain     warps 0/1 read their 32 lanes x 32 columns with tcgen05.ld and push 8-row slices to the owner ranks.
 //
 // The measured cost of the multiply phase of the FMA / mma.sync kernels was 1.0-3.6 us per node
-// (profiles/r01_call13_trace_step_*.log); here it is the latency of one commit.
+// (profiles/r01_call13_trace_step_*.log); this kernel's came out at 1.7-3.2 us (profiles/r01_call14_*).
 #pragma once
 
 #include <cuda.h>
