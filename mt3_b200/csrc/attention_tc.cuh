@@ -6,9 +6,10 @@
 // One CTA = 128 query rows of one (batch, head); T <= 256 keys, head_dim 64.
 //   S[128 q, T k]  = Q . K^T   tcgen05.mma kind::tf32, M=128, N=128 per key chunk, K=64 (8 k-steps);
 //                               error-compensated (Qhi.Khi + Qhi.Klo + Qlo.Khi) when hi/lo operands are given
-//   P = exp(S - rowmax)         one thread per query row reads its row from TMEM (tcgen05.ld), writes P
-//                               (rounded to tf32, unnormalised) into shared memory in the 128B-swizzled
-//                               K-major layout the next MMA reads as its A operand
+//   P = exp(S - rowmax)         two threads per query row read the row from TMEM (tcgen05.ld) and write P (rounded to
+//                               tf32, unnormalised) back over S in tensor memory (tcgen05.st): the next MMA reads
+//                               its A operand straight from TMEM (kAtPTmem; the older route through 128B-swizzled
+//                               shared-memory sub-tiles is kept behind the switch)
 //   O[128 q, 64 d] = P . V      B operand = V^T tiles [64 d x 32 keys] (keys contiguous, K-major), written per head
 //                               by the QKV GEMM epilogue (TcGemmArgs::VT_*): P . Vhi + P . Vlo; 1/rowsum is
 //                               applied in the epilogue.  (An MN-major tf32 B operand returned zeros on sm_100a
@@ -47,6 +48,8 @@ constexpr int kVSub = 64 * 32 * 4;        // one [64 d x 32 keys] V^T sub-tile =
 constexpr int kAtStage = 128 * 64 * 4;    // O staging tile (XOR-swizzled rows of 256 B) = 32 KB
 constexpr int kAtSmem = 3 * 4 * kAtSub + kAtStage + 256 + 2 * 2 * 128 * 4;   // 231 680 B of the 232 448 a CTA may have: no
                                                                               // slack, the dynamic window must be 1024-aligned
+constexpr int kAtPTmem = 1;               // 1: P stays in tensor memory (overwrites S in place) and is the P.V MMA's A operand;
+                                          // 0: P goes through four swizzled shared-memory sub-tile buffers in the Q region
 constexpr int kAtThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / epilogue (two per TMEM lane group)
 
 // PERSISTENT: one CTA per SM walks over work items (sequence b, head h, 128-query tile) with stride gridDim.x.  All
@@ -132,6 +135,16 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
         const uint32_t ph = it & 1, pph = ph ^ 1;
         const int qt = item % ntile, h = (item / ntile) % H, b = item / (ntile * H);
         const int row0 = b * T, q0 = qt * kAtQ;
+        auto load_q = [&]() {
+          tc::mbar_arrive_expect_tx(q_full, 2 * lo_tiles * kSubBytes);
+          for (int sub = 0; sub < 2; ++sub) {
+            tc::tma_load_2d(sQ + sub * kAtSub, &tm_hi, q_full, h * 64 + sub * 32, row0 + q0);
+            if (SPLIT3) tc::tma_load_2d(sQ + (2 + sub) * kAtSub, &tm_lo, q_full, h * 64 + sub * 32, row0 + q0);
+          }
+        };
+        // Q -> Q region.  With P in tensor memory the region is free as soon as the previous item's S MMAs have read Q
+        // (s_done, which this thread waited for before it loaded that item's V): request it first.
+        if (kAtPTmem) load_q();
         // K chunk 0 -> slot 0: free once the previous item's P.V MMAs over V chunk 0 are done
         if (it > 0) tc::mbar_wait(&pv_done[3], pph);
         tc::mbar_arrive_expect_tx(&k_full[0], 2 * lo_tiles * kSubBytes);
@@ -139,13 +152,10 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
           tc::tma_load_2d(slot[0] + sub * kAtSub, &tm_hi, &k_full[0], Q + h * 64 + sub * 32, row0);
           if (SPLIT3) tc::tma_load_2d(slot[0] + (2 + sub) * kAtSub, &tm_lo, &k_full[0], Q + h * 64 + sub * 32, row0);
         }
-        // Q -> Q region (= the previous item's P buffers) and K chunk 1 -> slot 1: free once its last P.V MMA is done
+        // Without P in tensor memory the Q region holds the previous item's P buffers until its last P.V MMA is done.
         if (it > 0) tc::mbar_wait(&pv_done[last_qc], pph);
-        tc::mbar_arrive_expect_tx(q_full, 2 * lo_tiles * kSubBytes);
-        for (int sub = 0; sub < 2; ++sub) {
-          tc::tma_load_2d(sQ + sub * kAtSub, &tm_hi, q_full, h * 64 + sub * 32, row0 + q0);
-          if (SPLIT3) tc::tma_load_2d(sQ + (2 + sub) * kAtSub, &tm_lo, q_full, h * 64 + sub * 32, row0 + q0);
-        }
+        if (!kAtPTmem) load_q();
+        // K chunk 1 -> slot 1: free once the previous item's last P.V MMA (over V chunk 1) is done (waited for above)
         if (nchunk > 1) {
           tc::mbar_arrive_expect_tx(&k_full[1], 2 * lo_tiles * kSubBytes);
           for (int sub = 0; sub < 2; ++sub) {
@@ -224,13 +234,20 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
           if (i == (c << 2)) AT_STAMP(5 + 3 * c);
           tc::tc_fence_after();
           const uint32_t p_addr = tc::smem_u32(sQ) + sub * kSubBytes;
+          const uint32_t p_tmem = tmem_S + (uint32_t)(qc * 32);            // P quarter-chunk: columns [32 qc, +32), all 128 lanes
           const uint32_t v_addr = tc::smem_u32(slot[c]) + sub * kVSub;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {                   // 32 keys = 4 k-steps of 8
-            const uint64_t a = tc::smem_desc_k_sw128(p_addr + ks * 32);
-            tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + ks * 32), idesc_o, acc);
-            acc = 1u;
-            if (SPLIT3) tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + 4 * kVSub + ks * 32), idesc_o, 1u);
+            if (kAtPTmem) {
+              tc::mma_tf32_ts(tmem_O, p_tmem + ks * 8, tc::smem_desc_k_sw128(v_addr + ks * 32), idesc_o, acc);
+              acc = 1u;
+              if (SPLIT3) tc::mma_tf32_ts(tmem_O, p_tmem + ks * 8, tc::smem_desc_k_sw128(v_addr + 4 * kVSub + ks * 32), idesc_o, 1u);
+            } else {
+              const uint64_t a = tc::smem_desc_k_sw128(p_addr + ks * 32);
+              tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + ks * 32), idesc_o, acc);
+              acc = 1u;
+              if (SPLIT3) tc::mma_tf32(tmem_O, a, tc::smem_desc_k_sw128(v_addr + 4 * kVSub + ks * 32), idesc_o, 1u);
+            }
           }
           tc::mma_commit(&pv_done[qc]);
           if ((i & 3) == 3) AT_STAMP(6 + 3 * c);
@@ -285,7 +302,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
         for (int sub = half * 2; sub < half * 2 + 2; ++sub) {  // this half's two quarter-chunks of chunk c -> P buffers `sub`
           const int qc = c * 4 + sub;
           const int c0 = c * kAtKC + sub * 32;
-          if (c > 0) {                                       // the buffer was read by quarter-chunk qc - 4's MMAs
+          if (c > 0 && !kAtPTmem) {                          // the buffer was read by quarter-chunk qc - 4's MMAs
             tc::mbar_wait(&pv_done[qc - 4], ph);
             tc::tc_fence_after();
           }
@@ -301,12 +318,21 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
             p[j] = e;
             sum += e;
           }
-          // P sub-tile buffer `sub`, row r, 8 x 16-byte pieces XOR-swizzled by (r % 8)
-          uint8_t* rowp = sQ + sub * kAtSub + r * 128;
+          if (kAtPTmem) {
+            // P overwrites S in place: same lanes, same 32 columns; the P.V MMA reads it as its A operand
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            *reinterpret_cast<float4*>(rowp + ((j4 ^ (r & 7)) << 4)) = make_float4(p[4 * j4], p[4 * j4 + 1], p[4 * j4 + 2], p[4 * j4 + 3]);
-          tc::fence_proxy_async();                           // generic-proxy writes -> visible to the MMA (async proxy)
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(p[j]);
+            tc::tmem_st_32x32(tmem_S + lane_base + c0, v);
+            tc::tmem_st_wait();
+            tc::tc_fence_before();
+          } else {
+            // P sub-tile buffer `sub`, row r, 8 x 16-byte pieces XOR-swizzled by (r % 8)
+            uint8_t* rowp = sQ + sub * kAtSub + r * 128;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<float4*>(rowp + ((j4 ^ (r & 7)) << 4)) = make_float4(p[4 * j4], p[4 * j4 + 1], p[4 * j4 + 2], p[4 * j4 + 3]);
+            tc::fence_proxy_async();                         // generic-proxy writes -> visible to the MMA (async proxy)
+          }
           tc::mbar_arrive(&p_full[qc]);
         }
         AT_STAMP(19 + 2 * c);

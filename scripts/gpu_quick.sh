@@ -1,7 +1,8 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -4 | tee gpurun_out/pytest_gpu.log
-echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/smoke.log
-echo "== bench"; timeout 600 python bench.py 2> gpurun_out/bench_default.err | tail -1 > gpurun_out/bench_default.json
-grep -E "timed|e2e |cpu port" gpurun_out/bench_default.err; cut -c1-260 gpurun_out/bench_default.json
+timeout 300 ./mt3_b200/csrc/tools/attn_tc_test 2>&1 | tail -7 | tee gpurun_out/attn_tc_test.log
+echo "== pytest -m gpu"; timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -3 | tee gpurun_out/pytest_gpu.log
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1 | tee gpurun_out/smoke.log
+timeout 600 python bench.py --ref-budget-s 5 2> gpurun_out/bench_default.err | tail -1 > gpurun_out/bench_default.json
+grep -E "timed|e2e |microbench" gpurun_out/bench_default.err | sed 's/.*kernel microbench: .*enc_qkv/enc_qkv/'
