@@ -248,3 +248,25 @@ def test_no_cpu_fallback_without_gpu():
         inference.InferenceModel('synthetic', 'mt3')
     with pytest.raises(ValueError):
         inference.InferenceModel('synthetic', 'nope')
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU port on the host cores) runs without a GPU and prints ONE JSON line with
+    the contract's keys; under torchrun only rank 0 prints (the others exit 0 without work)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+           "--dec-steps", "3", "--ref-batch", "2", "--ref-budget-s", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "audio_seconds_per_second" and line["unit"] == "audio-s/s"
+    assert line["higher_is_better"] is True and line["value"] > 0 and line["n_gpus"] == 1
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["e2e"]["value"] == line["value"]
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    other = subprocess.run(cmd[:2] + ["--impl", "reference", "--gpus", "2"], capture_output=True, text=True, timeout=120, cwd=root, env=env)
+    assert other.returncode == 0 and other.stdout.strip() == ""
