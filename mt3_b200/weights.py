@@ -117,5 +117,11 @@ def save(path: str, params: Dict[str, np.ndarray]) -> None:
 
 
 def load(path: str) -> Dict[str, np.ndarray]:
+    """A .npz written by save(), or a T5X checkpoint directory (the reference's `gs://mt3/checkpoints/<model>/`,
+    notebook :247-262) read by mt3_b200.checkpoints without t5x / tensorstore."""
+    import os
+    if os.path.isdir(path) or os.path.basename(path) == "checkpoint":
+        from . import checkpoints
+        return checkpoints.load_t5x_checkpoint(path)
     with np.load(path) as z:
         return {k.replace("|", "/"): z[k] for k in z.files}

@@ -270,3 +270,37 @@ def test_bench_reference_arm_contract():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
     other = subprocess.run(cmd[:2] + ["--impl", "reference", "--gpus", "2"], capture_output=True, text=True, timeout=120, cwd=root, env=env)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("old_layout", [False, True])
+def test_t5x_checkpoint_reader_roundtrip(tmp_path, old_layout):
+    """checkpoints.load_t5x_checkpoint reads the T5X directory layout (msgpack state with inlined small arrays and
+    PLACEHOLDER:// references to gzip zarr-v2 arrays, chunked) back to the Flax tree paths weights.flatten expects."""
+    from mt3_b200 import checkpoints, network, weights
+    cfg = network.T5Config(vocab_size=256, emb_dim=64, num_heads=2, num_encoder_layers=1, num_decoder_layers=1, head_dim=64,
+                           mlp_dim=128, mlp_activations=('gelu', 'linear'))
+    params = weights.synthetic_params(cfg, 5)
+    d = tmp_path / "ckpt"
+    checkpoints.save_t5x_checkpoint(str(d), params, step=123, inline_below=200, max_chunk=48, old_layout=old_layout)
+    assert (d / "checkpoint").exists()
+    root = "optimizer.target" if old_layout else "target"
+    zdir = d / f"{root}.decoder.logits_dense.kernel"
+    assert (zdir / ".zarray").exists() and (zdir / "0.0").exists() and (zdir / "1.5").exists()      # 64x256 in 48x48 chunks
+    got = weights.load(str(d))
+    assert set(got) == set(params)
+    for k in params:
+        assert got[k].dtype == np.float32 and np.array_equal(got[k], params[k]), k
+    np.testing.assert_array_equal(weights.flatten(got, cfg), weights.flatten(params, cfg))
+    np.testing.assert_array_equal(checkpoints.load_t5x_checkpoint(str(d / "checkpoint"))["encoder/encoder_norm/scale"],
+                                  params["encoder/encoder_norm/scale"])
+    # uncompressed, F-order, missing chunk -> fill value
+    import json
+    a = np.arange(12, dtype=np.float32).reshape(3, 4)
+    z = tmp_path / "arr"
+    z.mkdir()
+    (z / ".zarray").write_text(json.dumps({"zarr_format": 2, "shape": [3, 4], "chunks": [2, 4], "dtype": "<f4", "order": "F",
+                                           "compressor": None, "fill_value": 7.0, "filters": None}))
+    (z / "0.0").write_bytes(np.asfortranarray(a[:2]).tobytes(order="F"))
+    r = checkpoints.read_zarr_array(str(z))
+    np.testing.assert_array_equal(r[:2], a[:2])
+    assert (r[2] == 7.0).all()
