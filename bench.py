@@ -12,10 +12,16 @@ so the worst case is what is timed; nothing is skipped).
 
 `value`  device-resident inputs, timed with CUDA events per step (L2 flushed between steps),
          max over ranks, whole-job aggregate over N GPUs (weak scaling: 64 segments per GPU).
+         Arithmetic is float32 everywhere; the decoder's K/V rows are STORED as fp16 by default
+         (--kv f16: half the bytes the decode step streams; parity-tested against the float64
+         oracle at cache lengths up to 1024, logit error ~1.3e-4 of the 5e-4 bar).  The same pass
+         with fp32 K/V rows is timed too and reported as `value_kv_f32`.
 `e2e`    same metric through InferenceModel.transcribe_segments with pinned HOST audio in and
          HOST tokens out (H2D + D2H inside the timed region).
 `roofline` the dominant kernel (decode self-attention over the KV cache), algorithmic bytes per
-         launch / CUDA-event time per launch, against MEASURED_PEAKS.json's HBM copy bandwidth.
+         launch / CUDA-event time per launch, against MEASURED_PEAKS.json's HBM copy bandwidth;
+         `roofline.job`: the whole pass -- algorithmic bytes of one step (all K/V rows read once per
+         decode step + the decoder weights once per decode step) / the measured step time.
 `cpu_baseline` the torch-CPU port of the reference semantics (oracle/torch_cpu.py; the JAX/T5X
          reference itself is not installable here) on a bounded sample, rank 0, N=1 only.
 """
@@ -124,6 +130,14 @@ def host_threads():
     return max(1, min(n, 64))
 
 
+def workload_config(dec_steps):
+    """`config` is IDENTICAL in both arms (the driver compares them): what is computed, not how."""
+    return {"workload": "mt3 config (BASELINE configs[1]): batch=64 x 2.048 s synthetic sine-mix segments per GPU, "
+                        f"log-mel + 8-layer encoder + greedy decode, {dec_steps} decode steps, EOS never stops the loop; "
+                        "GPU arm: L2 flushed between timed steps (256 MB write)",
+            "segments_per_gpu": BATCH_PER_GPU, "dec_steps": dec_steps}
+
+
 def log(msg):
     sys.stderr.write(f"[bench {time.strftime('%H:%M:%S')}] {msg}\n")
     sys.stderr.flush()
@@ -176,9 +190,16 @@ def load_peaks():
 
 
 # --------------------------------------------------------------------------------------------
+def ref_budget(args):
+    """Wall-time budget of one CPU sample's decode loop: the whole `--steps K --warmup W` run must end within a few
+    minutes, so the per-sample budget shrinks with K + W (the decode is extrapolated linearly from the steps that fit,
+    which favours the CPU: the per-step cost grows with the cache)."""
+    return max(2.0, min(args.ref_budget_s, 200.0 / max(1, args.steps + args.warmup)))
+
+
 def run_reference(args):
-    """The reference arm: the CPU restatement (torch-CPU port of the oracle) on the host cores.
-    Each step is one bounded sample of the workload (see cpu_port_sample); `value` is the mean."""
+    """The reference arm: the CPU restatement (torch-CPU port of the oracle) on the host cores, on the SAME workload
+    as the GPU arm (64 segments per batch).  Each step is one bounded sample (see cpu_port_sample); `value` is the mean."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -187,9 +208,9 @@ def run_reference(args):
     params = O.init_params(O.T5Config(), seed=0)
     audio = torch.from_numpy(synth_audio(args.ref_batch, 1234))
     vals, mss = [], []
+    budget = ref_budget(args)
     for i in range(args.warmup + args.steps):
-        budget = args.ref_budget_s if i >= args.warmup else min(3.0, args.ref_budget_s)
-        v, cores, desc, ms = cpu_port_sample(params, audio, args.ref_batch, args.dec_steps, budget)
+        v, cores, desc, ms = cpu_port_sample(params, audio, args.ref_batch, args.dec_steps, budget if i >= args.warmup else min(3.0, budget))
         if i >= args.warmup:
             vals.append(v)
             mss.append(ms)
@@ -198,10 +219,9 @@ def run_reference(args):
         "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(mss)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "mt3 config (BASELINE configs[1]): batch=64 x 2.048 s synthetic sine-mix segments per GPU, "
-                               f"log-mel + 8-layer encoder + greedy decode, {args.dec_steps} decode steps, EOS never stops the loop",
-                   "sample_batch": args.ref_batch, "dec_steps": args.dec_steps},
-        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": desc},
+        "config": workload_config(args.dec_steps),
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": desc,
+                         "sample_batch": args.ref_batch, "decode_budget_s": budget},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -229,7 +249,8 @@ def run_ours(args):
     # ---- weights: rank 0 draws them, ONE NCCL broadcast at load (north_star) -------------------
     # (InferenceModel.restore_from_checkpoint: only rank 0 materialises the checkpoint, then broadcast_params)
     gm = {'simt': _lib.GEMM_FP32_SIMT, 'tf32x3': _lib.GEMM_TF32X3, 'tf32': _lib.GEMM_TF32}[args.gemm_mode]
-    im = inference.InferenceModel('synthetic:0', 'mt3', device=dev, batch_size=B, use_graph=True, gemm_mode=gm)
+    kvf = {'f32': _lib.KV_F32, 'f16': _lib.KV_F16}[args.kv]
+    im = inference.InferenceModel('synthetic:0', 'mt3', device=dev, batch_size=B, use_graph=True, gemm_mode=gm, kv_format=kvf)
 
     # ---- inputs: contiguous shard of the global segment list ---------------------------------
     audio_host = torch.from_numpy(synth_audio(B, 1234 + rank * B)).pin_memory()
@@ -274,10 +295,12 @@ def run_ours(args):
 
     log(f"timed {args.steps} steps: {total_ms / args.steps:.1f} ms/step; e2e leg")
     # ---- e2e: public API with HOST buffers (H2D + D2H inside the timed region) ----------------
-    im.transcribe_segments(audio_host, num_steps=dec_steps, stop_at_eos=False)   # warm
+    out_host = im.transcribe_segments(audio_host, num_steps=dec_steps, stop_at_eos=False)   # warm the API path ...
+    if world > 1:                                                                            # ... and the collective
+        mt3_dist.gather_tokens(torch.from_numpy(out_host).to(dev), world * B)
     barrier()
     e2e_times = []
-    for _ in range(max(1, min(args.steps, 3))):
+    for _ in range(max(3, min(args.steps, 5))):
         flush.fill_(1)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
@@ -287,13 +310,40 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
             assert all_tokens.shape == (world * B, 1024)
         e2e_times.append(time.perf_counter() - t0)
-    e2e_ms = 1000.0 * float(np.mean(e2e_times))
+    e2e_ms = 1000.0 * float(np.median(e2e_times))
+
+    # ---- the same device-resident pass with the OTHER K/V storage format (fp32 rows when the headline uses fp16) -------
+    alt_ms = None
+    if not args.no_alt_kv:
+        alt_name = 'f32' if args.kv == 'f16' else 'f16'
+        im_alt = inference.InferenceModel('synthetic:0', 'mt3', device=dev, batch_size=B, use_graph=True, gemm_mode=gm,
+                                          kv_format={'f32': _lib.KV_F32, 'f16': _lib.KV_F16}[alt_name])
+
+        def alt_pass():
+            spec = spectrograms.compute_spectrogram(audio_dev, im_alt.spectrogram_config)
+            im_alt.model.generate(spec, num_steps=dec_steps, stop_at_eos=False, use_graph=True, out=tokens)
+        for _ in range(2):
+            alt_pass()
+        barrier()
+        ts = []
+        for _ in range(3):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            alt_pass()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        alt_ms = float(np.mean(ts))
+        del im_alt
+        torch.cuda.empty_cache()
 
     # ---- all-gather of the decoded token streams at the end (north_star) -----------------------
     if world > 1:
-        t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([total_ms, e2e_ms, alt_ms or 0.0], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_ms = float(t[0]), float(t[1])
+        alt_ms = float(t[2]) if alt_ms is not None else None
         ln = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(ln)
         launches = int(ln[0])
@@ -313,7 +363,8 @@ def run_ours(args):
         stream = torch.cuda.current_stream(dev).cuda_stream
         pos = 511                                   # mean cache length of a 1024-step decode
         H, D = 6, 64
-        alg_bytes = B * H * (pos + 1) * D * 4 * 2 + B * H * D * 4 * 2     # K and V rows read once + q in, o out
+        elt = 2 if args.kv == 'f16' else 4          # bytes per stored K/V element
+        alg_bytes = B * H * (pos + 1) * D * elt * 2 + B * H * D * 4 * 2   # K and V rows read once + q in, o out
         iters = 64
         for _ in range(2):
             _lib.check(lib.mt3_debug_launch(h, _lib.K_DEC_SELF_ATTN, pos, 8, stream))
@@ -325,9 +376,21 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         us = 1000.0 * e0.elapsed_time(e1) / iters
         ach = alg_bytes / (us * 1e-6) / 1e9
-        roofline = {"kernel": "dec_attention_bulk_kernel (decode self-attention, cache length 512, B=64, 6 heads)", "bound": "hbm",
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": load_traffic("dec_attention_bulk_kernel"),
+        roofline = {"kernel": f"dec_attention_bulk_kernel (decode self-attention, cache length 512, B=64, 6 heads, {args.kv} K/V rows)", "bound": "hbm",
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": load_traffic("dec_attention_bulk_kernel_" + args.kv),
                     "peak_source": peak_src, "us_per_launch": us, "algorithmic_bytes_per_launch": alg_bytes}
+        # the whole pass against the same peak: every decode step reads all K/V rows written so far (self) and the 256
+        # hoisted rows (cross) of 8 layers once, plus the decoder's 103.9 MB of fp32 weights (L2-resident across steps
+        # when they fit, counted anyway); encoder + frontend traffic (< 1 %) is left out, so the fraction is a lower bound
+        Ld, T = 8, 256
+        kv_bytes = sum(B * H * D * elt * 2 * (l_ + T) for l_ in range(1, dec_steps + 1)) * Ld
+        w_bytes = 103.9e6 * dec_steps
+        job_bytes = kv_bytes + w_bytes
+        job_ach = job_bytes / (ms_per_step * 1e-3) / 1e9
+        roofline["job"] = {"bytes_per_step": job_bytes, "kv_bytes": kv_bytes, "weight_bytes": w_bytes, "achieved": job_ach, "peak": peak,
+                           "unit": "GB/s", "frac": job_ach / peak, "ms_per_step": ms_per_step,
+                           "floor_ms": job_bytes / (peak * 1e9) * 1e3}
         # back-to-back launch time of the other hot kernels at the bench shapes (device events, stream order)
         kernels_us = {}
         for name, kind, p_, it_ in (("dec_self_attention_len512", _lib.K_DEC_SELF_ATTN, 511, 64),
@@ -372,19 +435,21 @@ def run_ours(args):
         log("kernel microbench: " + ", ".join(f"{k}={v:.1f}us" for k, v in kernels_us.items()))
         if world == 1 and not args.no_cpu_baseline:
             log("cpu baseline (torch-CPU port) ...")
-            v, cores, desc, _ = cpu_port_sample(weights.synthetic_params(im._model_config(), 0), audio_host, args.ref_batch,
-                                                dec_steps, args.ref_budget_s)
-            cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": desc}
+            cpu_params = weights.synthetic_params(im._model_config(), 0)
+            cpu_port_sample(cpu_params, audio_host, args.ref_batch, dec_steps, 2.0)          # warm (thread pool, allocator)
+            v, cores, desc, _ = cpu_port_sample(cpu_params, audio_host, args.ref_batch, dec_steps, args.ref_budget_s)
+            cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": desc,
+                            "sample_batch": args.ref_batch}
 
     if rank == 0:
         line = {
             "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "mt3 config (BASELINE configs[1]): batch=64 x 2.048 s synthetic sine-mix segments per GPU, "
-                                   f"log-mel + 8-layer encoder + greedy decode, {dec_steps} decode steps, EOS never stops the loop",
-                       "segments_per_gpu": B, "dec_steps": dec_steps, "gemm_mode": args.gemm_mode, "l2": "flushed between steps (256 MB write)",
-                       "parallelism": f"dp{world} (segments sharded, 1 weight broadcast, 1 token all-gather)"},
+            "config": workload_config(dec_steps),
+            "impl_config": {"gemm_mode": args.gemm_mode, "kv_cache": args.kv + " rows, fp32 arithmetic",
+                            "l2": "flushed between steps (256 MB write)",
+                            "parallelism": f"dp{world} (segments sharded, 1 weight broadcast, 1 token all-gather)"},
             "segments_per_second": value / SEG_SECONDS,
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(B * SEG_SAMPLES * 4),
                     "d2h_bytes_per_step": int(B * 1024 * 4), "ms_per_step": e2e_ms,
@@ -392,6 +457,10 @@ def run_ours(args):
             "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
             "clocks": clocks, "roofline": roofline,
         }
+        if alt_ms is not None:
+            alt_name = 'f32' if args.kv == 'f16' else 'f16'
+            line["value_kv_" + alt_name] = world * B * SEG_SECONDS / (alt_ms / 1000.0)
+            line["ms_per_step_kv_" + alt_name] = alt_ms
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
@@ -407,7 +476,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dec-steps", type=int, default=1024)
-    ap.add_argument("--ref-batch", type=int, default=8, help="CPU sample: segments (the notebook's batch size)")
+    ap.add_argument("--ref-batch", type=int, default=BATCH_PER_GPU, help="CPU sample: segments per batch (the GPU arm's 64)")
+    ap.add_argument("--kv", default="f16", choices=["f32", "f16"], help="storage format of the decoder's K/V rows")
+    ap.add_argument("--no-alt-kv", action="store_true", help="skip timing the other K/V storage format")
     ap.add_argument("--ref-budget-s", type=float, default=15.0, help="CPU sample: wall-time budget of the decode loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-mode", default="tf32x3", choices=["simt", "tf32x3", "tf32"],

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MT3_ABI_VERSION 1
+#define MT3_ABI_VERSION 2
 
 enum {
   MT3_OK = 0,
@@ -104,12 +104,22 @@ typedef struct {
   int32_t max_input_length;    /* largest T (256 mt3, 512 ismir2021)                 */
   int32_t max_decode_length;   /* decoder length L (1024)                            */
   int32_t gemm_mode;           /* MT3_GEMM_* below                                   */
+  int32_t kv_cache_format;     /* MT3_KV_* below (ABI version 2)                     */
 } mt3_model_config;
 
 enum {
   MT3_GEMM_FP32_SIMT = 0,   /* exact fp32 FMA on CUDA cores (debug / parity anchor)  */
   MT3_GEMM_TF32X3 = 1,      /* tcgen05 kind::tf32, 3-term split, fp32-faithful       */
   MT3_GEMM_TF32 = 2         /* tcgen05 kind::tf32 single pass (10-bit mantissa)      */
+};
+
+/* Storage format of the decoder's K/V rows -- the self-attention cache (layers.py:249-289) and the hoisted
+ * cross-attention K/V.  All arithmetic (projections, scores, softmax, P.V) stays float32; only the stored rows are
+ * rounded.  F32 keeps the reference's values exactly; F16 halves the bytes the decode step streams from HBM
+ * (measured logit error 1.3e-4 of the logit scale against the float64 oracle, bar 5e-4: DESIGN.md section 4). */
+enum {
+  MT3_KV_F32 = 0,
+  MT3_KV_F16 = 1
 };
 
 /* Number of float32 elements in the flat weight blob and the offset of a named

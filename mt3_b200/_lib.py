@@ -14,7 +14,9 @@ LIB_PATH = os.path.join(HERE, "libmt3b200.so")
 
 MT3_OK = 0
 GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_TF32 = 0, 1, 2
+KV_F32, KV_F16 = 0, 1
 GEN_STOP_AT_EOS, GEN_USE_GRAPH = 1, 2
+ABI_VERSION = 2
 K_DEC_SELF_ATTN, K_DEC_CROSS_ATTN, K_DEC_QKV_GEMM, K_ENC_QKV_GEMM, K_ENC_ATTN = 0, 1, 2, 3, 4
 
 EXPORTS = [
@@ -41,7 +43,8 @@ class ModelConfig(C.Structure):
     _fields_ = [("vocab_size", C.c_int32), ("emb_dim", C.c_int32), ("num_heads", C.c_int32),
                 ("head_dim", C.c_int32), ("num_encoder_layers", C.c_int32), ("num_decoder_layers", C.c_int32),
                 ("mlp_dim", C.c_int32), ("input_depth", C.c_int32), ("max_batch", C.c_int32),
-                ("max_input_length", C.c_int32), ("max_decode_length", C.c_int32), ("gemm_mode", C.c_int32)]
+                ("max_input_length", C.c_int32), ("max_decode_length", C.c_int32), ("gemm_mode", C.c_int32),
+                ("kv_cache_format", C.c_int32)]
 
 
 _lib = None
@@ -83,6 +86,9 @@ def load() -> C.CDLL:
     lib.mt3_debug_trace_step.argtypes = [vp, i32, vp, i32, C.c_char_p, i32, C.POINTER(C.c_int32), vp]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here = header/library mismatch
+    if lib.mt3_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{LIB_PATH} has ABI version {lib.mt3_abi_version()}, this package binds version {ABI_VERSION}: "
+                           "rebuild with `python -m mt3_b200.build --force`")
     _lib = lib
     return lib
 

@@ -91,20 +91,13 @@ inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, di
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[3];
+  cudaLaunchAttribute attr[2];
   int na = 0;
   attr[na].id = cudaLaunchAttributeClusterDimension;
   attr[na].val.clusterDim.x = 1;
   attr[na].val.clusterDim.y = cluster_y;
   attr[na].val.clusterDim.z = 1;
   ++na;
-  // MT3_CLUSTER_POLICY=1 spread / 2 load-balancing: where the CTAs of a cluster land (default: the driver's choice)
-  static const int policy = [] { const char* e = getenv("MT3_CLUSTER_POLICY"); return e ? atoi(e) : 0; }();
-  if (policy == 1 || policy == 2) {
-    attr[na].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;
-    attr[na].val.clusterSchedulingPolicyPreference = policy == 1 ? cudaClusterSchedulingPolicySpread : cudaClusterSchedulingPolicyLoadBalancing;
-    ++na;
-  }
   if (pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
@@ -113,6 +106,18 @@ inline cudaError_t launch_kernel_cluster(void (*kernel)(KArgs...), dim3 grid, di
   cfg.attrs = attr;
   cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// Packed fp32 FMA (sm_100a FFMA2): d.x = a * b.x + d.x, d.y = a * b.y + d.y -- two IEEE fp32 FMAs in one issue slot
+// (ptxas emits FFMA2 Rd, Ra.F32, Rb.F32x2, Rc.F32x2: the scalar operand is broadcast by the instruction itself).
+// Scalar FFMA issues at half rate per sub-partition on this part; FFMA2 is how the fp32 pipe reaches its peak.
+__device__ __forceinline__ void ffma2(float2& d, float a, float2 b) {
+  unsigned long long aa, bb, dd;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(dd) : "f"(d.x), "f"(d.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(dd));
 }
 
 // x = hi + lo with hi = x truncated to tf32 (what kind::tf32 reads), lo = x - hi (exact in fp32).

@@ -17,6 +17,8 @@
 // norm's learned scale is folded into B's rows when the model is created.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace mt3 {
@@ -33,7 +35,7 @@ struct GemmArgs {
   const float* pe; int pe_T; int pe_ld;  // EPI_ADD_PE
   float* C; int ldc;
   int n_split;                 // columns >= n_split -> head-major K/V store at C1 (N if unused)
-  float* C1; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // head-major K/V store, see kv_dest()
+  void* C1; int kv_half; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // head-major K/V store (fp32 / fp16), see kv_dest()
 };
 
 // Head-major K/V layout shared by the self-attention cache and the hoisted cross K/V:
@@ -181,7 +183,14 @@ sgemm_kernel(const GemmArgs p) {
           *reinterpret_cast<float4*>(p.C + (long long)m * p.ldc + n) = v;
         } else {
           const int pos = p.hm_pos ? *p.hm_pos : 0;
-          *reinterpret_cast<float4*>(p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos)) = v;
+          const long long d = kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos);
+          if (p.kv_half) {
+            __half2* dst = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.C1) + d);
+            dst[0] = __floats2half2_rn(v.x, v.y);
+            dst[1] = __floats2half2_rn(v.z, v.w);
+          } else {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C1) + d) = v;
+          }
         }
       }
     }

@@ -21,6 +21,8 @@
 // sinusoid add, gated-GELU, split store (KV-cache append), plus optional hi/lo split of the output.
 #pragma once
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "gemm_simt.cuh"   // EPI_* enums, gelu_tanh
 #include "tc.cuh"
@@ -34,7 +36,7 @@ struct TcGemmArgs {
   const float* R_hi; const float* R_lo; int ldr;
   const float* pe; int pe_T; int pe_ld;
   float* C_hi; float* C_lo; int ldc;       // C_lo != null: write hi/lo split of the result
-  int n_split; float* C1; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // head-major K/V store, see kv_dest()
+  int n_split; void* C1; int kv_half; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // head-major K/V store (fp32 / fp16), see kv_dest()
   // Transposed per-head store for columns >= vt_col0 (the V third of a fused QKV projection), enabled by VT_hi:
   // vt[((b*H + h)*64 + d)*vt_T + t] with row m = b*vt_T + t, column = vt_col0 + h*64 + d.  This is the K-major
   // (keys contiguous) operand the tcgen05 attention kernel reads for P.V.
@@ -220,7 +222,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (p.C_lo) cl = p.C_lo + (long long)m * p.ldc + n;
       } else {
         const int pos = p.hm_pos ? *p.hm_pos : 0;
-        ch = p.C1 + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos);
+        const long long d = kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos);
+        if (p.kv_half) {                     // 32 consecutive columns of one head: 64 contiguous bytes of fp16
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C1) + d);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __half2 h0 = __floats2half2_rn(v[8 * q], v[8 * q + 1]), h1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
+            __half2 h2 = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]), h3 = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
+            uint4 u;
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            dst[q] = u;
+          }
+          continue;
+        }
+        ch = reinterpret_cast<float*>(p.C1) + d;
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {

@@ -5,8 +5,8 @@
 // Data layout in HBM (all fp32, row-major):
 //   hidden h        [B*T, D]
 //   qkv             [B*T, 3Q]   columns [q | k | v], each (head, 64)
-//   cross K/V       [Ld][B*T, 2Q]  columns [k | v]          (hoisted: computed once per batch)
-//   self K/V cache  [Ld][B][L][2Q] columns [k | v]          (append = one contiguous row write)
+//   cross K/V       [Ld][B][K|V][H][T][64]  head-major, fp32 or fp16 (hoisted: computed once per batch)
+//   self K/V cache  [Ld][B][K|V][H][L][64]  head-major, fp32 or fp16 (append = 12 rows of 64 per sequence per layer)
 // The reference's [B,H,D,L] cache layout (layers.py:249-260) is a TPU scatter trick; the
 // ABI exposes tokens and logits, not the cache, so the layout is ours.
 #include <string.h>
@@ -21,9 +21,6 @@
 #include "gemm_tc.cuh"
 #include "attention_tc.cuh"
 #include "decode.cuh"
-#include "decode_tc.cuh"
-#include "decode_chain.cuh"
-#include "decode_mega.cuh"
 #include "layers.cuh"
 
 namespace mt3 {
@@ -91,34 +88,20 @@ struct Model {
   bool fuse_q = true;             // MT3_DEC_FUSE=0: keep the self-attention out-projection and the cross-attention query
                                   // projection as two launches (default: one launch with a precomposed weight block)
   float *dy2 = nullptr, *dssq = nullptr;   // second residual-stream buffer (ping-pong) and [B][D/32] sum-of-squares partials
-  float* slab_dect = nullptr;     // K-major fp32 copies W^T [N, K] of the decoder's step weights (tcgen05 decode GEMM)
-  bool dec_tc = true;             // MT3_DEC_TC=0: tensor-core decode modes use the mma.sync kernel instead of tcgen05
-  std::map<const float*, const float*> dec_wt;                                   // [K, N] weight -> its W^T copy
-  std::map<std::tuple<const void*, int, int, int>, CUtensorMap> dec_maps;       // (ptr, rows, K, ld) -> TMA map
   bool tc = false, split3 = false;
   TcW t_w_in;
   Act a_x, a_h, a_ao, a_g, a_enc, a_qkv, a_vt; // tcgen05-path activation buffers (workspace); a_vt = per-head V^T
   bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between all decode-step kernels
   bool pdl_attn = false;          // MT3_PDL=2: only the attention launches (K/V prefetch under the preceding GEMM)
   bool pdl_gemm = false;          // MT3_PDL=4: only the GEMM launches; bits combine (6 = attention + GEMM)
-  int dec_gemm_mode = 0;          // decode GEMM arithmetic: 0 fp32 FMA, 1 3xTF32 mma, 2 1xTF32 mma (follows gemm_mode;
-                                  // MT3_DEC_GEMM_MODE overrides)
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
-  int dec_streams = 1;            // MT3_DEC_STREAMS=n: decode step runs as n concurrent sub-batches
+  DecGemmOpts dec_opts;           // MT3_DEC_GROUPS / MT3_DEC_CLUSTER16
+  bool kv_half = false;           // cfg.kv_cache_format == MT3_KV_F16: self and cross K/V rows stored as fp16
+  int kv_elt = 4;                 // bytes per K/V element
   // debug timeline (mt3_debug_trace_step): while `tracing` is set every decode GEMM / attention launch gets a slot
   unsigned long long* trace = nullptr;
   bool tracing = false;
   std::vector<std::string> trace_names;
-  bool chain = false;             // MT3_DEC_CHAIN=1: cluster-local GEMM chains (decode_chain.cuh), 35 launches per step
-  int chain_cluster = 0;          // cluster size picked for the chain kernel (16 or 8)
-  bool mega = false;              // MT3_DEC_MEGA=1: the whole decode step as one persistent kernel (decode_mega.cuh)
-  MegaPhase* mega_prog = nullptr; int64_t mega_prog_bytes = 0; unsigned* mega_bar = nullptr;
-  int mega_phases = 0, mega_clusters = 0; bool mega_ready = false;
-  cudaStream_t sub_stream[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
-  int interleave = 0;             // MT3_DEC_INTERLEAVE=n: n blocks of sequences, attention nodes serialised across blocks
-  cudaEvent_t ev_hbm[64] = {};    // one per bandwidth-bound node of a step (n * Ld * 2 <= 64)
-  int64_t dpartial_stride = 0, dcounters_stride = 0;
   bool tc_attn_ok = true;         // MT3_TC_ATTENTION=0 in the environment forces the exact-fp32 attention kernel
   float* w_in = nullptr;
   std::vector<EncLayer> enc;
@@ -134,10 +117,11 @@ struct Model {
   int64_t ws_bytes = 0;
   int B = 0, T = 0;
   float *h = nullptr, *rstd = nullptr, *qkv = nullptr, *ao = nullptr, *g = nullptr, *encoded = nullptr;
-  float *ckv = nullptr, *skv = nullptr;
+  char *ckv = nullptr, *skv = nullptr;   // head-major K/V (kv_elt bytes per element)
   float *dy = nullptr, *drstd = nullptr, *dq = nullptr, *dao = nullptr, *dg = nullptr, *dlogits = nullptr;
   int *tok_cur = nullptr, *finished = nullptr, *tokens = nullptr, *state = nullptr;
-  float* dpartial = nullptr;      // split-K scratch of the decode GEMM
+  float* dpartial = nullptr;      // split-K scratch of the non-cluster decode GEMM
+  int dcounters_n = 0;
   int* dcounters = nullptr;
   int sm_count = 148;
   bool have_cross = false;
@@ -150,6 +134,11 @@ struct Model {
   uint64_t graph_kernels = 0;
   int* h_flag = nullptr;          // pinned
 };
+
+// byte address of layer l's K/V block: [B][K|V][H][cap][64] elements of kv_elt bytes
+static char* kv_layer(const Model* m, char* base, int l, int cap) {
+  return base + (int64_t)l * m->B * cap * 2 * m->Q * m->kv_elt;
+}
 
 static int64_t prepared_floats(const mt3_model_config& c) {
   const int64_t D = c.emb_dim, Q = (int64_t)c.num_heads * c.head_dim, F = c.mlp_dim, V = c.vocab_size;
@@ -319,7 +308,7 @@ static int cross_kv_tc_impl(Model* m, const float* encoded, cudaStream_t s) {
   }
   for (int l = 0; l < m->Ld; ++l) {
     TcGemmArgs a = tc_args(M, 2 * Q, D, nullptr, nullptr, 2 * Q);
-    a.n_split = 0; a.C1 = m->ckv + (int64_t)l * M * 2 * Q; a.hm_rows_per_b = m->T; a.hm_cap = m->T; a.hm_H = m->H;
+    a.n_split = 0; a.C1 = kv_layer(m, m->ckv, l, m->T); a.kv_half = m->kv_half ? 1 : 0; a.hm_rows_per_b = m->T; a.hm_cap = m->T; a.hm_H = m->H;
     MT3_TRY(launch_tc_gemm(ope, m->dec[l].t_wkv_c.op, a, m->split3, s));
   }
   return MT3_OK;
@@ -378,12 +367,12 @@ static int cross_kv_impl(Model* m, const float* encoded, cudaStream_t s) {
   } else {
     for (int l = 0; l < m->Ld; ++l) {
       GemmArgs a = gemm_args(encoded, D, m->dec[l].wkv_c, 2 * Q, M, 2 * Q, D, nullptr, 2 * Q);
-      a.n_split = 0; a.C1 = m->ckv + (int64_t)l * M * 2 * Q; a.hm_rows_per_b = m->T; a.hm_cap = m->T; a.hm_H = m->H;
+      a.n_split = 0; a.C1 = kv_layer(m, m->ckv, l, m->T); a.kv_half = m->kv_half ? 1 : 0; a.hm_rows_per_b = m->T; a.hm_cap = m->T; a.hm_H = m->H;
       MT3_TRY(gemm(m, a, s));
     }
   }
   MT3_CUDA_CHECK(cudaMemsetAsync(m->state, 0, 4 * sizeof(int), s));
-  MT3_CUDA_CHECK(cudaMemsetAsync(m->dcounters, 0, (size_t)4 * m->dcounters_stride * sizeof(int), s));
+  MT3_CUDA_CHECK(cudaMemsetAsync(m->dcounters, 0, (size_t)m->dcounters_n * sizeof(int), s));
   MT3_CUDA_CHECK(cudaMemsetAsync(m->finished, 0, (size_t)m->B * sizeof(int), s));
   MT3_CUDA_CHECK(cudaMemsetAsync(m->tok_cur, 0, (size_t)m->B * sizeof(int), s));
   m->have_cross = true;
@@ -391,10 +380,8 @@ static int cross_kv_impl(Model* m, const float* encoded, cudaStream_t s) {
   return MT3_OK;
 }
 
-// Decode-step GEMM on M = B rows: split-K exact-fp32 kernel with the RMSNorm statistic fused
-// (decode.cuh); batches above 64 rows run in 64-row blocks.
-// A contiguous block of sequences decoded on one stream (MT3_DEC_STREAMS sub-batches per step).
-struct Rows { int begin, count, stream_idx; };
+// A contiguous block of sequences decoded in one launch (batches above 64 rows run in 64-row blocks).
+struct Rows { int begin, count; };
 
 constexpr int kTraceSlots = 256, kTraceWords = 16;   // words 8..15: %smid of the 8 CTAs of tile 0's cluster
 static unsigned long long* trace_slot(Model* m, const char* name) {
@@ -403,22 +390,9 @@ static unsigned long long* trace_slot(Model* m, const char* name) {
   return m->trace + (size_t)(m->trace_names.size() - 1) * kTraceWords;
 }
 
-// TMA map of an [rows, K] fp32 operand (leading dimension ld), box 32 floats x box_rows; built once and cached.
-static int dec_tmap(Model* m, const float* ptr, int rows, int K, int ld, int box_rows, CUtensorMap* out) {
-  const auto key = std::make_tuple((const void*)ptr, rows, K, ld);
-  auto it = m->dec_maps.find(key);
-  if (it == m->dec_maps.end()) {
-    CUtensorMap tm;
-    MT3_TRY(make_tmap_2d(&tm, ptr, (uint64_t)rows, (uint64_t)K, (uint64_t)ld, (uint32_t)box_rows));
-    it = m->dec_maps.emplace(key, tm).first;
-  }
-  *out = it->second;
-  return MT3_OK;
-}
-
+// Decode-step GEMM on M = B rows: split-K exact-fp32 kernel with the RMSNorm statistic fused (decode.cuh).
 static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, int K, int norm, int epi, float* C, int ldc,
-                    int n_split, float* kv, const int* pos, const Rows& rows, cudaStream_t s) {
-  const int splits = dec_gemm_splits(N, K, m->sm_count);
+                    int n_split, char* kv, const int* pos, const Rows& rows, cudaStream_t s) {
   for (int r0 = rows.begin; r0 < rows.begin + rows.count; r0 += kDecBM) {
     DecGemmArgs a;
     memset(&a, 0, sizeof(a));
@@ -427,48 +401,48 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
     a.norm = norm; a.eps = 1e-6f; a.epi = epi;
     a.R = C + (int64_t)r0 * ldc; a.ldr = ldc;                  // residual is always added in place
     a.C = C + (int64_t)r0 * ldc; a.ldc = ldc; a.n_split = n_split;
-    if (kv) {  // rows_per_b = 1: skip r0 sequences, each 2*H*cap*64 floats
-      a.C1 = kv + (int64_t)r0 * 2 * m->H * m->L * 64; a.hm_rows_per_b = 1; a.hm_cap = m->L; a.hm_H = m->H; a.hm_pos = pos;
+    if (kv) {  // rows_per_b = 1: skip r0 sequences, each 2*H*cap*64 elements
+      a.C1 = kv + (int64_t)r0 * 2 * m->H * m->L * 64 * m->kv_elt; a.kv_half = m->kv_half ? 1 : 0;
+      a.hm_rows_per_b = 1; a.hm_cap = m->L; a.hm_H = m->H; a.hm_pos = pos;
     }
-    a.partial = m->dpartial + (int64_t)rows.stream_idx * m->dpartial_stride;      // per-stream split-K scratch
-    a.counters = m->dcounters + (int64_t)rows.stream_idx * m->dcounters_stride;
+    a.partial = m->dpartial;
+    a.counters = m->dcounters;
     a.trace = trace_slot(m, K == m->F ? "gemm_mlp_out" : (N == 2 * m->F ? "gemm_mlp_in" : (kv ? "gemm_qkv_append" : (N == m->V ? "gemm_logits" : (K == m->Q ? "gemm_attn_out" : "gemm_cross_q")))));
     int rc = MT3_ERR_UNSUPPORTED;
-    if (m->dec_cluster && m->dec_gemm_mode >= 1 && m->dec_tc && dec_gemm_tc_supported(a)) {
-      const auto wt = m->dec_wt.find(W);
-      if (wt != m->dec_wt.end()) {
-        DecTcMaps maps;
-        MT3_TRY(dec_tmap(m, a.A, a.M, K, lda, kDecBM, &maps.a));
-        MT3_TRY(dec_tmap(m, wt->second, N, K, K, kDecBN, &maps.b));
-        rc = launch_dec_gemm_tc(maps, a, m->dec_gemm_mode, s, m->pdl_gemm);
-      }
-    }
-    if (rc == MT3_ERR_UNSUPPORTED && m->dec_cluster) rc = launch_dec_gemm_cluster(a, m->dec_gemm_mode, s, m->pdl_gemm);
-    if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, splits, s, m->pdl_gemm);   // shapes the cluster kernel does not tile
+    if (m->dec_cluster) rc = launch_dec_gemm_cluster(a, m->dec_opts, s, m->pdl_gemm);
+    if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, s, m->pdl_gemm);   // shapes the cluster kernel does not tile
     MT3_TRY(rc);
   }
   return MT3_OK;
 }
 
-static int launch_dec_attention(Model* m, const float* q, const float* kv, int cap, const int* len_ptr, int len_add,
-                                float* out, const Rows& rows, cudaStream_t s, const float* q_ssq = nullptr) {
+template <bool HALF>
+static int launch_dec_attention_t(Model* m, const float* q, const char* kv, int cap, const int* len_ptr, int len_add,
+                                  float* out, const Rows& rows, cudaStream_t s, const float* q_ssq, size_t smem, int max_len) {
   static bool attr_done = false;
-  const int max_len = std::max(m->L, m->T);
-  const size_t smem = dec_attention_smem(max_len);
   if (!attr_done) {
-    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel<HALF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel<HALF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
-  MT3_REQUIRE(smem <= 100 * 1024, MT3_ERR_UNSUPPORTED, "decode attention: length %d too long", max_len);
-  MT3_CUDA_CHECK(launch_kernel(m->tracing ? dec_attention_bulk_kernel<true> : dec_attention_bulk_kernel<false>, dim3(m->H, rows.count),
-                               dim3(kAttThreads), smem, s, m->pdl_attn,
-                               q + (int64_t)rows.begin * m->Q, m->Q, 0, kv + (int64_t)rows.begin * 2 * m->H * cap * 64, m->H, cap,
+  MT3_CUDA_CHECK(launch_kernel(m->tracing ? dec_attention_bulk_kernel<HALF, true> : dec_attention_bulk_kernel<HALF, false>,
+                               dim3(m->H, rows.count), dim3(kAttThreads), smem, s, m->pdl_attn,
+                               q + (int64_t)rows.begin * m->Q, m->Q, 0,
+                               (const void*)(kv + (int64_t)rows.begin * 2 * m->H * cap * 64 * m->kv_elt), m->H, cap,
                                len_ptr, len_add, max_len, out + (int64_t)rows.begin * m->Q, m->Q,
                                q_ssq ? q_ssq + (int64_t)rows.begin * (m->D / 32) : (const float*)nullptr, m->D / 32, m->D / 32,
                                (float)m->D, 1e-6f, trace_slot(m, len_ptr ? "attn_self" : "attn_cross")));
   MT3_LAUNCH_CHECK();
   return MT3_OK;
+}
+
+static int launch_dec_attention(Model* m, const float* q, const char* kv, int cap, const int* len_ptr, int len_add,
+                                float* out, const Rows& rows, cudaStream_t s, const float* q_ssq = nullptr) {
+  const int max_len = std::max(m->L, m->T);
+  const size_t smem = dec_attention_smem(max_len);
+  MT3_REQUIRE(smem <= 100 * 1024, MT3_ERR_UNSUPPORTED, "decode attention: length %d too long", max_len);
+  return m->kv_half ? launch_dec_attention_t<true>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len)
+                    : launch_dec_attention_t<false>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len);
 }
 
 // y_out = y_in + o.Wo  and  q_raw = [o | y_in].[Wo.Wq ; Wq]  in ONE launch; the RMSNorm factor of y_out is applied to
@@ -489,36 +463,33 @@ static int dec_gemm_out_q(Model* m, const DecLayer& w, const float* y_in, float*
   a1.eps = 1e-6f; a1.epi = EPI_STORE; a1.C = m->dq + r0 * Q; a1.ldc = Q; a1.n_split = Q;
   a1.R = a1.C; a1.ldr = Q;
   a1.trace = a0.trace;
-  return launch_dec_gemm_out_q(a0, a1, m->dec_gemm_mode, s, m->pdl_gemm);
+  return launch_dec_gemm_out_q(a0, a1, m->dec_opts, s, m->pdl_gemm);
 }
 
-constexpr int kHbmEvents = 64;
-
-// A block of sequences walking through the step on its own stream.
+// The residual stream of one step (ping-pongs between m->dy and m->dy2 across fused launches).
 struct DecBranch { Rows rows; cudaStream_t s; float* y; int fused; };
 
 static int dec_embed(Model* m, DecBranch& b, const int* tok_in) {
   MT3_CUDA_CHECK(launch_kernel(embed_kernel, dim3(b.rows.count), dim3(128), 0, b.s, m->pdl, tok_in, (const float*)m->emb, m->D, m->V,
                                (const float*)m->pe, (const int*)m->state, m->dy, b.rows.begin));
   MT3_LAUNCH_CHECK();
-  b.y = m->dy;                      // residual stream of the step (ping-pongs with m->dy2 across fused launches)
+  b.y = m->dy;
   return MT3_OK;
 }
 // fused RMSNorm + QKV projection + K/V cache append (layers.py:238-240, :272-289)
 static int dec_layer_qkv(Model* m, DecBranch& b, int l) {
-  float* skv = m->skv + (int64_t)l * m->B * m->L * 2 * m->Q;
-  return dec_gemm(m, b.y, m->D, m->dec[l].wqkv, 3 * m->Q, m->D, 1, EPI_STORE, m->dq, m->Q, m->Q, skv, m->state, b.rows, b.s);
+  return dec_gemm(m, b.y, m->D, m->dec[l].wqkv, 3 * m->Q, m->D, 1, EPI_STORE, m->dq, m->Q, m->Q, kv_layer(m, m->skv, l, m->L), m->state,
+                  b.rows, b.s);
 }
 static int dec_layer_self(Model* m, DecBranch& b, int l) {
-  float* skv = m->skv + (int64_t)l * m->B * m->L * 2 * m->Q;
-  return launch_dec_attention(m, m->dq, skv, m->L, m->state, 1, m->dao, b.rows, b.s);
+  return launch_dec_attention(m, m->dq, kv_layer(m, m->skv, l, m->L), m->L, m->state, 1, m->dao, b.rows, b.s);
 }
 // self-attention out-projection + residual, cross-attention query projection (one launch when fused)
 static int dec_layer_outq(Model* m, DecBranch& b, int l) {
   const DecLayer& w = m->dec[l];
   const int D = m->D, Q = m->Q;
   b.fused = MT3_ERR_UNSUPPORTED;
-  if (m->fuse_q && m->dec_cluster && !(m->dec_gemm_mode >= 1 && m->dec_tc && m->slab_dect)) {
+  if (m->fuse_q && m->dec_cluster) {
     float* y_next = (b.y == m->dy) ? m->dy2 : m->dy;    // the fused launch reads y while other CTAs write y': ping-pong
     b.fused = dec_gemm_out_q(m, w, b.y, y_next, b.rows, b.s);
     if (b.fused == MT3_OK) b.y = y_next;
@@ -531,8 +502,8 @@ static int dec_layer_outq(Model* m, DecBranch& b, int l) {
   return MT3_OK;
 }
 static int dec_layer_cross(Model* m, DecBranch& b, int l) {
-  const float* ckv = m->ckv + (int64_t)l * m->B * m->T * 2 * m->Q;
-  return launch_dec_attention(m, m->dq, ckv, m->T, nullptr, m->T, m->dao, b.rows, b.s, b.fused == MT3_OK ? m->dssq : nullptr);
+  return launch_dec_attention(m, m->dq, kv_layer(m, m->ckv, l, m->T), m->T, nullptr, m->T, m->dao, b.rows, b.s,
+                              b.fused == MT3_OK ? m->dssq : nullptr);
 }
 static int dec_layer_mlp(Model* m, DecBranch& b, int l) {
   const DecLayer& w = m->dec[l];
@@ -542,25 +513,14 @@ static int dec_layer_mlp(Model* m, DecBranch& b, int l) {
   MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s));
   return MT3_OK;
 }
-static int dec_logits_argmax(Model* m, DecBranch& b, float* logits, int greedy, int* tok_user, int use_finished, int* tokens_ws) {
-  MT3_TRY(dec_gemm(m, b.y, m->D, m->w_logits, m->V, m->D, 1, EPI_STORE, logits, m->V, m->V, nullptr, nullptr, b.rows, b.s));
-  if (greedy) {
-    // B (whole batch) sizes the arrival counter: the LAST CTA over all sub-batches advances the position
-    MT3_CUDA_CHECK(launch_kernel(argmax_step_kernel, dim3(b.rows.count), dim3(256), 0, b.s, m->pdl, (const float*)logits, m->V, m->B,
-                                 use_finished ? m->tok_cur : (int*)nullptr, use_finished ? m->finished : (int*)nullptr,
-                                 tokens_ws, m->L, tok_user, m->state, 1, b.rows.begin));
-    MT3_LAUNCH_CHECK();
-  }
-  return MT3_OK;
-}
 
-// One decode step (network.py:303-361 -> :196-262 -> :88-155) for one block of sequences.  tok_in DEV [B]; logits
+// One decode step (network.py:303-361 -> :196-262 -> :88-155) for the whole batch.  tok_in DEV [B]; logits
 // DEV [B,V]; greedy != 0 runs the argmax/bookkeeping kernel (tok_user optional), else only the position advances.
 // 7 launches per layer: [norm+QKV+KV-append] [self-attn] [out+residual | norm+q] [cross-attn] [out+residual]
 // [norm+gated-GELU MLP in] [MLP out+residual].
-static int decode_rows(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
-                       int* tokens_ws, const Rows& rows, cudaStream_t s) {
-  DecBranch b{rows, s, nullptr, MT3_ERR_UNSUPPORTED};
+static int decode_step_impl(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
+                            int* tokens_ws, cudaStream_t s) {
+  DecBranch b{Rows{0, m->B}, s, nullptr, MT3_ERR_UNSUPPORTED};
   MT3_TRY(dec_embed(m, b, tok_in));
   for (int l = 0; l < m->Ld; ++l) {
     MT3_TRY(dec_layer_qkv(m, b, l));
@@ -569,320 +529,16 @@ static int decode_rows(Model* m, const int* tok_in, float* logits, int greedy, i
     MT3_TRY(dec_layer_cross(m, b, l));
     MT3_TRY(dec_layer_mlp(m, b, l));
   }
-  return dec_logits_argmax(m, b, logits, greedy, tok_user, use_finished, tokens_ws);
-}
-
-// The same step for n blocks of sequences on n streams with the bandwidth-bound nodes SERIALISED across the blocks:
-// the attention kernels run one after the other in the fixed order  self(b0,l) self(b1,l) .. cross(b0,l) cross(b1,l) ..
-// (cross-stream events; captured as cross-branch edges of the step graph), so a block's attention never shares HBM
-// with another block's attention and always overlaps the other blocks' latency-bound GEMM chains.  (Plain forked
-// branches run in lockstep -- attention over attention, GEMM over GEMM -- and gain nothing: profiles/r01_call15.)
-static int decode_step_interleaved(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
-                                   int* tokens_ws, cudaStream_t s, int n) {
-  const int B = m->B;
-  DecBranch br[4];
-  const int per = (B + n - 1) / n;
-  MT3_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
-  for (int i = 0; i < n; ++i) {
-    const int b0 = i * per, cnt = std::min(per, B - b0);
-    br[i] = DecBranch{Rows{b0, cnt, i}, i == 0 ? s : m->sub_stream[i], nullptr, MT3_ERR_UNSUPPORTED};
-    if (i > 0) MT3_CUDA_CHECK(cudaStreamWaitEvent(br[i].s, m->ev_fork, 0));
-    MT3_TRY(dec_embed(m, br[i], tok_in));
-  }
-  cudaEvent_t prev = nullptr;       // completion of the previous bandwidth-bound node in the global order
-  int prev_branch = -1, ev_next = 0;
-  auto hbm_node = [&](int i, int l, bool self) -> int {
-    if (prev && prev_branch != i) MT3_CUDA_CHECK(cudaStreamWaitEvent(br[i].s, prev, 0));
-    MT3_TRY(self ? dec_layer_self(m, br[i], l) : dec_layer_cross(m, br[i], l));
-    cudaEvent_t e = m->ev_hbm[ev_next++ % kHbmEvents];
-    MT3_CUDA_CHECK(cudaEventRecord(e, br[i].s));
-    prev = e;
-    prev_branch = i;
-    return MT3_OK;
-  };
-  for (int l = 0; l < m->Ld; ++l) {
-    for (int i = 0; i < n; ++i) MT3_TRY(dec_layer_qkv(m, br[i], l));
-    for (int i = 0; i < n; ++i) {
-      MT3_TRY(hbm_node(i, l, true));
-      MT3_TRY(dec_layer_outq(m, br[i], l));
-    }
-    for (int i = 0; i < n; ++i) {
-      MT3_TRY(hbm_node(i, l, false));
-      MT3_TRY(dec_layer_mlp(m, br[i], l));
-    }
-  }
-  for (int i = 0; i < n; ++i) {
-    MT3_TRY(dec_logits_argmax(m, br[i], logits, greedy, tok_user, use_finished, tokens_ws));
-    if (i > 0) {
-      MT3_CUDA_CHECK(cudaEventRecord(m->ev_join[i], br[i].s));
-      MT3_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join[i], 0));
-    }
-  }
-  return MT3_OK;
-}
-
-static int decode_step_chain(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
-                             int* tokens_ws, cudaStream_t s);
-
-// One decode step for the whole batch.  With MT3_DEC_STREAMS = n > 1 the batch is cut into n blocks of
-// sequences that run on n streams (forked/joined with events; captured as parallel branches of the step
-// graph): one block's latency-bound GEMM chain overlaps another block's bandwidth-bound attention.
-static int ensure_sub_streams(Model* m) {
-  if (m->ev_fork) return MT3_OK;
-  MT3_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
-  for (int i = 0; i < 4; ++i) {
-    MT3_CUDA_CHECK(cudaStreamCreateWithFlags(&m->sub_stream[i], cudaStreamNonBlocking));
-    MT3_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_join[i], cudaEventDisableTiming));
-  }
-  for (int i = 0; i < kHbmEvents; ++i) MT3_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_hbm[i], cudaEventDisableTiming));
-  return MT3_OK;
-}
-
-static int decode_step_impl(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
-                            int* tokens_ws, cudaStream_t s) {
-  const int B = m->B;
-  if (m->interleave > 1 && !(m->chain && m->chain_cluster)) {
-    int n = std::min(m->interleave, 4);
-    while (n > 1 && (B / n < 8 || n * m->Ld * 2 > kHbmEvents)) --n;
-    if (n > 1) {
-      MT3_TRY(ensure_sub_streams(m));
-      MT3_TRY(decode_step_interleaved(m, tok_in, logits, greedy, tok_user, use_finished, tokens_ws, s, n));
-      if (!greedy) {
-        MT3_CUDA_CHECK(launch_kernel(advance_pos_kernel, dim3(1), dim3(1), 0, s, m->pdl, m->state));
-        MT3_LAUNCH_CHECK();
-      }
-      return MT3_OK;
-    }
-  }
-  if (m->chain && m->chain_cluster)
-    return decode_step_chain(m, tok_in, logits, greedy, tok_user, use_finished, tokens_ws, s);
-  int ns = std::max(1, std::min(m->dec_streams, 4));
-  while (ns > 1 && B / ns < 8) --ns;
-  if (ns == 1) {
-    MT3_TRY(decode_rows(m, tok_in, logits, greedy, tok_user, use_finished, tokens_ws, Rows{0, B, 0}, s));
-  } else {
-    MT3_TRY(ensure_sub_streams(m));
-    MT3_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
-    const int per = (B + ns - 1) / ns;
-    for (int i = 0; i < ns; ++i) {
-      const int b0 = i * per, n = std::min(per, B - b0);
-      if (n <= 0) break;
-      cudaStream_t si = (i == 0) ? s : m->sub_stream[i];
-      if (i > 0) MT3_CUDA_CHECK(cudaStreamWaitEvent(si, m->ev_fork, 0));
-      MT3_TRY(decode_rows(m, tok_in, logits, greedy, tok_user, use_finished, tokens_ws, Rows{b0, n, i}, si));
-      if (i > 0) {
-        MT3_CUDA_CHECK(cudaEventRecord(m->ev_join[i], si));
-        MT3_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join[i], 0));
-      }
-    }
-  }
-  if (!greedy) {
-    MT3_CUDA_CHECK(launch_kernel(advance_pos_kernel, dim3(1), dim3(1), 0, s, m->pdl, m->state));
-    MT3_LAUNCH_CHECK();
-  }
-  return MT3_OK;
-}
-
-// ---- decode step with cluster-local GEMM chains (decode_chain.cuh): 35 launches instead of 67 -------------
-static ChainStage chain_stage(Model* m, const float* A, int lda, int K, const float* W, int N, int norm, int epi, float* C,
-                              int ldc, int n_split, float* kv) {
-  ChainStage s;
-  memset(&s, 0, sizeof(s));
-  s.A = A; s.lda = lda; s.K = K; s.W = W; s.N = N; s.norm = norm; s.epi = epi; s.C = C; s.ldc = ldc; s.n_split = n_split;
-  if (kv) { s.kv = kv; s.kv_cap = m->L; s.kv_H = m->H; s.kv_pos = m->state; }
-  return s;
-}
-
-static bool chain_supported(const Model* m, int cl) {
-  const int ns[] = {3 * m->Q, m->D, m->Q, 2 * m->F, m->V};
-  for (int n : ns)
-    if (n % (cl * 8) != 0 || n / cl > kChMaxNc) return false;
-  return m->D % 4 == 0 && m->F % 4 == 0 && m->Q % 4 == 0 && std::max(std::max(m->D, m->F), m->Q) <= kChMaxK;
-}
-
-static int launch_chain(Model* m, const ChainArgs& a, cudaStream_t s) {
-  const int cl = m->chain_cluster;
-  const int n_clusters = cdiv(m->B, kChRows);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(n_clusters * cl); cfg.blockDim = dim3(kChThreads); cfg.dynamicSmemBytes = chain_smem_bytes(); cfg.stream = s;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = m->pdl ? 2 : 1;
-  MT3_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dec_chain_kernel, a));
-  MT3_LAUNCH_CHECK();
-  return MT3_OK;
-}
-
-static int chain_setup(Model* m) {
-  if (m->chain_cluster) return MT3_OK;
-  MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain_smem_bytes()));
-  MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_chain_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  for (int cl : {16, 8}) {
-    if (!chain_supported(m, cl)) continue;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(cl); cfg.blockDim = dim3(kChThreads); cfg.dynamicSmemBytes = chain_smem_bytes();
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, dec_chain_kernel, &cfg) == cudaSuccess && n >= 1) {
-      m->chain_cluster = cl;
-      return MT3_OK;
-    }
-    cudaGetLastError();
-  }
-  return fail(MT3_ERR_UNSUPPORTED, "no cluster size (16, 8) fits the GEMM-chain kernel for this model");
-}
-
-// greedy step, whole batch: embed | chain{QKV0} | 8 x [self-attn | chain A | cross-attn | chain B] | argmax
-static int decode_step_chain(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
-                             int* tokens_ws, cudaStream_t s) {
-  const int B = m->B, D = m->D, Q = m->Q, F = m->F, V = m->V, L = m->L, T = m->T;
-  int* pos = m->state;
-  const Rows all{0, B, 0};
-  MT3_CUDA_CHECK(launch_kernel(embed_kernel, dim3(B), dim3(128), 0, s, m->pdl, tok_in, (const float*)m->emb, D, V,
-                               (const float*)m->pe, (const int*)pos, m->dy, 0));
-  MT3_LAUNCH_CHECK();
-  ChainArgs c0;
-  memset(&c0, 0, sizeof(c0));
-  c0.B = B; c0.eps = 1e-6f; c0.n_stages = 1;
-  c0.st[0] = chain_stage(m, m->dy, D, D, m->dec[0].wqkv, 3 * Q, 1, EPI_STORE, m->dq, Q, Q, m->skv);
-  MT3_TRY(launch_chain(m, c0, s));
-  for (int l = 0; l < m->Ld; ++l) {
-    const DecLayer& w = m->dec[l];
-    float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
-    const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
-    MT3_TRY(launch_dec_attention(m, m->dq, skv, L, pos, 1, m->dao, all, s));
-    ChainArgs ca;
-    memset(&ca, 0, sizeof(ca));
-    ca.B = B; ca.eps = 1e-6f; ca.n_stages = 2;
-    ca.st[0] = chain_stage(m, m->dao, Q, Q, w.wo, D, 0, EPI_RESIDUAL, m->dy, D, D, nullptr);
-    ca.st[1] = chain_stage(m, m->dy, D, D, w.wq_c, Q, 1, EPI_STORE, m->dq, Q, Q, nullptr);
-    MT3_TRY(launch_chain(m, ca, s));
-    MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, all, s));
-    ChainArgs cb;
-    memset(&cb, 0, sizeof(cb));
-    cb.B = B; cb.eps = 1e-6f; cb.n_stages = 4;
-    cb.st[0] = chain_stage(m, m->dao, Q, Q, w.wo_c, D, 0, EPI_RESIDUAL, m->dy, D, D, nullptr);
-    cb.st[1] = chain_stage(m, m->dy, D, D, w.wi, 2 * F, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr);
-    cb.st[2] = chain_stage(m, m->dg, F, F, w.wo2, D, 0, EPI_RESIDUAL, m->dy, D, D, nullptr);
-    if (l + 1 < m->Ld)
-      cb.st[3] = chain_stage(m, m->dy, D, D, m->dec[l + 1].wqkv, 3 * Q, 1, EPI_STORE, m->dq, Q, Q,
-                             m->skv + (int64_t)(l + 1) * B * L * 2 * Q);
-    else
-      cb.st[3] = chain_stage(m, m->dy, D, D, m->w_logits, V, 1, EPI_STORE, logits, V, V, nullptr);
-    MT3_TRY(launch_chain(m, cb, s));
-  }
+  MT3_TRY(dec_gemm(m, b.y, m->D, m->w_logits, m->V, m->D, 1, EPI_STORE, logits, m->V, m->V, nullptr, nullptr, b.rows, s));
   if (greedy) {
-    MT3_CUDA_CHECK(launch_kernel(argmax_step_kernel, dim3(B), dim3(256), 0, s, m->pdl, (const float*)logits, V, B,
+    MT3_CUDA_CHECK(launch_kernel(argmax_step_kernel, dim3(m->B), dim3(256), 0, s, m->pdl, (const float*)logits, m->V, m->B,
                                  use_finished ? m->tok_cur : (int*)nullptr, use_finished ? m->finished : (int*)nullptr,
-                                 tokens_ws, L, tok_user, m->state, 1, 0));
+                                 tokens_ws, m->L, tok_user, m->state, 1, 0));
     MT3_LAUNCH_CHECK();
   } else {
     MT3_CUDA_CHECK(launch_kernel(advance_pos_kernel, dim3(1), dim3(1), 0, s, m->pdl, m->state));
     MT3_LAUNCH_CHECK();
   }
-  return MT3_OK;
-}
-
-// ---- the decode step as one persistent kernel (decode_mega.cuh); generate path, B <= 64 ------------------
-static DecGemmArgs mega_gemm_args(Model* m, const float* A, int lda, const float* W, int N, int K, int norm, int epi,
-                                  float* C, int ldc, int n_split, float* kv) {
-  DecGemmArgs a;
-  memset(&a, 0, sizeof(a));
-  a.A = A; a.lda = lda; a.W = W; a.ldw = N; a.M = m->B; a.N = N; a.K = K; a.norm = norm; a.eps = 1e-6f; a.epi = epi;
-  a.R = C; a.ldr = ldc; a.C = C; a.ldc = ldc; a.n_split = n_split;
-  if (kv) { a.C1 = kv; a.hm_rows_per_b = 1; a.hm_cap = m->L; a.hm_H = m->H; a.hm_pos = m->state; }
-  return a;
-}
-
-static bool mega_supported(const Model* m) {
-  auto kc_ok = [](int K) { return K % 8 == 0 && (K / 8 == 48 || K / 8 == 64 || K / 8 == 128); };
-  return m->B <= kDecBM && kc_ok(m->D) && kc_ok(m->Q) && kc_ok(m->F);
-}
-
-static int build_mega_program(Model* m) {
-  std::vector<MegaPhase> prog;
-  auto gemm_phase = [&](const DecGemmArgs& g) {
-    MegaPhase p;
-    memset(&p, 0, sizeof(p));
-    p.type = PH_GEMM; p.g = g; p.kc = g.K / 8;
-    prog.push_back(p);
-  };
-  auto attn_phase = [&](const float* kv, int cap, const int* len_ptr, int len_add) {
-    MegaPhase p;
-    memset(&p, 0, sizeof(p));
-    p.type = PH_ATTN; p.q = m->dq; p.kv = kv; p.cap = cap; p.len_ptr = len_ptr; p.len_add = len_add; p.out = m->dao;
-    prog.push_back(p);
-  };
-  const int B = m->B, D = m->D, Q = m->Q, F = m->F, V = m->V, L = m->L, T = m->T;
-  MegaPhase e;
-  memset(&e, 0, sizeof(e));
-  e.type = PH_EMBED;
-  prog.push_back(e);
-  for (int l = 0; l < m->Ld; ++l) {
-    const DecLayer& w = m->dec[l];
-    float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
-    const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
-    gemm_phase(mega_gemm_args(m, m->dy, D, w.wqkv, 3 * Q, D, 1, EPI_STORE, m->dq, Q, Q, skv));
-    attn_phase(skv, L, m->state, 1);
-    gemm_phase(mega_gemm_args(m, m->dao, Q, w.wo, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr));
-    gemm_phase(mega_gemm_args(m, m->dy, D, w.wq_c, Q, D, 1, EPI_STORE, m->dq, Q, Q, nullptr));
-    attn_phase(ckv, T, nullptr, T);
-    gemm_phase(mega_gemm_args(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, m->dy, D, D, nullptr));
-    gemm_phase(mega_gemm_args(m, m->dy, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr));
-    gemm_phase(mega_gemm_args(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, m->dy, D, D, nullptr));
-  }
-  gemm_phase(mega_gemm_args(m, m->dy, D, m->w_logits, V, D, 1, EPI_STORE, m->dlogits, V, V, nullptr));
-  e.type = PH_ARGMAX;
-  prog.push_back(e);
-  MT3_REQUIRE((int64_t)prog.size() * (int64_t)sizeof(MegaPhase) <= m->mega_prog_bytes, MT3_ERR_WORKSPACE,
-              "mega program (%zu phases) does not fit its workspace slot", prog.size());
-  MT3_CUDA_CHECK(cudaMemcpy(m->mega_prog, prog.data(), prog.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
-  MT3_CUDA_CHECK(cudaMemset(m->mega_bar, 0, 64));
-  m->mega_phases = (int)prog.size();
-  // co-resident clusters of 8 CTAs: the grid barrier needs every CTA on an SM at the same time
-  const size_t smem = mega_smem_bytes(std::max(L, T));
-  MT3_CUDA_CHECK(cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(8 * 64); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = smem;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  int max_clusters = 0;
-  MT3_CUDA_CHECK(cudaOccupancyMaxActiveClusters(&max_clusters, decode_mega_kernel, &cfg));
-  m->mega_clusters = std::min(64, max_clusters - 2);      // two clusters of slack
-  MT3_REQUIRE(m->mega_clusters >= 16, MT3_ERR_UNSUPPORTED, "only %d co-resident clusters for the persistent decode kernel",
-              max_clusters);
-  return MT3_OK;
-}
-
-static int decode_step_mega(Model* m, cudaStream_t s) {
-  MegaArgs a;
-  memset(&a, 0, sizeof(a));
-  a.prog = m->mega_prog; a.n_phases = m->mega_phases; a.bar = m->mega_bar;
-  a.B = m->B; a.H = m->H; a.Q = m->Q; a.D = m->D; a.V = m->V; a.L = m->L; a.max_len = std::max(m->L, m->T);
-  a.tok_in = m->tok_cur; a.emb = m->emb; a.pe = m->pe; a.y = m->dy;
-  a.logits = m->dlogits; a.tok_cur = m->tok_cur; a.finished = m->finished; a.tokens_out = m->tokens; a.tok_user = nullptr;
-  a.state = m->state; a.greedy = 1;
-  const size_t smem = mega_smem_bytes(a.max_len);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(8 * m->mega_clusters); cfg.blockDim = dim3(kMegaThreads); cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 8; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  MT3_CUDA_CHECK(cudaLaunchKernelEx(&cfg, decode_mega_kernel, a));
-  MT3_LAUNCH_CHECK();
   return MT3_OK;
 }
 
@@ -898,8 +554,7 @@ static int ensure_graph(Model* m) {
   if (!m->cap_stream) MT3_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
   const uint64_t before = g_launch_count.load();
   MT3_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-  int r = (m->mega && m->mega_ready) ? decode_step_mega(m, m->cap_stream)
-                                      : decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, m->cap_stream);
+  int r = decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, m->cap_stream);
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
   if (r != MT3_OK) {
@@ -946,6 +601,8 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
               "mt3_model_create: lengths above FixedEmbed.max_length=2048 (layers.py:565)");
   MT3_REQUIRE(cfg->gemm_mode == MT3_GEMM_FP32_SIMT || cfg->gemm_mode == MT3_GEMM_TF32X3 || cfg->gemm_mode == MT3_GEMM_TF32,
               MT3_ERR_BAD_ARG, "mt3_model_create: unknown gemm_mode %d", cfg->gemm_mode);
+  MT3_REQUIRE(cfg->kv_cache_format == MT3_KV_F32 || cfg->kv_cache_format == MT3_KV_F16, MT3_ERR_BAD_ARG,
+              "mt3_model_create: unknown kv_cache_format %d", cfg->kv_cache_format);
   if (cfg->gemm_mode != MT3_GEMM_FP32_SIMT)
     MT3_REQUIRE(cfg->emb_dim % 32 == 0 && cfg->mlp_dim % 32 == 0 && cfg->input_depth % 32 == 0, MT3_ERR_UNSUPPORTED,
                 "mt3_model_create: the tcgen05 path needs emb/mlp/input dims that are multiples of 32");
@@ -1054,26 +711,19 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     m->pdl = (pdl_bits & 1) != 0;
     m->pdl_attn = (pdl_bits & 3) != 0;
     m->pdl_gemm = (pdl_bits & 5) != 0;
-    const char* e_il = getenv("MT3_DEC_INTERLEAVE");
-    m->interleave = e_il ? atoi(e_il) : 0;
     const char* e_fuse = getenv("MT3_DEC_FUSE");
     m->fuse_q = !(e_fuse && e_fuse[0] == '0');
-    const char* e_chain = getenv("MT3_DEC_CHAIN");
-    m->chain = e_chain && e_chain[0] == '1';
-    const char* e_mega = getenv("MT3_DEC_MEGA");
-    m->mega = e_mega && e_mega[0] == '1';
-    const char* e_ns = getenv("MT3_DEC_STREAMS");
-    if (e_ns && e_ns[0] >= '1' && e_ns[0] <= '4') m->dec_streams = e_ns[0] - '0';
     const char* e_clu = getenv("MT3_DEC_CLUSTER");
     m->dec_cluster = !(e_clu && e_clu[0] == '0');
-    // The decode-step GEMMs are latency-bound (0.5 MFLOP per CTA): exact fp32 FMA is as fast as the tensor-core
-    // variants (measured: FMA 526, mma.sync 3xTF32 521, tcgen05 3xTF32 678 ms/step), so every gemm_mode decodes in
-    // exact fp32 unless MT3_DEC_GEMM_MODE asks for 1 (3xTF32) / 2 (1xTF32).
-    m->dec_gemm_mode = 0;
-    if (const char* e_dgm = getenv("MT3_DEC_GEMM_MODE")) m->dec_gemm_mode = std::max(0, std::min(2, atoi(e_dgm)));
+    const char* e_grp = getenv("MT3_DEC_GROUPS");
+    m->dec_opts.groups = (e_grp && e_grp[0] == '1') ? 1 : 2;
+    const char* e_c16 = getenv("MT3_DEC_CLUSTER16");
+    m->dec_opts.c16 = !(e_c16 && e_c16[0] == '0');
     const char* e_attn = getenv("MT3_TC_ATTENTION");
     m->tc_attn_ok = !(e_attn && e_attn[0] == '0');
   }
+  m->kv_half = cfg->kv_cache_format == MT3_KV_F16;
+  m->kv_elt = m->kv_half ? 2 : 4;
   m->tc = cfg->gemm_mode != MT3_GEMM_FP32_SIMT;
   m->split3 = cfg->gemm_mode == MT3_GEMM_TF32X3;
   if (rc == MT3_OK && m->tc) {
@@ -1096,33 +746,6 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
       if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: tc weight prep -> %s", cudaGetErrorString(e));
     }
   }
-  {
-    const char* e_dtc = getenv("MT3_DEC_TC");
-    m->dec_tc = !(e_dtc && e_dtc[0] == '0');
-  }
-  if (rc == MT3_OK && m->dec_gemm_mode >= 1 && m->dec_tc) {
-    // K-major copies of the decode-step weights for the tcgen05 decode GEMM (decode_tc.cuh)
-    const int64_t n_dect = (int64_t)m->Ld * ((int64_t)D * 3 * Q + (int64_t)Q * D + (int64_t)D * Q + (int64_t)Q * D + (int64_t)D * 2 * F + (int64_t)F * D) + (int64_t)D * V;
-    e = cudaMalloc((void**)&m->slab_dect, (size_t)n_dect * sizeof(float));
-    if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: cudaMalloc(decode W^T) -> %s", cudaGetErrorString(e));
-    float* cur = m->slab_dect;
-    auto tr = [&](const float* w, int K, int N) {
-      if (rc != MT3_OK) return;
-      transpose_split_kernel<<<dim3(cdiv(N, 32), cdiv(K, 32)), dim3(32, 8), 0, s>>>(w, K, N, cur, nullptr);
-      if (cudaGetLastError() != cudaSuccess) { rc = fail(MT3_ERR_CUDA, "mt3_model_create: decode W^T prep launch failed"); return; }
-      m->dec_wt[w] = cur;
-      cur += (int64_t)K * N;
-    };
-    for (int i = 0; i < m->Ld; ++i) {
-      const DecLayer& L = m->dec[i];
-      tr(L.wqkv, D, 3 * Q); tr(L.wo, Q, D); tr(L.wq_c, D, Q); tr(L.wo_c, Q, D); tr(L.wi, D, 2 * F); tr(L.wo2, F, D);
-    }
-    tr(m->w_logits, D, V);
-    if (rc == MT3_OK) {
-      e = cudaStreamSynchronize(s);
-      if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: decode W^T prep -> %s", cudaGetErrorString(e));
-    }
-  }
   if (rc == MT3_OK) {
     e = cudaMallocHost((void**)&m->h_flag, 4 * sizeof(int));
     if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: cudaMallocHost -> %s", cudaGetErrorString(e));
@@ -1130,7 +753,6 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
   if (rc != MT3_OK) {
     cudaFree(m->slab);
     cudaFree(m->slab_tc);
-    cudaFree(m->slab_dect);
     delete m;
     return rc;
   }
@@ -1143,17 +765,9 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
   Model* m = reinterpret_cast<Model*>(h);
   drop_graph(m);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
-  for (int i = 0; i < 4; ++i) {
-    if (m->sub_stream[i]) cudaStreamDestroy(m->sub_stream[i]);
-    if (m->ev_join[i]) cudaEventDestroy(m->ev_join[i]);
-  }
-  if (m->ev_fork) cudaEventDestroy(m->ev_fork);
-  for (int i = 0; i < kHbmEvents; ++i)
-    if (m->ev_hbm[i]) cudaEventDestroy(m->ev_hbm[i]);
   if (m->h_flag) cudaFreeHost(m->h_flag);
   cudaFree(m->slab);
   cudaFree(m->slab_tc);
-  cudaFree(m->slab_dect);
   delete m;
   return MT3_OK;
 }
@@ -1162,7 +776,7 @@ namespace {
 struct WsLayout {
   int64_t x_hi, x_lo, h_lo, ao_lo, g_lo, enc_hi, enc_lo, qkv_lo, vt_hi, vt_lo;
   int64_t dy2, dssq;
-  int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, mega_prog, mega_bar, total;
+  int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, total;
 };
 WsLayout ws_layout(const Model* m, int B, int T) {
   WsLayout w;
@@ -1186,8 +800,8 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   w.ao = take(M * Q * 4);
   w.g = take(M * F * 4);
   w.encoded = take(M * D * 4);
-  w.ckv = take((int64_t)m->Ld * M * 2 * Q * 4);
-  w.skv = take((int64_t)m->Ld * B * L * 2 * Q * 4);
+  w.ckv = take((int64_t)m->Ld * M * 2 * Q * m->kv_elt);
+  w.skv = take((int64_t)m->Ld * B * L * 2 * Q * m->kv_elt);
   w.dy = take((int64_t)B * D * 4);
   w.drstd = take((int64_t)B * 4);
   w.dy2 = take((int64_t)B * D * 4);
@@ -1200,10 +814,8 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   w.finished = take((int64_t)B * 4);
   w.tokens = take((int64_t)B * L * 4);
   w.state = take(64);
-  w.dpartial = take((int64_t)4 * 16 * cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * kDecTileFloats * 4);   // x4 decode streams
-  w.dcounters = take((int64_t)4 * cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * 4);
-  w.mega_prog = take((int64_t)(8 * m->Ld + 8) * (int64_t)sizeof(MegaPhase));
-  w.mega_bar = take(64);
+  w.dpartial = take((int64_t)16 * cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * kDecTileFloats * 4);   // up to 16 K chunks
+  w.dcounters = take((int64_t)cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * 4);
   w.total = off;
   return w;
 }
@@ -1227,17 +839,13 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
   char* b = (char*)workspace;
   m->ws = b; m->ws_bytes = bytes; m->B = batch; m->T = input_length;
   m->h = (float*)(b + w.h); m->rstd = (float*)(b + w.rstd); m->qkv = (float*)(b + w.qkv); m->ao = (float*)(b + w.ao);
-  m->g = (float*)(b + w.g); m->encoded = (float*)(b + w.encoded); m->ckv = (float*)(b + w.ckv); m->skv = (float*)(b + w.skv);
+  m->g = (float*)(b + w.g); m->encoded = (float*)(b + w.encoded); m->ckv = b + w.ckv; m->skv = b + w.skv;
   m->dy2 = (float*)(b + w.dy2); m->dssq = (float*)(b + w.dssq);
   m->dy = (float*)(b + w.dy); m->drstd = (float*)(b + w.drstd); m->dq = (float*)(b + w.dq); m->dao = (float*)(b + w.dao);
   m->dg = (float*)(b + w.dg); m->dlogits = (float*)(b + w.dlogits); m->tok_cur = (int*)(b + w.tok_cur);
   m->finished = (int*)(b + w.finished); m->tokens = (int*)(b + w.tokens); m->state = (int*)(b + w.state);
   m->dpartial = (float*)(b + w.dpartial); m->dcounters = (int*)(b + w.dcounters);
-  m->dcounters_stride = cdiv(std::max(std::max(3 * m->Q, 2 * m->F), m->V), kDecBN);
-  m->mega_prog = (MegaPhase*)(b + w.mega_prog); m->mega_prog_bytes = (int64_t)(8 * m->Ld + 8) * (int64_t)sizeof(MegaPhase);
-  m->mega_bar = (unsigned*)(b + w.mega_bar); m->mega_ready = false;
-  if (m->chain) MT3_TRY(chain_setup(m));
-  m->dpartial_stride = (int64_t)16 * m->dcounters_stride * kDecTileFloats;
+  m->dcounters_n = cdiv(std::max(std::max(3 * m->Q, 2 * m->F), m->V), kDecBN);
   m->have_cross = false;
   if (m->tc) {
     const int64_t M = (int64_t)batch * input_length;
@@ -1303,10 +911,6 @@ extern "C" int mt3_generate(mt3_model* h, const float* x, int32_t num_steps, int
   MT3_CUDA_CHECK(cudaMemsetAsync(m->tokens, 0, (size_t)m->B * m->L * sizeof(int), s));
   const bool use_graph = (flags & MT3_GEN_USE_GRAPH) != 0;
   const bool stop = (flags & MT3_GEN_STOP_AT_EOS) != 0;
-  if (m->mega && !m->mega_ready && mega_supported(m)) {
-    MT3_TRY(build_mega_program(m));
-    m->mega_ready = true;
-  }
   if (use_graph) MT3_TRY(ensure_graph(m));
   int ran = 0;
   for (int step = 0; step < num_steps; ++step) {
@@ -1314,8 +918,7 @@ extern "C" int mt3_generate(mt3_model* h, const float* x, int32_t num_steps, int
       MT3_CUDA_CHECK(cudaGraphLaunch(m->graph_exec, s));
       count_launch(m->graph_kernels);
     } else {
-      if (m->mega && m->mega_ready) MT3_TRY(decode_step_mega(m, s));
-      else MT3_TRY(decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, s));
+      MT3_TRY(decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, s));
     }
     ++ran;
     m->host_pos += 1;
@@ -1401,18 +1004,16 @@ extern "C" int mt3_debug_launch(mt3_model* h, int32_t kind, int32_t pos, int32_t
     const int l = it % m->Ld;
     switch (kind) {
       case MT3_K_DEC_SELF_ATTN: {
-        float* skv = m->skv + (int64_t)l * B * L * 2 * Q;
-        MT3_TRY(launch_dec_attention(m, m->dq, skv, L, nullptr, pos + 1, m->dao, Rows{0, B, 0}, s));
+        MT3_TRY(launch_dec_attention(m, m->dq, kv_layer(m, m->skv, l, L), L, nullptr, pos + 1, m->dao, Rows{0, B}, s));
         break;
       }
       case MT3_K_DEC_CROSS_ATTN: {
-        const float* ckv = m->ckv + (int64_t)l * B * T * 2 * Q;
-        MT3_TRY(launch_dec_attention(m, m->dq, ckv, T, nullptr, T, m->dao, Rows{0, B, 0}, s));
+        MT3_TRY(launch_dec_attention(m, m->dq, kv_layer(m, m->ckv, l, T), T, nullptr, T, m->dao, Rows{0, B}, s));
         break;
       }
       case MT3_K_DEC_QKV_GEMM: {
         // scratch output: the encoder qkv buffer (B*T rows >= B)
-        MT3_TRY(dec_gemm(m, m->dy, D, m->dec[l].wqkv, 3 * Q, D, 1, EPI_STORE, m->qkv, 3 * Q, 3 * Q, nullptr, nullptr, Rows{0, B, 0}, s));
+        MT3_TRY(dec_gemm(m, m->dy, D, m->dec[l].wqkv, 3 * Q, D, 1, EPI_STORE, m->qkv, 3 * Q, 3 * Q, nullptr, nullptr, Rows{0, B}, s));
         break;
       }
       case MT3_K_ENC_QKV_GEMM: {

@@ -31,7 +31,8 @@ class InferenceModel(object):
     """Wrapper of the B200 model for music transcription."""
 
     def __init__(self, checkpoint_path, model_type='mt3', *, device='cuda:0', batch_size: int = 8,
-                 gin_dir: Optional[str] = None, gemm_mode: int = _lib.GEMM_TF32X3, use_graph: bool = True):
+                 gin_dir: Optional[str] = None, gemm_mode: int = _lib.GEMM_TF32X3, use_graph: bool = True,
+                 kv_format: int = _lib.KV_F32):
         # Model Constants (notebook :175-185).
         if model_type == 'ismir2021':
             num_velocity_bins = 127
@@ -53,6 +54,7 @@ class InferenceModel(object):
         self.device = torch.device(device)
         self.use_graph = use_graph
         self._gemm_mode = gemm_mode
+        self._kv_format = kv_format
 
         # Build Codecs and Vocabularies (notebook :198-206).
         self.spectrogram_config = spectrograms.SpectrogramConfig()
@@ -102,7 +104,7 @@ class InferenceModel(object):
         model_config = self._model_config()
         return network.Transformer(model_config, params, device=self.device, max_batch=self.batch_size,
                                    max_input_length=self.inputs_length, max_decode_length=self.outputs_length,
-                                   gemm_mode=self._gemm_mode)
+                                   gemm_mode=self._gemm_mode, kv_format=self._kv_format)
 
     def restore_from_checkpoint(self, checkpoint_path):
         """Restore weights (notebook :247-262).  `checkpoint_path` is a .npz keyed by the Flax tree

@@ -39,7 +39,8 @@ class Transformer:
     """An encoder-decoder Transformer model (network.py:265-409), inference only."""
 
     def __init__(self, config: T5Config, params: Dict[str, np.ndarray], *, device="cuda:0", max_batch: int = 8,
-                 max_input_length: int = 256, max_decode_length: int = 1024, gemm_mode: int = _lib.GEMM_FP32_SIMT):
+                 max_input_length: int = 256, max_decode_length: int = 1024, gemm_mode: int = _lib.GEMM_FP32_SIMT,
+                 kv_format: int = _lib.KV_F32):
         if tuple(config.mlp_activations) != ('gelu', 'linear'):
             raise ValueError("only the gated-GELU MLP ('gelu','linear') of gin/model.gin:57 is built; got %r"
                              % (tuple(config.mlp_activations),))
@@ -56,7 +57,7 @@ class Transformer:
         self._cfg = _lib.ModelConfig(config.vocab_size, config.emb_dim, config.num_heads, config.head_dim,
                                      config.num_encoder_layers, config.num_decoder_layers, config.mlp_dim,
                                      config.input_depth, int(max_batch), int(max_input_length),
-                                     int(max_decode_length), int(gemm_mode))
+                                     int(max_decode_length), int(gemm_mode), int(kv_format))
         n = int(self._lib.mt3_model_num_params(C.byref(self._cfg)))
         if n != W.num_params(config):
             raise RuntimeError(f"parameter count mismatch: library {n}, host {W.num_params(config)}")

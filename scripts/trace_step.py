@@ -16,7 +16,8 @@ SM_GHZ = 1.965
 def main():
     B = int(os.environ.get("TRACE_B", "64"))
     dev = torch.device("cuda:0")
-    im = inference.InferenceModel("synthetic:0", "mt3", device=dev, batch_size=B)
+    kv = {"f32": _lib.KV_F32, "f16": _lib.KV_F16}[os.environ.get("TRACE_KV", "f16")]
+    im = inference.InferenceModel("synthetic:0", "mt3", device=dev, batch_size=B, kv_format=kv)
     rng = np.random.default_rng(0)
     audio = torch.from_numpy((0.1 * rng.standard_normal((B, 32768))).astype(np.float32))
     im.transcribe_segments(audio, num_steps=8, stop_at_eos=False)        # encoder state, cross K/V, warm

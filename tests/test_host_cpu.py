@@ -212,7 +212,7 @@ def test_abi_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/mt3_b200.h but not exported"
     assert set(_lib.EXPORTS) == declared
-    assert lib.mt3_abi_version() == 1
+    assert lib.mt3_abi_version() == 2
     assert isinstance(lib.mt3_kernel_launch_count(), int)
     # argument validation happens before any CUDA call -> testable without a GPU
     assert lib.mt3_frontend_create(None, None, None) == -1

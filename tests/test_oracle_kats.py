@@ -121,8 +121,33 @@ def test_mlp_relu_golden():
     np.testing.assert_allclose(out, expected, rtol=1e-6)
 
 
+# The reference's own vectors, literally (vocabularies_test.py:47-83): GenericTokenVocabulary(32[, extra_ids=4]),
+# i.e. 32 regular ids behind the 3 special ones.
+VOCAB_TEST_VECTORS = [
+    # (ids, decode_tf result) -- test_encode_decode :47-62
+    ([4, 5, 6], [1, 2, 3]),
+    # test_decode_invalid_ids :64-71
+    ([0, 2, 3, 4, 34, 35], [-2, -2, 0, 1, 31, -2]),
+    # test_decode_eos :73-83 (the TF form preserves the array length)
+    ([0, 2, 3, 4, 1, 0, 1, 0], [-2, -2, 0, 1, -1, -1, -1, -1]),
+]
+
+
+def test_vocab_decode_reference_vectors():
+    for ids, want in VOCAB_TEST_VECTORS:
+        np.testing.assert_array_equal(O.vocab_decode(np.array(ids), 32), want)
+    # the Python form of test_decode_eos truncates after the first EOS: [-2, -2, 0, 1, -1]
+    dec = O.vocab_decode(np.array([0, 2, 3, 4, 1, 0, 1, 0]), 32)
+    np.testing.assert_array_equal(dec[:int(np.argmax(dec == -1)) + 1], [-2, -2, 0, 1, -1])
+    from mt3_b200 import vocabularies
+    vocab = vocabularies.GenericTokenVocabulary(32, extra_ids=4)
+    assert list(vocab.encode([1, 2, 3])) == [4, 5, 6]
+    assert list(vocab.decode([0, 2, 3, 4, 34, 35])) == [-2, -2, 0, 1, 31, -2]
+    assert list(vocabularies.GenericTokenVocabulary(32).decode([0, 2, 3, 4, 1, 0, 1, 0])) == [-2, -2, 0, 1, -1]
+
+
 def test_vocab_decode_contract():
-    # vocabularies_test.py:47-83 (10 regular ids; 4 extra ids in the reference test)
+    # further cases in the spirit of vocabularies_test.py:47-83 (10 regular ids)
     n = 10
     np.testing.assert_array_equal(O.vocab_decode(np.array([3, 4, 5, 12]), n), [0, 1, 2, 9])
     # EOS is sticky: it and everything after -> -1
