@@ -482,10 +482,12 @@ sgemm_dec_cluster2_kernel(const DecGemmArgs p0, const DecGemmArgs p1, const int 
   else dec_cluster_body<KC1, TRACE, 8, G>(p1, (int)blockIdx.x - tiles0);
 }
 
-// Per-model launch options of the cluster GEMM (read from the environment at mt3_model_create):
-//   groups  MT3_DEC_GROUPS=1: one warp group per CTA (128 threads, the round-1 shape); default 2 (256 threads)
-//   c16     MT3_DEC_CLUSTER16=0: keep clusters of 8 for the long-K MLP-out projection; default clusters of 16
-struct DecGemmOpts { int groups = 2; bool c16 = true; };
+// One warp group (128 threads) per CTA.  The body is also written for G = 2 groups that split the CTA's K chunk once
+// more and are summed through shared memory; measured on a B200 that is slower (437.8 vs 429.1 ms per batch,
+// profiles/r02_call1_*): the multiply loop is bound by shared-memory bandwidth (8 LDS.128 per 64 FMAs with 4 x 4
+// register tiles), not by issue latency, so more warps only add the combine step.  For the same reason FFMA2 is not
+// faster than scalar FFMA here.
+constexpr int kDecGroups = 1;
 
 template <int KC0, int KC1, int G>
 inline int launch_dec_gemm_cluster2_g(const DecGemmArgs& a0, const DecGemmArgs& a1, cudaStream_t s, bool pdl) {
@@ -508,11 +510,10 @@ inline int launch_dec_gemm_cluster2_g(const DecGemmArgs& a0, const DecGemmArgs& 
 }
 
 // the mt3 shapes: K = 384 (out-projection) and K = 384 + 512 (precomposed query block)
-inline int launch_dec_gemm_out_q(const DecGemmArgs& a0, const DecGemmArgs& a1, const DecGemmOpts& o, cudaStream_t s, bool pdl) {
+inline int launch_dec_gemm_out_q(const DecGemmArgs& a0, const DecGemmArgs& a1, cudaStream_t s, bool pdl) {
   if (a0.M > kDecBM || a1.M > kDecBM || a0.K != 8 * 48 || a1.K != 8 * 112 || a0.N % kDecBN != 0 || a1.N % kDecBN != 0)
     return MT3_ERR_UNSUPPORTED;
-  return o.groups == 2 ? launch_dec_gemm_cluster2_g<48, 112, 2>(a0, a1, s, pdl)
-                                : launch_dec_gemm_cluster2_g<48, 112, 1>(a0, a1, s, pdl);
+  return launch_dec_gemm_cluster2_g<48, 112, kDecGroups>(a0, a1, s, pdl);
 }
 
 template <int KC, int S, int G>
@@ -537,10 +538,10 @@ inline int launch_dec_gemm_cluster_kc(const DecGemmArgs& a, cudaStream_t s, bool
 }
 
 template <int G>
-inline int launch_dec_gemm_cluster_g(const DecGemmArgs& a, bool c16, cudaStream_t s, bool pdl) {
+inline int launch_dec_gemm_cluster_g(const DecGemmArgs& a, cudaStream_t s, bool pdl) {
   // the long-K, narrow-N GEMM (MLP out: K = 1024, N = 512) has only N/32 x 8 = 128 CTAs at cluster size 8: a
   // cluster of 16 halves every CTA's K chunk and fills the machine
-  if (c16 && a.K == 1024 && a.epi != EPI_GATED_GELU && a.N <= 512) return launch_dec_gemm_cluster_kc<64, 16, G>(a, s, pdl);
+  if ( a.K == 1024 && a.epi != EPI_GATED_GELU && a.N <= 512) return launch_dec_gemm_cluster_kc<64, 16, G>(a, s, pdl);
   switch (a.K / 8) {
     case 48: return launch_dec_gemm_cluster_kc<48, 8, G>(a, s, pdl);
     case 64: return launch_dec_gemm_cluster_kc<64, 8, G>(a, s, pdl);
@@ -550,9 +551,9 @@ inline int launch_dec_gemm_cluster_g(const DecGemmArgs& a, bool c16, cudaStream_
 }
 
 // Returns MT3_ERR_UNSUPPORTED (without launching) when K does not split into 8 chunks of 48/64/128.
-inline int launch_dec_gemm_cluster(const DecGemmArgs& a, const DecGemmOpts& o, cudaStream_t s, bool pdl) {
+inline int launch_dec_gemm_cluster(const DecGemmArgs& a, cudaStream_t s, bool pdl) {
   if (a.M > kDecBM || a.N % 4 != 0 || a.lda % 4 != 0 || a.ldw % 4 != 0 || a.n_split % 4 != 0 || a.K % 8 != 0) return MT3_ERR_UNSUPPORTED;
-  return o.groups == 2 ? launch_dec_gemm_cluster_g<2>(a, o.c16, s, pdl) : launch_dec_gemm_cluster_g<1>(a, o.c16, s, pdl);
+  return launch_dec_gemm_cluster_g<kDecGroups>(a, s, pdl);
 }
 
 inline int launch_dec_gemm(const DecGemmArgs& a, cudaStream_t s, bool pdl = false) {

@@ -92,10 +92,9 @@ struct Model {
   TcW t_w_in;
   Act a_x, a_h, a_ao, a_g, a_enc, a_qkv, a_vt; // tcgen05-path activation buffers (workspace); a_vt = per-head V^T
   bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between all decode-step kernels
-  bool pdl_attn = false;          // MT3_PDL=2: only the attention launches (K/V prefetch under the preceding GEMM)
-  bool pdl_gemm = false;          // MT3_PDL=4: only the GEMM launches; bits combine (6 = attention + GEMM)
+  bool pdl_attn = true;           // MT3_PDL=2 (default): only the attention launches (K/V prefetch under the preceding GEMM)
+  bool pdl_gemm = false;          // MT3_PDL=4: only the GEMM launches; bits combine (6 = attention + GEMM); 0 = off
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
-  DecGemmOpts dec_opts;           // MT3_DEC_GROUPS / MT3_DEC_CLUSTER16
   bool kv_half = false;           // cfg.kv_cache_format == MT3_KV_F16: self and cross K/V rows stored as fp16
   int kv_elt = 4;                 // bytes per K/V element
   // debug timeline (mt3_debug_trace_step): while `tracing` is set every decode GEMM / attention launch gets a slot
@@ -409,7 +408,7 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
     a.counters = m->dcounters;
     a.trace = trace_slot(m, K == m->F ? "gemm_mlp_out" : (N == 2 * m->F ? "gemm_mlp_in" : (kv ? "gemm_qkv_append" : (N == m->V ? "gemm_logits" : (K == m->Q ? "gemm_attn_out" : "gemm_cross_q")))));
     int rc = MT3_ERR_UNSUPPORTED;
-    if (m->dec_cluster) rc = launch_dec_gemm_cluster(a, m->dec_opts, s, m->pdl_gemm);
+    if (m->dec_cluster) rc = launch_dec_gemm_cluster(a, s, m->pdl_gemm);
     if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, s, m->pdl_gemm);   // shapes the cluster kernel does not tile
     MT3_TRY(rc);
   }
@@ -463,7 +462,7 @@ static int dec_gemm_out_q(Model* m, const DecLayer& w, const float* y_in, float*
   a1.eps = 1e-6f; a1.epi = EPI_STORE; a1.C = m->dq + r0 * Q; a1.ldc = Q; a1.n_split = Q;
   a1.R = a1.C; a1.ldr = Q;
   a1.trace = a0.trace;
-  return launch_dec_gemm_out_q(a0, a1, m->dec_opts, s, m->pdl_gemm);
+  return launch_dec_gemm_out_q(a0, a1, s, m->pdl_gemm);
 }
 
 // The residual stream of one step (ping-pongs between m->dy and m->dy2 across fused launches).
@@ -707,7 +706,9 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
   }
   {
     const char* e_pdl = getenv("MT3_PDL");
-    const int pdl_bits = e_pdl ? atoi(e_pdl) : 0;
+    // default: attention launches only (their K/V prefetch and launch latency hide under the preceding GEMM: 437.8 ->
+    // 415.4 ms per batch); PDL on the GEMM launches measured slower (451.8), profiles/r02_call1_bench_pdl*.json
+    const int pdl_bits = e_pdl ? atoi(e_pdl) : 2;
     m->pdl = (pdl_bits & 1) != 0;
     m->pdl_attn = (pdl_bits & 3) != 0;
     m->pdl_gemm = (pdl_bits & 5) != 0;
@@ -715,10 +716,6 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     m->fuse_q = !(e_fuse && e_fuse[0] == '0');
     const char* e_clu = getenv("MT3_DEC_CLUSTER");
     m->dec_cluster = !(e_clu && e_clu[0] == '0');
-    const char* e_grp = getenv("MT3_DEC_GROUPS");
-    m->dec_opts.groups = (e_grp && e_grp[0] == '1') ? 1 : 2;
-    const char* e_c16 = getenv("MT3_DEC_CLUSTER16");
-    m->dec_opts.c16 = !(e_c16 && e_c16[0] == '0');
     const char* e_attn = getenv("MT3_TC_ATTENTION");
     m->tc_attn_ok = !(e_attn && e_attn[0] == '0');
   }
