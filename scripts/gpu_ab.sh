@@ -24,13 +24,9 @@ except Exception as e:
     print(open("gpurun_out/bench_$name.err").read()[-1500:])
 PY
 }
-run_bench default MT3_X=0
-run_bench groups1 MT3_DEC_GROUPS=1
-run_bench pdl1 MT3_PDL=1
-run_bench pdl2 MT3_PDL=2
-run_bench pdl4 MT3_PDL=4
-run_bench pdl6 MT3_PDL=6
-run_bench c16off MT3_DEC_CLUSTER16=0
+for spec in ${AB_LIST:-default:MT3_X=0}; do
+  run_bench "${spec%%:*}" "${spec#*:}"
+done
 echo "== decode-step timeline"
 TRACE_POS=512 TRACE_ROWS=12 timeout 300 python scripts/trace_step.py > gpurun_out/trace_step.log 2>&1; tail -14 gpurun_out/trace_step.log
 TRACE_KV=f32 TRACE_POS=512 TRACE_ROWS=0 timeout 300 python scripts/trace_step.py > gpurun_out/trace_step_kvf32.log 2>&1; tail -12 gpurun_out/trace_step_kvf32.log
