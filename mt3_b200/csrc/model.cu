@@ -21,7 +21,6 @@
 #include "gemm_tc.cuh"
 #include "attention_tc.cuh"
 #include "decode.cuh"
-#include "decode_umma.cuh"
 #include "layers.cuh"
 
 namespace mt3 {
@@ -89,11 +88,6 @@ struct Model {
   bool fuse_q = true;             // MT3_DEC_FUSE=0: keep the self-attention out-projection and the cross-attention query
                                   // projection as two launches (default: one launch with a precomposed weight block)
   float *dy2 = nullptr, *dssq = nullptr;   // second residual-stream buffer (ping-pong) and [B][D/32] sum-of-squares partials
-  // tcgen05 decode GEMM (decode_umma.cuh): K-major copies W^T [N, K] of the decoder's step weights and cached TMA maps
-  bool dec_umma = false;          // tensor-core gemm_modes use it unless MT3_DEC_UMMA=0
-  float* slab_dect = nullptr;
-  std::map<const float*, const float*> dec_wt;                                   // [K, N] weight -> its W^T copy
-  std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> dec_maps;   // (ptr, rows, K, ld, box rows) -> TMA map
   bool tc = false, split3 = false;
   TcW t_w_in;
   Act a_x, a_h, a_ao, a_g, a_enc, a_qkv, a_vt; // tcgen05-path activation buffers (workspace); a_vt = per-head V^T
@@ -395,33 +389,8 @@ static unsigned long long* trace_slot(Model* m, const char* name) {
   return m->trace + (size_t)(m->trace_names.size() - 1) * kTraceWords;
 }
 
-// TMA map of an [rows, K] fp32 operand (leading dimension ld), box 32 floats x box_rows; built once and cached.
-static int dec_tmap(Model* m, const float* ptr, int rows, int K, int ld, int box_rows, CUtensorMap* out) {
-  const auto key = std::make_tuple((const void*)ptr, rows, K, ld, box_rows);
-  auto it = m->dec_maps.find(key);
-  if (it == m->dec_maps.end()) {
-    CUtensorMap tm;
-    MT3_TRY(make_tmap_2d(&tm, ptr, (uint64_t)rows, (uint64_t)K, (uint64_t)ld, (uint32_t)box_rows));
-    it = m->dec_maps.emplace(key, tm).first;
-  }
-  *out = it->second;
-  return MT3_OK;
-}
-
-// maps of one tcgen05 decode GEMM: W^T [N, K], X source 0 [M, K0 or K], X source 1 [M, K - K0]
-static int dec_umma_maps(Model* m, const DecGemmArgs& a, DecUmmaMaps* maps) {
-  const auto wt = m->dec_wt.find(a.W);
-  if (wt == m->dec_wt.end()) return MT3_ERR_UNSUPPORTED;
-  MT3_TRY(dec_tmap(m, wt->second, a.N, a.K, a.K, kDuBN, &maps->w));
-  const int k0 = a.A2 ? a.K0 : a.K;
-  MT3_TRY(dec_tmap(m, a.A, a.M, k0, a.lda, kDecBM, &maps->xa));
-  if (a.A2) MT3_TRY(dec_tmap(m, a.A2, a.M, a.K - a.K0, a.lda2, kDecBM, &maps->xb));
-  else maps->xb = maps->xa;
-  return MT3_OK;
-}
-
-// Decode-step GEMM on M = B rows: tcgen05 3xTF32 (decode_umma.cuh) for the tensor-core gemm_modes, else the split-K
-// exact-fp32 cluster kernel (decode.cuh); the RMSNorm statistic is fused in both.
+// Decode-step GEMM on M = B rows: split-K exact-fp32 cluster kernel with the RMSNorm statistic fused (decode.cuh), in every
+// gemm_mode (the tcgen05 variants of both rounds are correct but slower: csrc/experiments/).
 static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, int K, int norm, int epi, float* C, int ldc,
                     int n_split, char* kv, const int* pos, const Rows& rows, cudaStream_t s) {
   for (int r0 = rows.begin; r0 < rows.begin + rows.count; r0 += kDecBM) {
@@ -440,12 +409,7 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
     a.counters = m->dcounters;
     a.trace = trace_slot(m, K == m->F ? "gemm_mlp_out" : (N == 2 * m->F ? "gemm_mlp_in" : (kv ? "gemm_qkv_append" : (N == m->V ? "gemm_logits" : (K == m->Q ? "gemm_attn_out" : "gemm_cross_q")))));
     int rc = MT3_ERR_UNSUPPORTED;
-    if (m->dec_umma && dec_gemm_umma_supported(a)) {
-      DecUmmaMaps maps;
-      rc = dec_umma_maps(m, a, &maps);
-      if (rc == MT3_OK) rc = launch_dec_gemm_umma(maps, a, s, m->pdl_gemm);
-    }
-    if (rc == MT3_ERR_UNSUPPORTED && m->dec_cluster) rc = launch_dec_gemm_cluster(a, s, m->pdl_gemm);
+    if (m->dec_cluster) rc = launch_dec_gemm_cluster(a, s, m->pdl_gemm);
     if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, s, m->pdl_gemm);   // shapes the cluster kernel does not tile
     MT3_TRY(rc);
   }
@@ -499,13 +463,6 @@ static int dec_gemm_out_q(Model* m, const DecLayer& w, const float* y_in, float*
   a1.eps = 1e-6f; a1.epi = EPI_STORE; a1.C = m->dq + r0 * Q; a1.ldc = Q; a1.n_split = Q;
   a1.R = a1.C; a1.ldr = Q;
   a1.trace = a0.trace;
-  if (m->dec_umma && dec_gemm_umma_supported(a0) && dec_gemm_umma_supported(a1)) {
-    DecUmmaMaps m0, m1;
-    int rc = dec_umma_maps(m, a0, &m0);
-    if (rc == MT3_OK) rc = dec_umma_maps(m, a1, &m1);
-    if (rc == MT3_OK) return launch_dec_gemm_umma2(m0, m1, a0, a1, s, m->pdl_gemm);
-    if (rc != MT3_ERR_UNSUPPORTED) return rc;
-  }
   return launch_dec_gemm_out_q(a0, a1, s, m->pdl_gemm);
 }
 
@@ -532,7 +489,7 @@ static int dec_layer_outq(Model* m, DecBranch& b, int l) {
   const DecLayer& w = m->dec[l];
   const int D = m->D, Q = m->Q;
   b.fused = MT3_ERR_UNSUPPORTED;
-  if (m->fuse_q && (m->dec_cluster || m->dec_umma)) {
+  if (m->fuse_q && m->dec_cluster) {
     float* y_next = (b.y == m->dy) ? m->dy2 : m->dy;    // the fused launch reads y while other CTAs write y': ping-pong
     b.fused = dec_gemm_out_q(m, w, b.y, y_next, b.rows, b.s);
     if (b.fused == MT3_OK) b.y = y_next;
@@ -787,34 +744,6 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
       if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: tc weight prep -> %s", cudaGetErrorString(e));
     }
   }
-  {
-    const char* e_du = getenv("MT3_DEC_UMMA");
-    m->dec_umma = m->tc && !(e_du && e_du[0] == '0');
-  }
-  if (rc == MT3_OK && m->dec_umma) {
-    // K-major copies of the decode-step weights: the M operand of the tcgen05 decode GEMM
-    const int64_t n_dect = (int64_t)m->Ld * ((int64_t)D * 3 * Q + (int64_t)Q * D + (int64_t)D * Q + (int64_t)(Q + D) * Q + (int64_t)Q * D +
-                                             (int64_t)D * 2 * F + (int64_t)F * D) + (int64_t)D * V;
-    e = cudaMalloc((void**)&m->slab_dect, (size_t)n_dect * sizeof(float));
-    if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: cudaMalloc(decode W^T) -> %s", cudaGetErrorString(e));
-    float* cur = m->slab_dect;
-    auto tr = [&](const float* w, int K, int N) {
-      if (rc != MT3_OK) return;
-      transpose_split_kernel<<<dim3(cdiv(N, 32), cdiv(K, 32)), dim3(32, 8), 0, s>>>(w, K, N, cur, nullptr);
-      if (cudaGetLastError() != cudaSuccess) { rc = fail(MT3_ERR_CUDA, "mt3_model_create: decode W^T prep launch failed"); return; }
-      m->dec_wt[w] = cur;
-      cur += (int64_t)K * N;
-    };
-    for (int i = 0; i < m->Ld; ++i) {
-      const DecLayer& L = m->dec[i];
-      tr(L.wqkv, D, 3 * Q); tr(L.wo, Q, D); tr(L.wq_c, D, Q); tr(L.wc1, Q + D, Q); tr(L.wo_c, Q, D); tr(L.wi, D, 2 * F); tr(L.wo2, F, D);
-    }
-    tr(m->w_logits, D, V);
-    if (rc == MT3_OK) {
-      e = cudaStreamSynchronize(s);
-      if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: decode W^T prep -> %s", cudaGetErrorString(e));
-    }
-  }
   if (rc == MT3_OK) {
     e = cudaMallocHost((void**)&m->h_flag, 4 * sizeof(int));
     if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: cudaMallocHost -> %s", cudaGetErrorString(e));
@@ -822,7 +751,6 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
   if (rc != MT3_OK) {
     cudaFree(m->slab);
     cudaFree(m->slab_tc);
-    cudaFree(m->slab_dect);
     delete m;
     return rc;
   }
@@ -838,7 +766,6 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
   if (m->h_flag) cudaFreeHost(m->h_flag);
   cudaFree(m->slab);
   cudaFree(m->slab_tc);
-  cudaFree(m->slab_dect);
   delete m;
   return MT3_OK;
 }
