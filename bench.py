@@ -469,6 +469,69 @@ def run_ours(args):
     return 0
 
 
+def run_longform(args):
+    """BASELINE configs[4]: 3 minutes of audio -> 88 segments of 2.048 s -> tokens -> stitched NoteSequence, the segments
+    sharded over the N GPUs (strong scaling: the work is fixed).  Timed end to end through InferenceModel.__call__'s
+    pieces: host framing, H2D, log-mel + encoder + greedy decode, D2H, all-gather, host stitch."""
+    import torch
+    import torch.distributed as dist
+    from mt3_b200 import _lib, inference, note_decoding
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    kvf = {'f32': _lib.KV_F32, 'f16': _lib.KV_F16}[args.kv]
+    im = inference.InferenceModel('synthetic:0' if rank == 0 else None, 'mt3', device=dev, batch_size=BATCH_PER_GPU, kv_format=kvf)
+    n = 3 * 60 * 16000
+    audio = synth_audio(-(-n // SEG_SAMPLES), 100).reshape(-1)[:n]
+    launches0 = _lib.launch_count()
+
+    def one():
+        preds = im.predict_segments(audio)
+        return note_decoding.event_predictions_to_ns(preds, im.codec, im.encoding_spec)['est_ns'], len(preds)
+
+    for _ in range(max(1, args.warmup)):
+        one()
+    times = []
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        ns, nseg = one()
+        torch.cuda.synchronize(dev)
+        times.append(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = 1000.0 * float(np.mean(times))
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    if rank == 0:
+        v = (n / 16000.0) / (ms / 1000.0)
+        print(json.dumps({
+            "metric": "audio_seconds_per_second", "value": v, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "mt3 config long-form (BASELINE configs[4]): 3 min of 16 kHz audio -> 88 segments -> greedy decode "
+                                   "(1024 steps, synthetic weights never emit EOS) -> event_codec stitch to a NoteSequence",
+                       "segments": nseg, "segments_per_gpu": -(-nseg // world)},
+            "impl_config": {"kv_cache": args.kv + " rows, fp32 arithmetic", "parallelism": f"dp{world}: segments sharded, 1 all-gather"},
+            "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": int(nseg * SEG_SAMPLES * 4), "d2h_bytes_per_step": int(nseg * 1024 * 4),
+                    "ms_per_step": ms, "api": "InferenceModel.predict_segments + note_decoding.event_predictions_to_ns"},
+            "gpu_launches": int(_lib.launch_count() - launches0), "clocks": clocks, "notes_out": len(ns.notes)}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -483,9 +546,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gemm-mode", default="tf32x3", choices=["simt", "tf32x3", "tf32"],
                     help="encoder/cross-K/V GEMMs: exact fp32 CUDA cores, or tcgen05 tf32 (x3 = fp32-faithful split)")
+    ap.add_argument("--workload", default="batch", choices=["batch", "longform"],
+                    help="batch: BASELINE configs[1]/[2] (64 segments per GPU, the headline); longform: configs[4] (3 min of audio, strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "longform":
+        return run_longform(args)
     return run_ours(args)
 
 

@@ -128,9 +128,12 @@ struct Model {
 
   // CUDA graph of one greedy step
   cudaStream_t cap_stream = nullptr;
-  cudaGraph_t graph = nullptr;
+  cudaGraph_t graph = nullptr;              // the graph of the CURRENT (workspace, B, T) binding ...
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_kernels = 0;
+  struct StepGraph { cudaGraph_t g; cudaGraphExec_t e; uint64_t kernels; };
+  std::map<std::tuple<const void*, int, int>, StepGraph> graphs;   // ... kept per binding, so that a short tail batch does not
+                                                                   // throw away the full batch's graph (and vice versa)
   int* h_flag = nullptr;          // pinned
 };
 
@@ -542,11 +545,24 @@ static int decode_step_impl(Model* m, const int* tok_in, float* logits, int gree
   return MT3_OK;
 }
 
-static void drop_graph(Model* m) {
-  if (m->graph_exec) cudaGraphExecDestroy(m->graph_exec);
-  if (m->graph) cudaGraphDestroy(m->graph);
+static void drop_graphs(Model* m) {
+  for (auto& kv : m->graphs) {
+    if (kv.second.e) cudaGraphExecDestroy(kv.second.e);
+    if (kv.second.g) cudaGraphDestroy(kv.second.g);
+  }
+  m->graphs.clear();
   m->graph_exec = nullptr;
   m->graph = nullptr;
+}
+
+// make the graph of the current (workspace, B, T) binding current, if one has been captured
+static void select_graph(Model* m) {
+  const auto it = m->graphs.find(std::make_tuple((const void*)m->ws, m->B, m->T));
+  if (it == m->graphs.end()) {
+    m->graph = nullptr; m->graph_exec = nullptr; m->graph_kernels = 0;
+  } else {
+    m->graph = it->second.g; m->graph_exec = it->second.e; m->graph_kernels = it->second.kernels;
+  }
 }
 
 static int ensure_graph(Model* m) {
@@ -566,6 +582,13 @@ static int ensure_graph(Model* m) {
   m->graph_kernels = g_launch_count.load() - before;
   g_launch_count.fetch_sub(m->graph_kernels);   // capture does not execute
   MT3_CUDA_CHECK(cudaGraphInstantiate(&m->graph_exec, m->graph, 0));
+  if (m->graphs.size() >= 8) {                  // bound the cache: forget everything but the new graph
+    const Model::StepGraph keep{m->graph, m->graph_exec, m->graph_kernels};
+    m->graph = nullptr; m->graph_exec = nullptr;
+    drop_graphs(m);
+    m->graph = keep.g; m->graph_exec = keep.e; m->graph_kernels = keep.kernels;
+  }
+  m->graphs[std::make_tuple((const void*)m->ws, m->B, m->T)] = Model::StepGraph{m->graph, m->graph_exec, m->graph_kernels};
   return MT3_OK;
 }
 
@@ -761,7 +784,7 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
 extern "C" int mt3_model_destroy(mt3_model* h) {
   if (!h) return MT3_OK;
   Model* m = reinterpret_cast<Model*>(h);
-  drop_graph(m);
+  drop_graphs(m);
   if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   if (m->h_flag) cudaFreeHost(m->h_flag);
   cudaFree(m->slab);
@@ -833,9 +856,9 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
   MT3_REQUIRE(((uintptr_t)workspace & 255) == 0, MT3_ERR_WORKSPACE, "workspace must be 256-byte aligned");
   const WsLayout w = ws_layout(m, batch, input_length);
   MT3_REQUIRE(bytes >= w.total, MT3_ERR_WORKSPACE, "workspace has %lld bytes, %lld needed", (long long)bytes, (long long)w.total);
-  drop_graph(m);
   char* b = (char*)workspace;
   m->ws = b; m->ws_bytes = bytes; m->B = batch; m->T = input_length;
+  select_graph(m);
   m->h = (float*)(b + w.h); m->rstd = (float*)(b + w.rstd); m->qkv = (float*)(b + w.qkv); m->ao = (float*)(b + w.ao);
   m->g = (float*)(b + w.g); m->encoded = (float*)(b + w.encoded); m->ckv = b + w.ckv; m->skv = b + w.skv;
   m->dy2 = (float*)(b + w.dy2); m->dssq = (float*)(b + w.dssq);

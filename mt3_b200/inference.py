@@ -146,6 +146,8 @@ class InferenceModel(object):
         if isinstance(a, np.ndarray):
             a = torch.from_numpy(a)
         assert a.dim() == 2 and a.dtype == torch.float32
+        if not a.is_cuda and not a.is_pinned():
+            a = a.pin_memory()              # so that the per-batch H2D copies below are truly asynchronous
         S = a.shape[0]
         out = torch.empty((S, self.outputs_length), dtype=torch.int32, pin_memory=True)
         nv = None
@@ -221,7 +223,9 @@ class InferenceModel(object):
             flat = np.asarray(ex['inputs'], np.float32).reshape(-1)
             segs[i, :flat.size] = flat
             n_valid[i] = flat.size // hop
-        tokens = self.transcribe_segments(segs, n_valid_frames=n_valid)
+        # one process per GPU (torch.distributed initialised): every rank holds the same audio, transcribes its contiguous
+        # shard of the segments and receives all token streams after one all-gather; identity with a single process
+        tokens = self.transcribe_segments_sharded(segs, n_valid_frames=n_valid)
         return [self.postprocess(t, ex) for t, ex in zip(tokens, ds)]
 
     def audio_to_dataset(self, audio):

@@ -14,3 +14,9 @@ timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --mas
 echo "== distributed transcribe (InferenceModel over NCCL)"
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 \
    scripts/dist_check.py 2>&1 | tail -6 | tee gpurun_out/dist_check_n$N.log
+echo "== pytest multi-GPU long-form parity"
+timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu 2>&1 | tail -3 | tee gpurun_out/pytest_gpu_multi_n$N.log
+echo "== long-form workload (BASELINE configs[4]), 1 and $N GPUs"
+timeout 600 python bench.py --workload longform --steps 3 --warmup 1 2> gpurun_out/bench_longform_n1.err | tail -1 | tee gpurun_out/bench_longform_n1.json | cut -c1-260
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29520 \
+   bench.py --workload longform --gpus $N --steps 3 --warmup 1 2> gpurun_out/bench_longform_n$N.err | tail -1 | tee gpurun_out/bench_longform_n$N.json | cut -c1-260
