@@ -158,7 +158,12 @@ int mt3_decode_step(mt3_model* m, const int32_t* tok_in, float* logits, int32_t*
 
 enum {
   MT3_GEN_STOP_AT_EOS = 1,   /* end the loop once every sequence emitted EOS (id 1)   */
-  MT3_GEN_USE_GRAPH = 2      /* replay one captured CUDA graph per step                */
+  MT3_GEN_USE_GRAPH = 2,     /* replay one captured CUDA graph per step                */
+  MT3_GEN_BEAM1 = 4          /* t5x decoding.beam_search bookkeeping at num_decodes = 1 (the reference's decode_fn,
+                                models.py:127) instead of greedy-until-EOS: the live prefix continues with the best non-EOS
+                                token, "prefix + EOS" hypotheses are ranked by log-prob / ((5 + length) / 6)^0.6, and the best
+                                finished hypothesis is returned.  With MT3_GEN_STOP_AT_EOS the loop ends once every sequence's
+                                finished score beats what its live prefix can still reach.                                */
 };
 
 /* predict_batch_with_aux stand-in (models.py:121-138 + t5x decode loop, greedy):

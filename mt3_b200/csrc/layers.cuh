@@ -216,9 +216,11 @@ __global__ void embed_kernel(const int* __restrict__ tok, const float* __restric
 __global__ void __launch_bounds__(256)
 argmax_step_kernel(const float* __restrict__ logits, int V, int B, int* __restrict__ tok_cur,
                    int* __restrict__ finished, int* __restrict__ tokens_out, int out_ld, int* __restrict__ tok_out_user,
-                   int* __restrict__ state, int advance, int b0) {
+                   int* __restrict__ state, int advance, int b0, const float* __restrict__ emb, const float* __restrict__ pe, int D,
+                   float* __restrict__ y_next) {
   __shared__ float sv[8];
   __shared__ int si[8];
+  __shared__ int s_next[2];
   pdl_wait();
   pdl_trigger();
   // B = sequences in the whole batch (the arrival counter spans every sub-batch), b0 = first sequence of this launch
@@ -247,6 +249,8 @@ argmax_step_kernel(const float* __restrict__ logits, int V, int B, int* __restri
       if (finished[b]) nxt = 0;
       if (nxt == 1) finished[b] = 1;
     }
+    s_next[0] = nxt;
+    s_next[1] = pos + 1;
     if (tok_cur) tok_cur[b] = nxt;
     if (tokens_out) tokens_out[(long long)b * out_ld + pos] = nxt;
     if (tok_out_user) tok_out_user[b] = nxt;
@@ -267,6 +271,145 @@ argmax_step_kernel(const float* __restrict__ logits, int V, int B, int* __restri
       }
     }
   }
+  // generate loop: the next step's decoder input  y[b,:] = E[next,:] + PE[pos + 1,:]  (embed_kernel's work, layers.py:516-537,
+  // :589-596) is written here, which takes one launch out of every step.  pos was read before this CTA arrived at the
+  // counter, i.e. before the last CTA advances it.
+  if (y_next) {
+    __syncthreads();
+    const int t = min(max(s_next[0], 0), V - 1), p1 = s_next[1];
+    const float4* e = reinterpret_cast<const float4*>(emb + (long long)t * D);
+    const float4* pp = reinterpret_cast<const float4*>(pe + (long long)p1 * D);
+    float4* o = reinterpret_cast<float4*>(y_next + (long long)b * D);
+    for (int i = tid; i < D / 4; i += 256) {
+      const float4 a = __ldg(e + i), c = __ldg(pp + i);
+      o[i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// T5X decoding.beam_search at num_decodes = 1 (the reference's decode_fn, models.py:127), one CTA per sequence.
+// With one live beam the search keeps the 2 best extensions of the live prefix per step:
+//   live     continues with the best token that is NOT EOS (cumulative log-probability live_lp);
+//   finished whenever EOS is among the 2 best, the hypothesis "prefix + EOS" competes with the best finished one so far on
+//            (live_lp_before + log p(EOS)) / brevity_penalty(alpha, length),  brevity_penalty = ((5 + n) / 6)^alpha;
+//   a sequence is settled once its finished score beats what the live prefix can still reach,
+//            live_lp / brevity_penalty(alpha, max_len)   (`finished[b]`, feeds the loop's all-finished flag).
+// tokens_out holds the LIVE sequence; beam1_finalize_kernel cuts it at the winning finish.  Ties follow the reference's
+// stable top-k (lower vocabulary id first; an existing finished hypothesis beats an equal newcomer).
+// beam_f [B][2] = {live_lp, finished score}, beam_i [B] = length of the best finished hypothesis (0 = none yet).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool cand_better(float v, int i, float ov, int oi) { return v > ov || (v == ov && i < oi); }
+
+__global__ void __launch_bounds__(256)
+beam1_step_kernel(const float* __restrict__ logits, int V, int B, int* __restrict__ tok_cur, int* __restrict__ finished,
+                  int* __restrict__ tokens_out, int out_ld, int* __restrict__ state, float* __restrict__ beam_f,
+                  int* __restrict__ beam_i, float alpha, int max_len, const float* __restrict__ emb, const float* __restrict__ pe,
+                  int D, float* __restrict__ y_next) {
+  __shared__ float s1v[8], s2v[8], smx[8], ssum[8];
+  __shared__ int s1i[8], s2i[8];
+  __shared__ int s_next[2];
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* l = logits + (long long)b * V;
+  // best and second-best NON-EOS candidates (value, id), and the running maximum over everything for the log-sum-exp
+  float v1 = -INFINITY, v2 = -INFINITY, mx = -INFINITY;
+  int i1 = 0x7fffffff, i2 = 0x7fffffff;
+  for (int i = tid; i < V; i += 256) {
+    const float v = l[i];
+    mx = fmaxf(mx, v);
+    if (i == 1) continue;                        // EOS (vocabularies.py:157-159) is handled separately
+    if (cand_better(v, i, v1, i1)) { v2 = v1; i2 = i1; v1 = v; i1 = i; }
+    else if (cand_better(v, i, v2, i2)) { v2 = v; i2 = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov1 = __shfl_xor_sync(0xffffffffu, v1, o), ov2 = __shfl_xor_sync(0xffffffffu, v2, o);
+    const int oi1 = __shfl_xor_sync(0xffffffffu, i1, o), oi2 = __shfl_xor_sync(0xffffffffu, i2, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (cand_better(ov1, oi1, v1, i1)) {         // theirs wins: second = better of (mine first, their second)
+      if (cand_better(v1, i1, ov2, oi2)) { v2 = v1; i2 = i1; } else { v2 = ov2; i2 = oi2; }
+      v1 = ov1; i1 = oi1;
+    } else if (cand_better(ov1, oi1, v2, i2)) { v2 = ov1; i2 = oi1; }
+  }
+  if (lane == 0) { s1v[warp] = v1; s1i[warp] = i1; s2v[warp] = v2; s2i[warp] = i2; smx[warp] = mx; }
+  __syncthreads();
+  float gmx = smx[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) gmx = fmaxf(gmx, smx[w]);
+  float se = 0.f;
+  for (int i = tid; i < V; i += 256) se += expf(l[i] - gmx);
+  se = warp_sum(se);
+  if (lane == 0) ssum[warp] = se;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) {
+      const float ov1 = s1v[w], ov2 = s2v[w];
+      const int oi1 = s1i[w], oi2 = s2i[w];
+      if (cand_better(ov1, oi1, v1, i1)) {
+        if (cand_better(v1, i1, ov2, oi2)) { v2 = v1; i2 = i1; } else { v2 = ov2; i2 = oi2; }
+        v1 = ov1; i1 = oi1;
+      } else if (cand_better(ov1, oi1, v2, i2)) { v2 = ov1; i2 = oi1; }
+    }
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += ssum[w];
+    const float lse = gmx + logf(tot);
+    const float veos = l[1];
+    const int pos = state[0];
+    const float live_prev = beam_f[2 * b];
+    float fin_score = beam_f[2 * b + 1];
+    // EOS is one of the 2 best extensions iff it beats the second-best non-EOS candidate
+    if (cand_better(veos, 1, v2, i2)) {
+      const float cand = (live_prev + (veos - lse)) / powf((5.0f + (float)(pos + 1)) / 6.0f, alpha);
+      if (cand > fin_score) {
+        fin_score = cand;
+        beam_f[2 * b + 1] = cand;
+        beam_i[b] = pos + 1;
+      }
+    }
+    const float live = live_prev + (v1 - lse);
+    beam_f[2 * b] = live;
+    tok_cur[b] = i1;
+    tokens_out[(long long)b * out_ld + pos] = i1;
+    finished[b] = (beam_i[b] > 0 && fin_score > live / powf((5.0f + (float)max_len) / 6.0f, alpha)) ? 1 : 0;
+    s_next[0] = i1;
+    s_next[1] = pos + 1;
+    __threadfence();
+    const int done = atomicAdd(&state[1], 1);
+    if (done == B - 1) {
+      __threadfence();
+      int all = 1;
+      for (int i = 0; i < B; ++i) all &= (*(volatile int*)&finished[i]) != 0;
+      state[2] = all;
+      state[1] = 0;
+      state[0] = pos + 1;
+    }
+  }
+  if (y_next) {
+    __syncthreads();
+    const int t = min(max(s_next[0], 0), V - 1), p1 = s_next[1];
+    const float4* e = reinterpret_cast<const float4*>(emb + (long long)t * D);
+    const float4* pp = reinterpret_cast<const float4*>(pe + (long long)p1 * D);
+    float4* o = reinterpret_cast<float4*>(y_next + (long long)b * D);
+    for (int i = tid; i < D / 4; i += 256) {
+      const float4 a = __ldg(e + i), c = __ldg(pp + i);
+      o[i] = make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w);
+    }
+  }
+}
+
+// the best finished hypothesis = the live prefix up to its finish + EOS, zeros after; a sequence that never finished keeps
+// its live tokens (the reference returns the live beam when nothing finished)
+__global__ void beam1_finalize_kernel(int* __restrict__ tokens, int B, int L, int steps, const int* __restrict__ beam_i) {
+  const int b = blockIdx.x;
+  const int n = beam_i[b];
+  if (n <= 0) {
+    for (int i = steps + threadIdx.x; i < L; i += blockDim.x) tokens[(long long)b * L + i] = 0;
+    return;
+  }
+  if (threadIdx.x == 0) tokens[(long long)b * L + n - 1] = 1;
+  for (int i = n + threadIdx.x; i < L; i += blockDim.x) tokens[(long long)b * L + i] = 0;
 }
 
 // advance the position without an argmax (decode_step called with tok_out == NULL)

@@ -119,6 +119,7 @@ struct Model {
   char *ckv = nullptr, *skv = nullptr;   // head-major K/V (kv_elt bytes per element)
   float *dy = nullptr, *drstd = nullptr, *dq = nullptr, *dao = nullptr, *dg = nullptr, *dlogits = nullptr;
   int *tok_cur = nullptr, *finished = nullptr, *tokens = nullptr, *state = nullptr;
+  float* beam_f = nullptr; int* beam_i = nullptr;   // beam-size-1 search state (MT3_GEN_BEAM1)
   float* dpartial = nullptr;      // split-K scratch of the non-cluster decode GEMM
   int dcounters_n = 0;
   int* dcounters = nullptr;
@@ -131,8 +132,9 @@ struct Model {
   cudaGraph_t graph = nullptr;              // the graph of the CURRENT (workspace, B, T) binding ...
   cudaGraphExec_t graph_exec = nullptr;
   uint64_t graph_kernels = 0;
+  int graph_mode = 1;
   struct StepGraph { cudaGraph_t g; cudaGraphExec_t e; uint64_t kernels; };
-  std::map<std::tuple<const void*, int, int>, StepGraph> graphs;   // ... kept per binding, so that a short tail batch does not
+  std::map<std::tuple<const void*, int, int, int>, StepGraph> graphs;   // ... kept per binding, so that a short tail batch does not
                                                                    // throw away the full batch's graph (and vice versa)
   int* h_flag = nullptr;          // pinned
 };
@@ -521,10 +523,13 @@ static int dec_layer_mlp(Model* m, DecBranch& b, int l) {
 // DEV [B,V]; greedy != 0 runs the argmax/bookkeeping kernel (tok_user optional), else only the position advances.
 // 7 launches per layer: [norm+QKV+KV-append] [self-attn] [out+residual | norm+q] [cross-attn] [out+residual]
 // [norm+gated-GELU MLP in] [MLP out+residual].
+// loop_step: a step of mt3_generate's loop -- the decoder input m->dy was already written (by dec_embed before the first
+// step, by the previous step's argmax kernel afterwards), and this step's argmax kernel writes the next one.
 static int decode_step_impl(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
-                            int* tokens_ws, cudaStream_t s) {
+                            int* tokens_ws, cudaStream_t s, bool loop_step = false) {
   DecBranch b{Rows{0, m->B}, s, nullptr, MT3_ERR_UNSUPPORTED};
-  MT3_TRY(dec_embed(m, b, tok_in));
+  if (loop_step) b.y = m->dy;
+  else MT3_TRY(dec_embed(m, b, tok_in));
   for (int l = 0; l < m->Ld; ++l) {
     MT3_TRY(dec_layer_qkv(m, b, l));
     MT3_TRY(dec_layer_self(m, b, l));
@@ -533,10 +538,16 @@ static int decode_step_impl(Model* m, const int* tok_in, float* logits, int gree
     MT3_TRY(dec_layer_mlp(m, b, l));
   }
   MT3_TRY(dec_gemm(m, b.y, m->D, m->w_logits, m->V, m->D, 1, EPI_STORE, logits, m->V, m->V, nullptr, nullptr, b.rows, s));
-  if (greedy) {
+  if (greedy == 2) {        // T5X beam_search bookkeeping at num_decodes = 1 (generate loop only)
+    MT3_CUDA_CHECK(launch_kernel(beam1_step_kernel, dim3(m->B), dim3(256), 0, s, m->pdl, (const float*)logits, m->V, m->B, m->tok_cur,
+                                 m->finished, tokens_ws, m->L, m->state, m->beam_f, m->beam_i, 0.6f, m->L, (const float*)m->emb,
+                                 (const float*)m->pe, m->D, loop_step ? m->dy : (float*)nullptr));
+    MT3_LAUNCH_CHECK();
+  } else if (greedy) {
     MT3_CUDA_CHECK(launch_kernel(argmax_step_kernel, dim3(m->B), dim3(256), 0, s, m->pdl, (const float*)logits, m->V, m->B,
                                  use_finished ? m->tok_cur : (int*)nullptr, use_finished ? m->finished : (int*)nullptr,
-                                 tokens_ws, m->L, tok_user, m->state, 1, 0));
+                                 tokens_ws, m->L, tok_user, m->state, 1, 0, (const float*)m->emb, (const float*)m->pe, m->D,
+                                 loop_step ? m->dy : (float*)nullptr));
     MT3_LAUNCH_CHECK();
   } else {
     MT3_CUDA_CHECK(launch_kernel(advance_pos_kernel, dim3(1), dim3(1), 0, s, m->pdl, m->state));
@@ -555,9 +566,10 @@ static void drop_graphs(Model* m) {
   m->graph = nullptr;
 }
 
-// make the graph of the current (workspace, B, T) binding current, if one has been captured
-static void select_graph(Model* m) {
-  const auto it = m->graphs.find(std::make_tuple((const void*)m->ws, m->B, m->T));
+// make the graph of the current (workspace, B, T, decode mode) binding current, if one has been captured
+static void select_graph(Model* m, int mode = 1) {
+  m->graph_mode = mode;
+  const auto it = m->graphs.find(std::make_tuple((const void*)m->ws, m->B, m->T, mode));
   if (it == m->graphs.end()) {
     m->graph = nullptr; m->graph_exec = nullptr; m->graph_kernels = 0;
   } else {
@@ -565,12 +577,13 @@ static void select_graph(Model* m) {
   }
 }
 
-static int ensure_graph(Model* m) {
+static int ensure_graph(Model* m, int mode) {       // mode: 1 greedy, 2 beam-size-1 search
+  if (m->graph_mode != mode) select_graph(m, mode);
   if (m->graph_exec) return MT3_OK;
   if (!m->cap_stream) MT3_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
   const uint64_t before = g_launch_count.load();
   MT3_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-  int r = decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, m->cap_stream);
+  int r = decode_step_impl(m, m->tok_cur, m->dlogits, mode, nullptr, 1, m->tokens, m->cap_stream, true);
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
   if (r != MT3_OK) {
@@ -588,7 +601,7 @@ static int ensure_graph(Model* m) {
     drop_graphs(m);
     m->graph = keep.g; m->graph_exec = keep.e; m->graph_kernels = keep.kernels;
   }
-  m->graphs[std::make_tuple((const void*)m->ws, m->B, m->T)] = Model::StepGraph{m->graph, m->graph_exec, m->graph_kernels};
+  m->graphs[std::make_tuple((const void*)m->ws, m->B, m->T, mode)] = Model::StepGraph{m->graph, m->graph_exec, m->graph_kernels};
   return MT3_OK;
 }
 
@@ -797,7 +810,7 @@ namespace {
 struct WsLayout {
   int64_t x_hi, x_lo, h_lo, ao_lo, g_lo, enc_hi, enc_lo, qkv_lo, vt_hi, vt_lo;
   int64_t dy2, dssq;
-  int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, total;
+  int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, beam_f, beam_i, total;
 };
 WsLayout ws_layout(const Model* m, int B, int T) {
   WsLayout w;
@@ -837,6 +850,8 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   w.state = take(64);
   w.dpartial = take((int64_t)16 * cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * kDecTileFloats * 4);   // up to 16 K chunks
   w.dcounters = take((int64_t)cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * 4);
+  w.beam_f = take((int64_t)B * 2 * 4);
+  w.beam_i = take((int64_t)B * 4);
   w.total = off;
   return w;
 }
@@ -866,6 +881,7 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
   m->dg = (float*)(b + w.dg); m->dlogits = (float*)(b + w.dlogits); m->tok_cur = (int*)(b + w.tok_cur);
   m->finished = (int*)(b + w.finished); m->tokens = (int*)(b + w.tokens); m->state = (int*)(b + w.state);
   m->dpartial = (float*)(b + w.dpartial); m->dcounters = (int*)(b + w.dcounters);
+  m->beam_f = (float*)(b + w.beam_f); m->beam_i = (int*)(b + w.beam_i);
   m->dcounters_n = cdiv(std::max(std::max(3 * m->Q, 2 * m->F), m->V), kDecBN);
   m->have_cross = false;
   if (m->tc) {
@@ -925,21 +941,33 @@ extern "C" int mt3_generate(mt3_model* h, const float* x, int32_t num_steps, int
   Model* m = reinterpret_cast<Model*>(h);
   MT3_NEED_WS(m);
   MT3_REQUIRE(num_steps >= 0 && num_steps <= m->L, MT3_ERR_SHAPE, "num_steps %d outside [0, max_decode_length=%d]", num_steps, m->L);
-  MT3_REQUIRE((flags & ~(MT3_GEN_STOP_AT_EOS | MT3_GEN_USE_GRAPH)) == 0, MT3_ERR_BAD_ARG, "mt3_generate: unknown flag bits 0x%x", flags);
+  MT3_REQUIRE((flags & ~(MT3_GEN_STOP_AT_EOS | MT3_GEN_USE_GRAPH | MT3_GEN_BEAM1)) == 0, MT3_ERR_BAD_ARG, "mt3_generate: unknown flag bits 0x%x", flags);
   cudaStream_t s = (cudaStream_t)stream;
   MT3_TRY(encode_impl(m, x, m->encoded, s));
   MT3_TRY(cross_kv_impl(m, m->encoded, s));
   MT3_CUDA_CHECK(cudaMemsetAsync(m->tokens, 0, (size_t)m->B * m->L * sizeof(int), s));
   const bool use_graph = (flags & MT3_GEN_USE_GRAPH) != 0;
   const bool stop = (flags & MT3_GEN_STOP_AT_EOS) != 0;
-  if (use_graph) MT3_TRY(ensure_graph(m));
+  const int mode = (flags & MT3_GEN_BEAM1) ? 2 : 1;
+  if (mode == 2) {      // live log-probability 0, finished score NEG_INF (t5x decoding.NEG_INF = -1e7), no finished hypothesis
+    std::vector<float> init((size_t)2 * m->B);
+    for (int i = 0; i < m->B; ++i) { init[2 * i] = 0.f; init[2 * i + 1] = -1.0e7f; }
+    MT3_CUDA_CHECK(cudaMemcpyAsync(m->beam_f, init.data(), init.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+    MT3_CUDA_CHECK(cudaStreamSynchronize(s));        // `init` is stack-owned pageable memory
+    MT3_CUDA_CHECK(cudaMemsetAsync(m->beam_i, 0, (size_t)m->B * sizeof(int), s));
+  }
+  if (use_graph) MT3_TRY(ensure_graph(m, mode));
+  if (num_steps > 0) {     // decoder input of step 0: BOS (tok_cur was zeroed by cross_kv) at position 0; later ones come from the argmax kernel
+    DecBranch b0{Rows{0, m->B}, s, nullptr, MT3_ERR_UNSUPPORTED};
+    MT3_TRY(dec_embed(m, b0, m->tok_cur));
+  }
   int ran = 0;
   for (int step = 0; step < num_steps; ++step) {
     if (use_graph) {
       MT3_CUDA_CHECK(cudaGraphLaunch(m->graph_exec, s));
       count_launch(m->graph_kernels);
     } else {
-      MT3_TRY(decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, s));
+      MT3_TRY(decode_step_impl(m, m->tok_cur, m->dlogits, mode, nullptr, 1, m->tokens, s, true));
     }
     ++ran;
     m->host_pos += 1;
@@ -948,6 +976,10 @@ extern "C" int mt3_generate(mt3_model* h, const float* x, int32_t num_steps, int
       MT3_CUDA_CHECK(cudaStreamSynchronize(s));
       if (m->h_flag[0]) break;
     }
+  }
+  if (mode == 2) {
+    beam1_finalize_kernel<<<m->B, 128, 0, s>>>(m->tokens, m->B, m->L, ran, m->beam_i);
+    MT3_LAUNCH_CHECK();
   }
   MT3_CUDA_CHECK(cudaMemcpyAsync(tokens_out, m->tokens, (size_t)m->B * m->L * sizeof(int), cudaMemcpyDeviceToDevice, s));
   if (steps_run) *steps_run = ran;
@@ -983,7 +1015,7 @@ extern "C" int mt3_debug_trace_step(mt3_model* h, int32_t pos, uint64_t* out, in
   m->tracing = true;
   const uint64_t before = g_launch_count.load();
   MT3_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-  const int r = decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, m->cap_stream);
+  const int r = decode_step_impl(m, m->tok_cur, m->dlogits, 1, nullptr, 1, m->tokens, m->cap_stream, true);
   cudaGraph_t g = nullptr;
   const cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
   m->tracing = false;

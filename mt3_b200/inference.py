@@ -32,7 +32,7 @@ class InferenceModel(object):
 
     def __init__(self, checkpoint_path, model_type='mt3', *, device='cuda:0', batch_size: int = 8,
                  gin_dir: Optional[str] = None, gemm_mode: int = _lib.GEMM_TF32X3, use_graph: bool = True,
-                 kv_format: int = _lib.KV_F32):
+                 kv_format: int = _lib.KV_F32, decode: str = 'greedy'):
         # Model Constants (notebook :175-185).
         if model_type == 'ismir2021':
             num_velocity_bins = 127
@@ -55,6 +55,7 @@ class InferenceModel(object):
         self.use_graph = use_graph
         self._gemm_mode = gemm_mode
         self._kv_format = kv_format
+        self.decode = decode              # 'greedy' | 'beam1' (T5X beam_search at num_decodes=1, models.py:127)
 
         # Build Codecs and Vocabularies (notebook :198-206).
         self.spectrogram_config = spectrograms.SpectrogramConfig()
@@ -134,7 +135,7 @@ class InferenceModel(object):
         x = batch['encoder_input_tokens']
         if isinstance(x, np.ndarray):
             x = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(self.device, non_blocking=True)
-        prediction = self.model.generate(x, stop_at_eos=True, use_graph=self.use_graph)
+        prediction = self.model.generate(x, stop_at_eos=True, use_graph=self.use_graph, decode=self.decode)
         return self.vocabulary.decode_tf(prediction).cpu().numpy()
 
     def transcribe_segments(self, audio_segments, n_valid_frames=None, num_steps: Optional[int] = None,
@@ -159,7 +160,8 @@ class InferenceModel(object):
             spec = spectrograms.compute_spectrogram(dev, self.spectrogram_config,
                                                     n_valid_frames=None if nv is None else nv[s0:s1])
             spec = self._pad_inputs(spec)
-            toks = self.model.generate(spec, num_steps=num_steps, stop_at_eos=stop_at_eos, use_graph=self.use_graph)
+            toks = self.model.generate(spec, num_steps=num_steps, stop_at_eos=stop_at_eos, use_graph=self.use_graph,
+                                       decode=self.decode)
             if decoded:
                 toks = self.vocabulary.decode_tf(toks)
             out[s0:s1].copy_(toks, non_blocking=True)

@@ -162,16 +162,21 @@ class Transformer:
         return torch.cat(outs, dim=1)
 
     def generate(self, encoder_input_tokens: torch.Tensor, num_steps: Optional[int] = None, stop_at_eos: bool = True,
-                 use_graph: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """encode + greedy decode from BOS=0 (models.py:121-138 / t5x decode loop at num_decodes=1).
-        Returns raw model ids int32 [B, max_decode_length], 0 after EOS."""
+                 use_graph: bool = True, out: Optional[torch.Tensor] = None, decode: str = 'greedy') -> torch.Tensor:
+        """encode + decode from BOS=0 (models.py:121-138).  decode='greedy': argmax until EOS; decode='beam1': T5X's
+        decoding.beam_search at num_decodes=1, the reference's decode_fn (models.py:127) -- they differ when EOS is one of the
+        two best tokens without being decisive (tests/test_beam1.py).  Returns raw model ids int32 [B, max_decode_length],
+        0 after EOS."""
+        if decode not in ('greedy', 'beam1'):
+            raise ValueError("decode must be 'greedy' or 'beam1'")
         x = self._check_inputs(encoder_input_tokens)
         b, t, _ = x.shape
         self._bind(b, t)
         steps = self.max_decode_length if num_steps is None else int(num_steps)
         if out is None:
             out = torch.empty((b, self.max_decode_length), dtype=torch.int32, device=self.device)
-        flags = (_lib.GEN_STOP_AT_EOS if stop_at_eos else 0) | (_lib.GEN_USE_GRAPH if use_graph else 0)
+        flags = (_lib.GEN_STOP_AT_EOS if stop_at_eos else 0) | (_lib.GEN_USE_GRAPH if use_graph else 0) | \
+                (_lib.GEN_BEAM1 if decode == 'beam1' else 0)
         ran = C.c_int32(0)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.mt3_generate(self._h, x.data_ptr(), steps, flags, out.data_ptr(), C.byref(ran), self._stream()))

@@ -339,6 +339,45 @@ def test_generate_eos_semantics_and_graph_equivalence(pdl, monkeypatch):
     np.testing.assert_array_equal(dec, O.vocab_decode(t_plain, 1388))
 
 
+@pytest.mark.parametrize("seed,boost", [(9, 4.0), (11, 2.5)])
+def test_generate_beam1_matches_t5x_beam_search_restatement(seed, boost):
+    """MT3_GEN_BEAM1: T5X decoding.beam_search at num_decodes=1 (the reference's decode_fn, models.py:127) on the device,
+    against oracle/beam_search.py driven by the float64 oracle's step logits.  EOS-boosted weights make EOS compete at
+    scattered steps, so some sequences end where greedy ends, some earlier (a runner-up EOS with a better normalised
+    score) and some later (a first-ranked EOS that loses to a later finish)."""
+    from mt3_b200 import network
+    from oracle import beam_search as BS
+    ocfg = O.T5Config(vocab_size=1536, num_encoder_layers=2, num_decoder_layers=2)
+    params = _eos_params(ocfg, seed=seed, boost=boost)       # chosen so that one of the 8 sequences ends elsewhere than greedy's
+    cfg = _mt3_cfg(num_encoder_layers=2, num_decoder_layers=2)
+    L, Bn = 48, 8
+    m = network.Transformer(cfg, params, device=DEV, max_batch=Bn, max_input_length=64, max_decode_length=L)
+    x = _inputs(Bn, t=64, seed=50)
+    enc64 = O.encode(params, ocfg, x, np.float64)
+    p64 = O._cast(params, np.float64)
+    state = O.init_decode_state(ocfg, Bn, L, np.float64)
+    margins = []
+
+    def logits_fn(prefixes, step):          # K = 1: the live prefix only ever grows, so the oracle's KV cache can be reused
+        assert prefixes.shape[1] == 1 and state.position_index == step
+        cur = prefixes[:, 0, step - 1] if step > 0 else np.zeros((Bn,), np.int64)
+        lg = O.decode_step(p64, ocfg, enc64, cur, state)
+        margins.append(lg)
+        return lg[:, None, :]
+
+    want, score = BS.beam_search(logits_fn, Bn, L, eos_id=O.EOS_ID, num_decodes=1)
+    xg = torch.from_numpy(x).to(DEV)
+    got = m.generate(xg, stop_at_eos=False, use_graph=True, decode='beam1').cpu().numpy()
+    got_stop = m.generate(xg, stop_at_eos=True, use_graph=False, decode='beam1').cpu().numpy()
+    greedy = m.generate(xg, stop_at_eos=True, use_graph=True).cpu().numpy()
+    np.testing.assert_array_equal(got, got_stop)                 # graph replay == plain launches, early stop changes nothing
+    n_diff = int((got != greedy).any(axis=1).sum())
+    print(f"beam1: {n_diff} of {Bn} sequences differ from greedy; lengths beam1 {[(int(np.argmax(r == 1)) if (r == 1).any() else -1) for r in got]}"
+          f" greedy {[(int(np.argmax(r == 1)) if (r == 1).any() else -1) for r in greedy]}")
+    np.testing.assert_array_equal(got, want)
+    assert n_diff > 0, "the crafted weights should make beam-1 and greedy disagree somewhere"
+
+
 @pytest.mark.parametrize("kv", ["f32", "f16"])
 @pytest.mark.parametrize("gm,pdl,cluster", [("tf32x3", "0", "1"), ("tf32x3", "1", "1"), ("tf32x3", "6", "1"), ("simt", "1", "1"),
                                             ("simt", "2", "0")])
