@@ -180,6 +180,14 @@ int mt3_generate(mt3_model* m, const float* x, int32_t num_steps, int32_t flags,
 int mt3_vocab_decode(const int32_t* ids, int32_t batch, int32_t length, int32_t num_regular_tokens, int32_t* out,
                      void* stream);
 
+/* layers.dot_product_attention(query, key, value, bias=None) (layers.py:85-157) as a standalone op, float32, any head_dim:
+ * softmax(q k^T + bias) v with no 1/sqrt(d) scaling.  q DEV f32 [batch, q_len, heads, head_dim]; k, v DEV f32
+ * [batch, kv_len, heads, head_dim]; bias DEV f32 [batch, heads, q_len, kv_len] or NULL (the reference's combined mask /
+ * relative-position bias, layers.py:143-146; broadcasting is the caller's job); out DEV f32 like q.  The model's own
+ * attention kernels specialise this op for head_dim 64 and the two mask shapes MT3 uses (all-ones, causal-to-length). */
+int mt3_dot_product_attention_f32(const float* q, const float* k, const float* v, const float* bias, int32_t batch,
+                                  int32_t q_len, int32_t kv_len, int32_t num_heads, int32_t head_dim, float* out, void* stream);
+
 /* Measurement hook for bench.py's roofline leg: launches one named hot kernel `iters` times at
  * the shapes of the bound workspace, cycling over the decoder/encoder layers so that successive
  * launches touch different memory.  kind: MT3_K_* below; `pos` = KV-cache length - 1 for the

@@ -24,7 +24,7 @@ EXPORTS = [
     "mt3_frontend_create", "mt3_frontend_destroy", "mt3_frontend_num_frames", "mt3_logmel_f32",
     "mt3_model_num_params", "mt3_model_param_offset", "mt3_model_create", "mt3_model_destroy",
     "mt3_workspace_bytes", "mt3_model_set_workspace", "mt3_encode", "mt3_cross_kv", "mt3_decode_step",
-    "mt3_generate", "mt3_vocab_decode", "mt3_debug_launch", "mt3_debug_trace_step",
+    "mt3_generate", "mt3_vocab_decode", "mt3_dot_product_attention_f32", "mt3_debug_launch", "mt3_debug_trace_step",
 ]
 
 
@@ -82,6 +82,7 @@ def load() -> C.CDLL:
     lib.mt3_decode_step.argtypes = [vp, i32p, f32p, i32p, vp]
     lib.mt3_generate.argtypes = [vp, f32p, i32, i32, i32p, C.POINTER(i32), vp]
     lib.mt3_vocab_decode.argtypes = [i32p, i32, i32, i32, i32p, vp]
+    lib.mt3_dot_product_attention_f32.argtypes = [f32p, f32p, f32p, f32p, i32, i32, i32, i32, i32, f32p, vp]
     lib.mt3_debug_launch.argtypes = [vp, i32, i32, i32, vp]
     lib.mt3_debug_trace_step.argtypes = [vp, i32, vp, i32, C.c_char_p, i32, C.POINTER(C.c_int32), vp]
     for name in EXPORTS:

@@ -12,8 +12,11 @@ UNPINNED: no published checkpoint is reachable offline, so the reader is tested 
   <dir>/<array name>/.zarray     zarr v2 metadata (shape, chunks, dtype, compressor, order, fill_value)
   <dir>/<array name>/<i>.<j>...  one file per chunk, gzip-compressed C-order bytes (tensorstore's zarr driver)
 
-The parameters live under state['target'] (T5X >= 2022) or state['optimizer']['target'] (older checkpoints);
-array names are the tree path joined with '.', e.g. 'target.decoder.layers_0.mlp.wi_0.kernel'.
+T5X serialises its train state as {'version': .., 'optimizer': {'target': <params>, 'state': ..}}; the array names (zarr
+directories and placeholders) are 'target.' + the parameter path joined with '.', e.g.
+'target.decoder.layers_0.mlp.wi_0.kernel' -- NOT prefixed with 'optimizer.'.  That is the layout `save_t5x_checkpoint`
+writes by default and the tests read; a top-level 'target' tree is accepted too.  The reader has NOT been run against a
+real gs://mt3/checkpoints directory (unreachable offline): treat it as unverified until one can be read.
 """
 from __future__ import annotations
 
@@ -97,10 +100,10 @@ def load_t5x_checkpoint(path: str) -> Dict[str, np.ndarray]:
     ckpt_dir = path if os.path.isdir(path) else os.path.dirname(path)
     with open(os.path.join(ckpt_dir, "checkpoint"), "rb") as f:
         state = msgpack.unpackb(f.read(), ext_hook=_ext_hook, raw=False, strict_map_key=False)
-    if "target" in state:
+    if "optimizer" in state and isinstance(state["optimizer"], Mapping) and "target" in state["optimizer"]:
+        target = state["optimizer"]["target"]           # the layout T5X writes
+    elif "target" in state:
         target = state["target"]
-    elif "optimizer" in state and "target" in state["optimizer"]:
-        target = state["optimizer"]["target"]
     else:
         raise ValueError(f"{ckpt_dir}/checkpoint: no 'target' parameter tree (keys: {sorted(state)})")
     params: Dict[str, np.ndarray] = {}
@@ -116,13 +119,14 @@ def load_t5x_checkpoint(path: str) -> Dict[str, np.ndarray]:
 
 
 def save_t5x_checkpoint(path: str, params: Mapping[str, np.ndarray], step: int = 0, inline_below: int = 4096,
-                        max_chunk: int = 512, old_layout: bool = False) -> None:
-    """Write {tree path: array} in the layout described above (arrays with fewer than `inline_below` elements are
-    inlined in the msgpack file, the others become gzip zarr arrays chunked at `max_chunk` per axis).  Used by the
-    tests and to hand-convert weights; `old_layout` nests the tree under optimizer/target."""
+                        max_chunk: int = 512, top_level_target: bool = False) -> None:
+    """Write {tree path: array} in the layout described above: {'version', 'optimizer': {'target', 'state'}}, arrays
+    with fewer than `inline_below` elements inlined in the msgpack file, the others as gzip zarr arrays named
+    'target.<dotted path>' chunked at `max_chunk` per axis.  Used by the tests and to hand-convert weights;
+    `top_level_target` puts the tree at state['target'] instead (the variant the reader also accepts)."""
     import msgpack
     os.makedirs(path, exist_ok=True)
-    root = "optimizer.target" if old_layout else "target"
+    root = "target"
 
     def pack_array(a: np.ndarray):
         a = np.ascontiguousarray(a)
@@ -152,10 +156,11 @@ def save_t5x_checkpoint(path: str, params: Mapping[str, np.ndarray], step: int =
             block[tuple(slice(0, s.stop - s.start) for s in sel)] = arr[sel]
             with open(os.path.join(adir, ".".join(str(i) for i in idx)), "wb") as f:
                 f.write(gzip.compress(block.tobytes(), compresslevel=1))
-    state: Dict[str, Any] = {"version": 3, "state": {"step": step}}
-    if old_layout:
-        state["optimizer"] = {"target": tree, "state": {"step": step}}
-    else:
+    state: Dict[str, Any] = {"version": 3}
+    if top_level_target:
         state["target"] = tree
+        state["state"] = {"step": step}
+    else:
+        state["optimizer"] = {"target": tree, "state": {"step": step, "param_states": {}}}
     with open(os.path.join(path, "checkpoint"), "wb") as f:
         f.write(msgpack.packb(state, use_bin_type=True))

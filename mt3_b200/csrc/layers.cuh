@@ -412,6 +412,49 @@ __global__ void beam1_finalize_kernel(int* __restrict__ tokens, int B, int L, in
   for (int i = n + threadIdx.x; i < L; i += blockDim.x) tokens[(long long)b * L + i] = 0;
 }
 
+// ---------------------------------------------------------------------------------
+// layers.dot_product_attention (layers.py:85-157) as a standalone op, exact fp32, any head_dim, optional additive bias
+// [b, h, q, kv] (layers.py:143-146: combined mask / relative-position bias).  No 1/sqrt(d) scaling (the reference folds it
+// into the query initialiser, layers.py:230-234).  One warp per (batch, head, query); scores in shared memory.
+// q [b, tq, h, d], k / v [b, tk, h, d], out [b, tq, h, d].
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+dot_product_attention_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                             const float* __restrict__ bias, int B, int TQ, int TK, int H, int D, float* __restrict__ out) {
+  extern __shared__ float att_sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * 4 + warp;          // (b, h, qi)
+  if (item >= (long long)B * H * TQ) return;
+  const int qi = (int)(item % TQ), h = (int)((item / TQ) % H), b = (int)(item / ((long long)TQ * H));
+  float* sc = att_sm + (size_t)warp * TK;
+  const float* qr = q + (((long long)b * TQ + qi) * H + h) * D;
+  float mx = -INFINITY;
+  for (int j = lane; j < TK; j += 32) {
+    const float* kr = k + (((long long)b * TK + j) * H + h) * D;
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) s = fmaf(qr[d], kr[d], s);
+    if (bias) s += bias[(((long long)b * H + h) * TQ + qi) * TK + j];
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < TK; j += 32) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  const float inv = 1.0f / sum;
+  float* orow = out + (((long long)b * TQ + qi) * H + h) * D;
+  for (int d = lane; d < D; d += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < TK; ++j) acc = fmaf(sc[j], v[(((long long)b * TK + j) * H + h) * D + d], acc);
+    orow[d] = acc * inv;
+  }
+}
+
 // advance the position without an argmax (decode_step called with tok_out == NULL)
 __global__ void advance_pos_kernel(int* state) {
   pdl_wait();

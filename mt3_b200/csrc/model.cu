@@ -996,6 +996,27 @@ extern "C" int mt3_vocab_decode(const int32_t* ids, int32_t batch, int32_t lengt
   return MT3_OK;
 }
 
+extern "C" int mt3_dot_product_attention_f32(const float* q, const float* k, const float* v, const float* bias, int32_t batch,
+                                             int32_t q_len, int32_t kv_len, int32_t num_heads, int32_t head_dim, float* out,
+                                             void* stream) {
+  MT3_REQUIRE(q && k && v && out, MT3_ERR_BAD_ARG, "mt3_dot_product_attention_f32: null argument");
+  MT3_REQUIRE(batch >= 0 && q_len >= 0 && kv_len > 0 && num_heads > 0 && head_dim > 0, MT3_ERR_BAD_ARG,
+              "mt3_dot_product_attention_f32: non-positive size");
+  MT3_REQUIRE(kv_len <= 8192, MT3_ERR_UNSUPPORTED, "mt3_dot_product_attention_f32: kv_len %d above 8192", kv_len);
+  const long long items = (long long)batch * num_heads * q_len;
+  if (items == 0) return MT3_OK;
+  const size_t smem = (size_t)4 * kv_len * sizeof(float);
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(dot_product_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  dot_product_attention_kernel<<<(unsigned)((items + 3) / 4), 128, smem, (cudaStream_t)stream>>>(q, k, v, bias, batch, q_len, kv_len,
+                                                                                                 num_heads, head_dim, out);
+  MT3_LAUNCH_CHECK();
+  return MT3_OK;
+}
+
 __global__ void trace_reset_kernel(unsigned long long* t, int n_slots) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_slots * mt3::kTraceWords) t[i] = (i % mt3::kTraceWords == 0) ? ~0ull : 0ull;

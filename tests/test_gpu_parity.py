@@ -470,6 +470,38 @@ def test_decode_fused_out_q_matches_unfused(monkeypatch):
     assert np.abs(fused - ref).max() <= 5e-4 * np.abs(ref).max()
 
 
+def test_dot_product_attention_op_reference_kat():
+    """layers_test.py:375-387, literally (np.random.seed(0); b, q, h, d, k = 2, 3, 4, 5, 6; full additive bias), plus the
+    broadcast bias shapes the reference uses (mask-derived [b, 1, q, k]; relative-position [1, h, q, k]) and no bias."""
+    from mt3_b200 import layers
+    b, q, h, d, k = 2, 3, 4, 5, 6
+    np.random.seed(0)
+    query = np.random.randn(b, q, h, d)
+    key = np.random.randn(b, k, h, d)
+    value = np.random.randn(b, k, h, d)
+    bias = np.random.randn(b, h, q, k)
+    dev = lambda a: torch.from_numpy(a.astype(np.float32)).to(DEV)
+
+    def expected(bias_):
+        logits = np.einsum('bqhd,bkhd->bhqk', query, key) + (0.0 if bias_ is None else bias_)
+        w = np.exp(logits - logits.max(-1, keepdims=True))
+        w /= w.sum(-1, keepdims=True)
+        return np.einsum('bhqk,bkhd->bqhd', w, value)
+
+    for bias_ in (bias, None, bias[:, :1], bias[:1]):
+        got = layers.dot_product_attention(dev(query), dev(key), dev(value), bias=None if bias_ is None else dev(bias_)).cpu().numpy()
+        np.testing.assert_allclose(got, expected(bias_), atol=2e-6)
+    # a larger shape with head_dim 64 against the oracle's restatement, mask bias of -1e10 included (layers.py:297-322)
+    rng = np.random.default_rng(1)
+    Q, K_, V_ = (rng.standard_normal((3, 40, 6, 64)) * 0.3 for _ in range(3))
+    mask = np.tril(np.ones((40, 40)))[None, None]
+    mb = np.where(mask > 0, 0.0, -1e10)
+    got = layers.dot_product_attention(dev(Q), dev(K_), dev(V_), bias=dev(mb)).cpu().numpy()
+    np.testing.assert_allclose(got, O.dot_product_attention(Q, K_, V_, mb), atol=5e-6)
+    with pytest.raises(AssertionError):
+        layers.dot_product_attention(dev(query), dev(key[:, :, :2]), dev(value))
+
+
 def test_vocab_decode_kernel_random():
     from mt3_b200 import vocabularies
     # vocabularies_test.py:47-83, literally (GenericTokenVocabulary(32, extra_ids=4))

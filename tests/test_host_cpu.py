@@ -272,8 +272,8 @@ def test_bench_reference_arm_contract():
     assert other.returncode == 0 and other.stdout.strip() == ""
 
 
-@pytest.mark.parametrize("old_layout", [False, True])
-def test_t5x_checkpoint_reader_roundtrip(tmp_path, old_layout):
+@pytest.mark.parametrize("top_level_target", [False, True])
+def test_t5x_checkpoint_reader_roundtrip(tmp_path, top_level_target):
     """checkpoints.load_t5x_checkpoint reads the T5X directory layout (msgpack state with inlined small arrays and
     PLACEHOLDER:// references to gzip zarr-v2 arrays, chunked) back to the Flax tree paths weights.flatten expects."""
     from mt3_b200 import checkpoints, network, weights
@@ -281,10 +281,9 @@ def test_t5x_checkpoint_reader_roundtrip(tmp_path, old_layout):
                            mlp_dim=128, mlp_activations=('gelu', 'linear'))
     params = weights.synthetic_params(cfg, 5)
     d = tmp_path / "ckpt"
-    checkpoints.save_t5x_checkpoint(str(d), params, step=123, inline_below=200, max_chunk=48, old_layout=old_layout)
+    checkpoints.save_t5x_checkpoint(str(d), params, step=123, inline_below=200, max_chunk=48, top_level_target=top_level_target)
     assert (d / "checkpoint").exists()
-    root = "optimizer.target" if old_layout else "target"
-    zdir = d / f"{root}.decoder.logits_dense.kernel"
+    zdir = d / "target.decoder.logits_dense.kernel"              # T5X names arrays 'target.<dotted path>' in both variants
     assert (zdir / ".zarray").exists() and (zdir / "0.0").exists() and (zdir / "1.5").exists()      # 64x256 in 48x48 chunks
     got = weights.load(str(d))
     assert set(got) == set(params)

@@ -128,6 +128,86 @@ def test_midi_writer_roundtrip_header(tmp_path):
     assert f.read_bytes() == data
 
 
+def _parse_smf(data: bytes):
+    """A minimal, independent Standard MIDI File reader (SMF 1.0 spec): header, tracks, variable-length deltas, channel
+    voice / meta events, no running status assumed away (it is handled).  Returns (format, division, tracks) with each track
+    a list of (absolute tick, kind, channel, data1, data2)."""
+    assert data[:4] == b'MThd' and int.from_bytes(data[4:8], 'big') == 6
+    fmt, ntrk, div = (int.from_bytes(data[8 + 2 * i:10 + 2 * i], 'big') for i in range(3))
+    pos, tracks = 14, []
+    for _ in range(ntrk):
+        assert data[pos:pos + 4] == b'MTrk'
+        n = int.from_bytes(data[pos + 4:pos + 8], 'big')
+        body, pos = data[pos + 8:pos + 8 + n], pos + 8 + n
+        i, tick, status, ev = 0, 0, None, []
+        while i < len(body):
+            d = 0
+            while True:                                   # variable-length quantity
+                d = (d << 7) | (body[i] & 0x7F)
+                i += 1
+                if not body[i - 1] & 0x80:
+                    break
+            tick += d
+            if body[i] & 0x80:
+                status = body[i]
+                i += 1
+            if status == 0xFF:                            # meta: type, length, payload
+                mtype, mlen = body[i], body[i + 1]
+                ev.append((tick, 'meta', mtype, bytes(body[i + 2:i + 2 + mlen]), None))
+                i += 2 + mlen
+                continue
+            kind, ch = status & 0xF0, status & 0x0F
+            if kind in (0xC0, 0xD0):
+                ev.append((tick, kind, ch, body[i], None))
+                i += 1
+            else:
+                ev.append((tick, kind, ch, body[i], body[i + 1]))
+                i += 2
+        assert ev[-1][1] == 'meta' and ev[-1][2] == 0x2F  # end of track
+        tracks.append(ev)
+    assert pos == len(data)
+    return fmt, div, tracks
+
+
+def test_midi_writer_event_level_readback():
+    """Every note of the NoteSequence comes back from the written file: pitch, velocity, onset / offset ticks
+    (seconds x ticks_per_quarter x qpm / 60), program change per instrument track, drums on channel 9 (the notebook's
+    note_seq.sequence_proto_to_midi_file target format)."""
+    ns = nd.NoteSequence()
+    ns.add(0.00, 0.50, 60, 100, program=0)
+    ns.add(0.25, 0.75, 64, 90, program=0)
+    ns.add(0.50, 0.50, 67, 80, program=0)              # zero-length note still gets one tick
+    ns.add(0.10, 1.30, 40, 127, program=32)
+    ns.add(1.00, 1.01, 36, 127, is_drum=True)
+    ns.add(1.50, 1.51, 42, 127, is_drum=True)
+    nd.assign_instruments(ns)
+    qpm = 120.0
+    fmt, div, tracks = _parse_smf(nd.note_sequence_to_midi_bytes(ns, qpm=qpm))
+    assert fmt == 1 and div == ns.ticks_per_quarter == 220 and len(tracks) == 4     # tempo + 2 melodic + drums
+    assert tracks[0][0][:4] == (0, 'meta', 0x51, (500000).to_bytes(3, 'big'))        # 120 qpm
+    tps = div * qpm / 60.0
+    got = []
+    for tr in tracks[1:]:
+        program, open_notes = None, {}
+        for tick, kind, ch, d1, d2 in tr:
+            if kind == 0xC0:
+                program = d1
+            elif kind == 0x90 and d2 > 0:
+                open_notes.setdefault((ch, d1), []).append((tick, d2))
+            elif kind == 0x80 or (kind == 0x90 and d2 == 0):
+                on, vel = open_notes[(ch, d1)].pop(0)
+                got.append((d1, vel, on, tick, program, ch))
+        assert not any(open_notes.values())
+    want = []
+    for n in ns.notes:
+        on = int(round(n.start_time * tps))
+        off = max(on + 1, int(round(n.end_time * tps)))
+        ch = 9 if n.is_drum else (n.instrument % 16 if n.instrument % 16 != 9 else 10)
+        want.append((n.pitch, n.velocity, on, off, None if n.is_drum else n.program, ch))
+    assert sorted(got) == sorted(want)
+    assert {g[5] for g in got if g[4] is None} == {9}                                # drums: channel 9, no program change
+
+
 def test_unknown_spec():
     with pytest.raises(ValueError):
         nd.NoteDecoder(FULL, 'NoSuchSpec')
