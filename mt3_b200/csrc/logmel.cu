@@ -37,6 +37,7 @@ struct Frontend {
   int n_bins;              // fft/2 + 1
   float* d_window;         // [fft]
   float2* d_tw1024;        // [32 k1][32 lane]  W_1024^(lane*k1)
+  float2* d_tw_nc = nullptr;   // [R k1][32 lane]  W_NC^(lane*k1), NC = fft/2 = 32 R (fft 1024 / 4096 kernels)
   float2* d_rtw;           // [1024]            W_2048^k
   int* d_mel_bin0;         // [n_mel] first FFT bin of the tap window
   float* d_mel_w;          // [taps][n_mel] zero-padded band of the mel matrix
@@ -231,7 +232,183 @@ logmel2048_kernel(const float* __restrict__ audio, long long audio_stride, int n
   }
 }
 
-// Any power-of-two FFT size other than the reference's 2048 (BASELINE configs[3] sweeps 1024 / 2048 / 4096; the reference
+
+// ---------------------------------------------------------------------------------------------
+// The same warp-per-frame scheme for FFT sizes 1024 and 4096 (BASELINE configs[3] sweeps 1024 / 2048 / 4096 at hop 128; the
+// reference itself only ever uses 2048).  A real FFT of size 64 R is a complex FFT of NC = 32 R points, R in {16, 64}:
+//   stage 1   lane n2 holds z[32 n1 + n2], n1 < R, and runs an R-point radix-2 DIF FFT in registers (twiddles are
+//             immediates from a constant table), multiplies by W_NC^(n2 k1);
+//   transpose through a padded [R][33] shared-memory tile;
+//   stage 2   lane k1 (and k1 + 32 for R = 64; only 16 lanes for R = 16) runs the 32-point in-register FFT over n2 and
+//             writes Z[k1 + R k2] to a linear shared-memory array;
+//   untangle  X[k] = E[k] + W_N^k O[k] from Z[k] and Z[NC - k] read back from shared memory, magnitudes, banded mel, log.
+// ---------------------------------------------------------------------------------------------
+__constant__ float2 kTw64[32] = {{1.f, 0.f}, {0.99518472667219693f, 0.098017140329560604f}, {0.98078528040323043f, 0.19509032201612825f}, {0.95694033573220882f, 0.29028467725446233f}, {0.92387953251128674f, 0.38268343236508978f}, {0.88192126434835505f, 0.47139673682599764f}, {0.83146961230254524f, 0.55557023301960218f}, {0.77301045336273699f, 0.63439328416364549f}, {0.70710678118654757f, 0.70710678118654746f}, {0.63439328416364549f, 0.77301045336273699f}, {0.55557023301960229f, 0.83146961230254524f}, {0.47139673682599781f, 0.88192126434835494f}, {0.38268343236508984f, 0.92387953251128674f}, {0.29028467725446233f, 0.95694033573220894f}, {0.19509032201612833f, 0.98078528040323043f}, {0.09801714032956077f, 0.99518472667219682f}, {0.f, 1.f}, {-0.098017140329560645f, 0.99518472667219693f}, {-0.19509032201612819f, 0.98078528040323043f}, {-0.29028467725446216f, 0.95694033573220894f}, {-0.38268343236508973f, 0.92387953251128674f}, {-0.4713967368259977f, 0.88192126434835505f}, {-0.55557023301960196f, 0.83146961230254546f}, {-0.63439328416364538f, 0.7730104533627371f}, {-0.70710678118654746f, 0.70710678118654757f}, {-0.77301045336273699f, 0.63439328416364549f}, {-0.83146961230254535f, 0.55557023301960218f}, {-0.88192126434835494f, 0.47139673682599786f}, {-0.92387953251128674f, 0.38268343236508989f}, {-0.95694033573220882f, 0.29028467725446239f}, {-0.98078528040323043f, 0.19509032201612861f}, {-0.99518472667219682f, 0.098017140329560826f}};        // (cos, sin)(2 pi m / 64)
+
+template <int R> __host__ __device__ constexpr int brev_r(int r) {
+  int o = 0;
+  for (int b = 1, t = R >> 1; b < R; b <<= 1, t >>= 1)
+    if (r & b) o |= t;
+  return o;
+}
+
+// In-register R-point forward FFT, radix-2 decimation in frequency; output bit-reversed: x[r] holds X[brev_r<R>(r)].
+template <int R>
+__device__ __forceinline__ void fft_reg(float (&xr)[R], float (&xi)[R]) {
+#pragma unroll
+  for (int span = R / 2; span >= 1; span >>= 1) {
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      if ((a & span) == 0) {
+        const int b = a + span;
+        const int m = (a & (span - 1)) * (R / 2 / span);          // W_R^m
+        const float tr = xr[a] - xr[b];
+        const float ti = xi[a] - xi[b];
+        xr[a] += xr[b];
+        xi[a] += xi[b];
+        if (m == 0) {
+          xr[b] = tr;
+          xi[b] = ti;
+        } else if (m == R / 4) {  // * (-i)
+          xr[b] = ti;
+          xi[b] = -tr;
+        } else {
+          const float c = kTw64[m * (64 / R)].x, sn = kTw64[m * (64 / R)].y;
+          xr[b] = tr * c + ti * sn;
+          xi[b] = ti * c - tr * sn;
+        }
+      }
+    }
+  }
+}
+
+template <int R, int FRAMES_PER_CTA, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+logmel_r_kernel(const float* __restrict__ audio, long long audio_stride, int n_samples, int hop,
+                const int* __restrict__ n_valid_frames, int T, const float* __restrict__ window,
+                const float2* __restrict__ tw_nc, const float2* __restrict__ rtw, const int* __restrict__ mel_bin0,
+                const float* __restrict__ mel_wpad, int mel_taps, int mel_in_smem, int n_mel, float log_eps,
+                float* __restrict__ out) {
+  constexpr int NC = 32 * R, FFT = 2 * NC;
+  constexpr int J = (R + 31) / 32;                         // stage-2 passes per lane
+  constexpr int kT = R * 33;                               // transpose tile (float2)
+  constexpr int kScr = kT + NC;                            // per-warp scratch (float2): tile + linear Z
+  extern __shared__ __align__(16) float smem[];
+  const int chunk = (FRAMES_PER_CTA - 1) * hop + FFT;
+  const int chunk_pad = (chunk + 3) & ~3;
+  float* s_audio = smem;                                   // [chunk_pad]
+  float* s_win = s_audio + chunk_pad;                      // [FFT]
+  float2* s_tw = reinterpret_cast<float2*>(s_win + FFT);   // [R][32]  W_NC^(lane*k1)
+  float2* s_rtw = s_tw + R * 32;                           // [NC]     W_FFT^k
+  float2* s_scratch = s_rtw + NC;                          // [WARPS][kScr]
+  int* s_bin0 = reinterpret_cast<int*>(s_scratch + WARPS * kScr);          // [n_mel]
+  float* s_melw = reinterpret_cast<float*>(s_bin0 + ((n_mel + 3) & ~3));   // [mel_taps][n_mel] (if it fits)
+
+  const int seg = blockIdx.y;
+  const int t0 = blockIdx.x * FRAMES_PER_CTA;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  constexpr int NTHR = WARPS * 32;
+
+  const float* a = audio + (long long)seg * audio_stride;
+  const long long s0 = (long long)t0 * hop;
+  for (int i = tid; i < chunk; i += NTHR) {
+    const long long g = s0 + i;
+    s_audio[i] = (g < n_samples) ? __ldg(a + g) : 0.f;   // pad_end=True zeros
+  }
+  for (int i = tid; i < FFT; i += NTHR) s_win[i] = __ldg(window + i);
+  for (int i = tid; i < R * 32; i += NTHR) s_tw[i] = __ldg(tw_nc + i);
+  for (int i = tid; i < NC; i += NTHR) s_rtw[i] = __ldg(rtw + i);
+  for (int i = tid; i < n_mel; i += NTHR) s_bin0[i] = __ldg(mel_bin0 + i);
+  if (mel_in_smem)
+    for (int i = tid; i < mel_taps * n_mel; i += NTHR) s_melw[i] = __ldg(mel_wpad + i);
+  __syncthreads();
+  const float* melw = mel_in_smem ? s_melw : mel_wpad;
+
+  const int n_valid = n_valid_frames ? n_valid_frames[seg] : T;
+  float2* tile = s_scratch + warp * kScr;                  // [R][33]
+  float2* zs = tile + kT;                                  // [NC] Z in natural order
+  float* mag = reinterpret_cast<float*>(tile);             // reused after stage 2: [NC + 1] magnitudes (NC + 1 <= 2 kT)
+
+  for (int f = warp; f < FRAMES_PER_CTA; f += WARPS) {
+    const int t = t0 + f;
+    if (t >= T) break;
+    float* orow = out + ((long long)seg * T + t) * n_mel;
+    if (t >= n_valid) {                                    // feature-converter zero padding
+      for (int m = lane; m < n_mel; m += 32) orow[m] = 0.f;
+      continue;
+    }
+    {
+      float xr[R], xi[R];
+      const float2* fa = reinterpret_cast<const float2*>(s_audio + f * hop);
+      const float2* fw = reinterpret_cast<const float2*>(s_win);
+#pragma unroll
+      for (int n1 = 0; n1 < R; ++n1) {
+        const float2 v = fa[32 * n1 + lane];
+        const float2 w = fw[32 * n1 + lane];
+        xr[n1] = v.x * w.x;
+        xi[n1] = v.y * w.y;
+      }
+      fft_reg<R>(xr, xi);   // over n1: x[r] = A[k1 = brev_r(r)] for n2 = lane
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int k1 = brev_r<R>(r);
+        float vr = xr[r], vi = xi[r];
+        if (k1 != 0) {
+          const float2 w = s_tw[k1 * 32 + lane];
+          const float nr = vr * w.x - vi * w.y;
+          vi = vr * w.y + vi * w.x;
+          vr = nr;
+        }
+        tile[k1 * 33 + lane] = make_float2(vr, vi);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int k1 = lane + 32 * j;
+      if (k1 < R) {
+        float xr[32], xi[32];
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) {
+          const float2 v = tile[k1 * 33 + n2];
+          xr[n2] = v.x;
+          xi[n2] = v.y;
+        }
+        fft32(xr, xi);   // over n2: x[r] = Z[k1 + R * brev5(r)]
+#pragma unroll
+        for (int r = 0; r < 32; ++r) zs[k1 + R * brev5(r)] = make_float2(xr[r], xi[r]);
+      }
+    }
+    __syncwarp();
+    // untangle: X[k] = E[k] + W_FFT^k O[k], E = (Z[k] + conj Z[NC-k]) / 2, O = (Z[k] - conj Z[NC-k]) / (2i)
+    for (int k = lane; k < NC; k += 32) {
+      const float2 zk = zs[k];
+      if (k == 0) {
+        mag[0] = fabsf(zk.x + zk.y);
+        mag[NC] = fabsf(zk.x - zk.y);                      // Nyquist bin
+        continue;
+      }
+      const float2 zq = zs[NC - k];
+      const float er = 0.5f * (zk.x + zq.x), ei = 0.5f * (zk.y - zq.y);
+      const float orr = 0.5f * (zk.y + zq.y), oi = -0.5f * (zk.x - zq.x);
+      const float2 w = s_rtw[k];
+      const float Xr = er + (w.x * orr - w.y * oi);
+      const float Xi = ei + (w.x * oi + w.y * orr);
+      mag[k] = sqrtf(Xr * Xr + Xi * Xi);
+    }
+    __syncwarp();
+    for (int m = lane; m < n_mel; m += 32) {
+      const float* mg = mag + s_bin0[m];
+      float acc = 0.f;
+      for (int j = 0; j < mel_taps; ++j) acc = fmaf(mg[j], melw[j * n_mel + m], acc);
+      orow[m] = logf(acc <= 0.f ? log_eps : acc);      // safe_log: replace, not add
+    }
+    __syncwarp();
+  }
+}
+
+// Any OTHER power-of-two FFT size (BASELINE configs[3] sweeps 1024 / 2048 / 4096, which have the kernels above; the reference
 // itself only ever uses 2048, spectrograms.py:27-28).  Same arithmetic contract, plain structure: one CTA per frame,
 // real FFT of size N as a complex radix-2 DIF FFT of size N/2 in shared memory (output bit-reversed, read back through
 // the bit-reversed index), untangle, magnitude, banded mel, safe log.  Tables (window, W_N^k) come from global memory.
@@ -361,6 +538,16 @@ extern "C" int mt3_frontend_create(const mt3_frontend_config* cfg, const float* 
   FE_ALLOC_COPY(fe->d_window, win);
   FE_ALLOC_COPY(fe->d_tw1024, tw);
   FE_ALLOC_COPY(fe->d_rtw, rt);
+  if (fft == 1024 || fft == 4096) {
+    const int R = fft / 64, NC = fft / 2;
+    std::vector<float2> twn((size_t)R * 32);
+    for (int k1 = 0; k1 < R; ++k1)
+      for (int l = 0; l < 32; ++l) {
+        const double th = -2.0 * M_PI * (double)(k1 * l) / (double)NC;
+        twn[(size_t)k1 * 32 + l] = make_float2((float)cos(th), (float)sin(th));
+      }
+    FE_ALLOC_COPY(fe->d_tw_nc, twn);
+  }
   FE_ALLOC_COPY(fe->d_mel_bin0, bin0);
   FE_ALLOC_COPY(fe->d_mel_w, w);
 #undef FE_ALLOC_COPY
@@ -373,6 +560,7 @@ extern "C" int mt3_frontend_destroy(mt3_frontend* h) {
   Frontend* fe = reinterpret_cast<Frontend*>(h);
   cudaFree(fe->d_window);
   cudaFree(fe->d_tw1024);
+  cudaFree(fe->d_tw_nc);
   cudaFree(fe->d_rtw);
   cudaFree(fe->d_mel_bin0);
   cudaFree(fe->d_mel_w);
@@ -398,6 +586,30 @@ extern "C" int mt3_logmel_f32(const mt3_frontend* h, const float* audio, int64_t
   const Frontend* fe = reinterpret_cast<const Frontend*>(h);
   const int hop = fe->cfg.hop_width;
   const int T = (n_samples + hop - 1) / hop;
+  if ((fe->cfg.fft_size == 1024 || fe->cfg.fft_size == 4096) && fe->d_tw_nc) {
+    // warp-per-frame kernels for the other two sizes of BASELINE configs[3]
+    const int fft = fe->cfg.fft_size, n_mel = fe->cfg.num_mel_bins;
+    auto launch_r = [&](auto kern, int R, int F, int W) -> int {
+      const int NC = 32 * R;
+      const int chunk = (F - 1) * hop + fft;
+      const size_t base = (size_t)(((chunk + 3) & ~3) + fft) * sizeof(float) + (size_t)(R * 32 + NC) * sizeof(float2) +
+                          (size_t)W * (R * 33 + NC) * sizeof(float2) + (size_t)((n_mel + 3) & ~3) * sizeof(int);
+      const size_t mel_bytes = (size_t)fe->taps * n_mel * sizeof(float);
+      const int mel_in_smem = base + mel_bytes <= 220 * 1024;
+      const size_t smem = base + (mel_in_smem ? mel_bytes : 0);
+      MT3_REQUIRE(smem <= 227 * 1024, MT3_ERR_UNSUPPORTED, "mt3_logmel_f32: hop %d needs %zu B of shared memory", hop, smem);
+      MT3_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      dim3 grid((T + F - 1) / F, num_segments);
+      kern<<<grid, W * 32, smem, (cudaStream_t)stream>>>(audio, audio_stride, n_samples, hop, n_valid_frames, T, fe->d_window,
+                                                         fe->d_tw_nc, fe->d_rtw, fe->d_mel_bin0, fe->d_mel_w, fe->taps, mel_in_smem,
+                                                         n_mel, fe->cfg.log_eps, out);
+      return MT3_OK;
+    };
+    const int rc = fft == 1024 ? launch_r(logmel_r_kernel<16, 16, 8>, 16, 16, 8) : launch_r(logmel_r_kernel<64, 8, 4>, 64, 8, 4);
+    if (rc != MT3_OK) return rc;
+    MT3_LAUNCH_CHECK();
+    return MT3_OK;
+  }
   if (fe->cfg.fft_size != kFft) {
     const int fft = fe->cfg.fft_size, nc = fft / 2;
     int log2_nc = 0;
