@@ -37,11 +37,15 @@ struct Frontend {
   int n_bins;              // fft/2 + 1
   float* d_window;         // [fft]
   float2* d_tw1024;        // [32 k1][32 lane]  W_1024^(lane*k1)
+  int* d_mel_off = nullptr;    // [n_mel + 1] CSR offsets into d_mel_csr (compact per-mel-bin taps, no padding)
+  float* d_mel_csr = nullptr;  // [nnz span] weights of mel bin m for FFT bins bin0[m] .. bin0[m] + cnt - 1
+  int* d_mel_lo = nullptr;     // [n_mel] first non-zero FFT bin of mel bin m (un-clamped)
   float2* d_tw_nc = nullptr;   // [R k1][32 lane]  W_NC^(lane*k1), NC = fft/2 = 32 R (fft 1024 / 4096 kernels)
   float2* d_rtw;           // [1024]            W_2048^k
   int* d_mel_bin0;         // [n_mel] first FFT bin of the tap window
   float* d_mel_w;          // [taps][n_mel] zero-padded band of the mel matrix
   int taps;                // taps per mel bin (max support width)
+  int csr_len = 0;         // floats in d_mel_csr
   int nnz;
 };
 
@@ -286,8 +290,8 @@ template <int R, int FRAMES_PER_CTA, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 logmel_r_kernel(const float* __restrict__ audio, long long audio_stride, int n_samples, int hop,
                 const int* __restrict__ n_valid_frames, int T, const float* __restrict__ window,
-                const float2* __restrict__ tw_nc, const float2* __restrict__ rtw, const int* __restrict__ mel_bin0,
-                const float* __restrict__ mel_wpad, int mel_taps, int mel_in_smem, int n_mel, float log_eps,
+                const float2* __restrict__ tw_nc, const float2* __restrict__ rtw, const int* __restrict__ mel_lo,
+                const int* __restrict__ mel_off, const float* __restrict__ mel_csr, int mel_nnz, int n_mel, float log_eps,
                 float* __restrict__ out) {
   constexpr int NC = 32 * R, FFT = 2 * NC;
   constexpr int J = (R + 31) / 32;                         // stage-2 passes per lane
@@ -301,8 +305,10 @@ logmel_r_kernel(const float* __restrict__ audio, long long audio_stride, int n_s
   float2* s_tw = reinterpret_cast<float2*>(s_win + FFT);   // [R][32]  W_NC^(lane*k1)
   float2* s_rtw = s_tw + R * 32;                           // [NC]     W_FFT^k
   float2* s_scratch = s_rtw + NC;                          // [WARPS][kScr]
-  int* s_bin0 = reinterpret_cast<int*>(s_scratch + WARPS * kScr);          // [n_mel]
-  float* s_melw = reinterpret_cast<float*>(s_bin0 + ((n_mel + 3) & ~3));   // [mel_taps][n_mel] (if it fits)
+  // mel filterbank in compact CSR form (the fixed-tap padded band of the 2048 kernel would be 80 KB at FFT 4096)
+  int* s_lo = reinterpret_cast<int*>(s_scratch + WARPS * kScr);            // [n_mel] first FFT bin
+  int* s_off = s_lo + ((n_mel + 3) & ~3);                                  // [n_mel + 1]
+  float* s_csr = reinterpret_cast<float*>(s_off + ((n_mel + 4) & ~3));     // [mel_nnz]
 
   const int seg = blockIdx.y;
   const int t0 = blockIdx.x * FRAMES_PER_CTA;
@@ -319,11 +325,10 @@ logmel_r_kernel(const float* __restrict__ audio, long long audio_stride, int n_s
   for (int i = tid; i < FFT; i += NTHR) s_win[i] = __ldg(window + i);
   for (int i = tid; i < R * 32; i += NTHR) s_tw[i] = __ldg(tw_nc + i);
   for (int i = tid; i < NC; i += NTHR) s_rtw[i] = __ldg(rtw + i);
-  for (int i = tid; i < n_mel; i += NTHR) s_bin0[i] = __ldg(mel_bin0 + i);
-  if (mel_in_smem)
-    for (int i = tid; i < mel_taps * n_mel; i += NTHR) s_melw[i] = __ldg(mel_wpad + i);
+  for (int i = tid; i < n_mel; i += NTHR) s_lo[i] = __ldg(mel_lo + i);
+  for (int i = tid; i <= n_mel; i += NTHR) s_off[i] = __ldg(mel_off + i);
+  for (int i = tid; i < mel_nnz; i += NTHR) s_csr[i] = __ldg(mel_csr + i);
   __syncthreads();
-  const float* melw = mel_in_smem ? s_melw : mel_wpad;
 
   const int n_valid = n_valid_frames ? n_valid_frames[seg] : T;
   float2* tile = s_scratch + warp * kScr;                  // [R][33]
@@ -398,10 +403,12 @@ logmel_r_kernel(const float* __restrict__ audio, long long audio_stride, int n_s
       mag[k] = sqrtf(Xr * Xr + Xi * Xi);
     }
     __syncwarp();
-    for (int m = lane; m < n_mel; m += 32) {
-      const float* mg = mag + s_bin0[m];
+    for (int m = lane; m < n_mel; m += 32) {           // ascending FFT bin order, like the padded band
+      const float* mg = mag + s_lo[m];
+      const float* w = s_csr + s_off[m];
+      const int cnt = s_off[m + 1] - s_off[m];
       float acc = 0.f;
-      for (int j = 0; j < mel_taps; ++j) acc = fmaf(mg[j], melw[j * n_mel + m], acc);
+      for (int j = 0; j < cnt; ++j) acc = fmaf(mg[j], w[j], acc);
       orow[m] = logf(acc <= 0.f ? log_eps : acc);      // safe_log: replace, not add
     }
     __syncwarp();
@@ -531,6 +538,18 @@ extern "C" int mt3_frontend_create(const mt3_frontend_config* cfg, const float* 
   }
   fe->taps = taps;
   fe->nnz = nnz;
+  // compact form: per mel bin the span [lo, hi] only
+  std::vector<int> off(n_mel + 1, 0), lo0(n_mel, 0);
+  std::vector<float> csr;
+  for (int m = 0; m < n_mel; ++m) {
+    off[m] = (int)csr.size();
+    if (lo[m] >= 0) {
+      lo0[m] = lo[m];
+      for (int b = lo[m]; b <= hi[m]; ++b) csr.push_back(mel_matrix[(size_t)b * n_mel + m]);
+    }
+  }
+  off[n_mel] = (int)csr.size();
+  if (csr.empty()) csr.push_back(0.f);
 
 #define FE_ALLOC_COPY(dst, vec)                                                            \
   MT3_CUDA_CHECK(cudaMalloc((void**)&(dst), (vec).size() * sizeof((vec)[0])));            \
@@ -550,6 +569,10 @@ extern "C" int mt3_frontend_create(const mt3_frontend_config* cfg, const float* 
   }
   FE_ALLOC_COPY(fe->d_mel_bin0, bin0);
   FE_ALLOC_COPY(fe->d_mel_w, w);
+  FE_ALLOC_COPY(fe->d_mel_off, off);
+  FE_ALLOC_COPY(fe->d_mel_csr, csr);
+  FE_ALLOC_COPY(fe->d_mel_lo, lo0);
+  fe->csr_len = off[n_mel];
 #undef FE_ALLOC_COPY
   *out = reinterpret_cast<mt3_frontend*>(fe);
   return MT3_OK;
@@ -561,6 +584,9 @@ extern "C" int mt3_frontend_destroy(mt3_frontend* h) {
   cudaFree(fe->d_window);
   cudaFree(fe->d_tw1024);
   cudaFree(fe->d_tw_nc);
+  cudaFree(fe->d_mel_off);
+  cudaFree(fe->d_mel_csr);
+  cudaFree(fe->d_mel_lo);
   cudaFree(fe->d_rtw);
   cudaFree(fe->d_mel_bin0);
   cudaFree(fe->d_mel_w);
@@ -592,16 +618,14 @@ extern "C" int mt3_logmel_f32(const mt3_frontend* h, const float* audio, int64_t
     auto launch_r = [&](auto kern, int R, int F, int W) -> int {
       const int NC = 32 * R;
       const int chunk = (F - 1) * hop + fft;
-      const size_t base = (size_t)(((chunk + 3) & ~3) + fft) * sizeof(float) + (size_t)(R * 32 + NC) * sizeof(float2) +
-                          (size_t)W * (R * 33 + NC) * sizeof(float2) + (size_t)((n_mel + 3) & ~3) * sizeof(int);
-      const size_t mel_bytes = (size_t)fe->taps * n_mel * sizeof(float);
-      const int mel_in_smem = base + mel_bytes <= 220 * 1024;
-      const size_t smem = base + (mel_in_smem ? mel_bytes : 0);
+      const size_t smem = (size_t)(((chunk + 3) & ~3) + fft) * sizeof(float) + (size_t)(R * 32 + NC) * sizeof(float2) +
+                          (size_t)W * (R * 33 + NC) * sizeof(float2) + (size_t)(((n_mel + 3) & ~3) + ((n_mel + 4) & ~3)) * sizeof(int) +
+                          (size_t)fe->csr_len * sizeof(float);
       MT3_REQUIRE(smem <= 227 * 1024, MT3_ERR_UNSUPPORTED, "mt3_logmel_f32: hop %d needs %zu B of shared memory", hop, smem);
       MT3_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       dim3 grid((T + F - 1) / F, num_segments);
       kern<<<grid, W * 32, smem, (cudaStream_t)stream>>>(audio, audio_stride, n_samples, hop, n_valid_frames, T, fe->d_window,
-                                                         fe->d_tw_nc, fe->d_rtw, fe->d_mel_bin0, fe->d_mel_w, fe->taps, mel_in_smem,
+                                                         fe->d_tw_nc, fe->d_rtw, fe->d_mel_lo, fe->d_mel_off, fe->d_mel_csr, fe->csr_len,
                                                          n_mel, fe->cfg.log_eps, out);
       return MT3_OK;
     };
