@@ -10,9 +10,12 @@ tf.data / seqio / T5X are replaced by plain Python lists and the CUDA library:
     audio --host pad/split--> segments --H2D--> log-mel kernel --> encoder + greedy decoder
           --D2H--> token ids --vocabulary.decode_tf--> per-segment predictions
 
-A "dataset" here is a list of example dicts.  Known divergence from the notebook, recorded in
-DESIGN.md: greedy instead of T5X beam_search(num_decodes=1).  `__call__` returns a
-NoteSequence built by the host-side stitch in mt3_b200/note_decoding.py.
+A "dataset" here is a list of example dicts.  Divergences from the notebook, recorded in DESIGN.md:
+  * decode='greedy' by default; decode='beam1' runs T5X's beam_search bookkeeping at num_decodes=1, the reference's
+    decode_fn (models.py:127) -- the two differ when EOS is among the two best tokens without being decisive;
+  * kv_format=KV_F16 by default: the decoder's K/V rows are stored as fp16 (all arithmetic stays float32; logit error
+    ~1.5e-4 of the logit scale against the float64 oracle, bar 5e-4); kv_format=_lib.KV_F32 keeps them in float32;
+  * `__call__` returns a NoteSequence stand-in (mt3_b200.note_decoding.NoteSequence), not a note_seq protobuf.
 """
 from __future__ import annotations
 
@@ -32,7 +35,7 @@ class InferenceModel(object):
 
     def __init__(self, checkpoint_path, model_type='mt3', *, device='cuda:0', batch_size: int = 8,
                  gin_dir: Optional[str] = None, gemm_mode: int = _lib.GEMM_TF32X3, use_graph: bool = True,
-                 kv_format: int = _lib.KV_F32, decode: str = 'greedy'):
+                 kv_format: int = _lib.KV_F16, decode: str = 'greedy'):
         # Model Constants (notebook :175-185).
         if model_type == 'ismir2021':
             num_velocity_bins = 127
