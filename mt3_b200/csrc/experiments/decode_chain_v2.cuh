@@ -70,6 +70,7 @@ struct C2Args {
   float eps;
   const int* pos;
   unsigned long long* trace;             // debug timeline slot or null: [0] min start, [1] max end (ns)
+  int dbg_mode;                          // measurement only (mt3_debug_launch): 1 = stream without computing, 2 = compute without streaming
 };
 
 __device__ __forceinline__ void c2_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -94,7 +95,17 @@ dec_chain2_kernel(const C2Args a) {
   const int cluster_id = blockIdx.x / kC2Cluster;
   const int row0 = cluster_id * kC2Rows;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (a.trace && tid == 0) atomicMin(a.trace, gtime_ns());
+  const bool tr0 = a.trace != nullptr && tid == 0 && blockIdx.x == 0;
+  long long c0 = 0;
+  if (a.trace && tid == 0) {
+    atomicMin(a.trace, gtime_ns());
+    c0 = clock64();
+    if (blockIdx.x < 128 && (blockIdx.x & 15) == 0) {     // SM of rank 0 of each cluster, start offset of each cluster (ns / 8)
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      a.trace[8 + (blockIdx.x >> 4)] = smid;
+    }
+  }
 
   if (tid == 0) {
     for (int s = 0; s < kC2Slots; ++s) {
@@ -112,7 +123,7 @@ dec_chain2_kernel(const C2Args a) {
     int it = 0;
     for (int s = 0; s < a.n_stages; ++s) {
       const C2Stage& S = a.st[s];
-      if (lane == 0) {
+      if (lane == 0 && a.dbg_mode != 2) {
         for (int gi = 0; gi < S.n_gemm; ++gi) {
           const C2Gemm& G = S.g[gi];
           const int nch = G.K / G.KB;
@@ -154,6 +165,7 @@ dec_chain2_kernel(const C2Args a) {
       asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kC2Compute) : "memory");
+    if (tr0 && s == 0) a.trace[2] = (unsigned long long)(clock64() - c0);      // input rows staged
     if (S.g[0].norm || (S.n_gemm > 1 && S.g[1].norm)) {          // RMSNorm statistic of the input rows (layers.py:613-616)
       for (int r = warp; r < kC2Rows; r += kC2Compute / 32) {
         float ss = 0.f;
@@ -181,8 +193,9 @@ dec_chain2_kernel(const C2Args a) {
 
       for (int c = 0; c < nch; ++c, ++it) {
         const int slot = it % kC2Slots;
-        tc::mbar_wait(&full[slot], (it / kC2Slots) & 1);
-        if (active) {
+        if (a.dbg_mode != 2) tc::mbar_wait(&full[slot], (it / kC2Slots) & 1);
+        if (tr0 && it == 0) a.trace[3] = (unsigned long long)(clock64() - c0);  // first weight chunk landed
+        if (active && a.dbg_mode != 1) {
           const float* wt = reinterpret_cast<const float*>(ring + (size_t)slot * kC2SlotBytes) + (kp * 4) * ncp;
           const float* ap = As + c * G.KB + kp * 4;
           float4 av[kC2Rows], w0[4], w1[4];
@@ -209,6 +222,7 @@ dec_chain2_kernel(const C2Args a) {
         if (lane == 0) tc::mbar_arrive(&empty[slot]);
       }
 
+      if (tr0 && s == 0 && gi == 0) a.trace[4] = (unsigned long long)(clock64() - c0);   // multiply of stage 0 / GEMM 0 done
       // ---- k-parts through shared memory, summed in k-part order ----
       if (active) {
 #pragma unroll
@@ -270,6 +284,7 @@ dec_chain2_kernel(const C2Args a) {
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kC2Compute) : "memory");      // red / s_rs are reused by the next GEMM / stage
+      if (tr0 && s == 0 && gi == 0) a.trace[5] = (unsigned long long)(clock64() - c0);   // reduce + epilogue of stage 0 / GEMM 0 done
     }
     if (s + 1 < a.n_stages) {
       // stage outputs (global) become visible to the whole cluster before anyone reloads its input rows
@@ -277,7 +292,10 @@ dec_chain2_kernel(const C2Args a) {
       asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     }
   }
-  if (a.trace && tid == 0) atomicMax(a.trace + 1, gtime_ns());
+  if (a.trace && tid == 0) {
+    if (tr0) a.trace[6] = (unsigned long long)(clock64() - c0);
+    atomicMax(a.trace + 1, gtime_ns());
+  }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------
@@ -321,6 +339,7 @@ inline int launch_chain2(const C2Args& a, cudaStream_t s) {
   }
   const int n_clusters = cdiv(a.B, kC2Rows);
   cudaLaunchConfig_t cfg;
+  static bool printed = false;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(n_clusters * kC2Cluster);
   cfg.blockDim = dim3(kC2Threads);
@@ -331,6 +350,13 @@ inline int launch_chain2(const C2Args& a, cudaStream_t s) {
   attr[0].val.clusterDim.x = kC2Cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (!printed && getenv("MT3_CHAIN_INFO")) {
+    int n = -1;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, dec_chain2_kernel, &cfg);
+    fprintf(stderr, "[mt3] chain kernel: max active clusters of %d CTAs = %d (%s), smem %zu B, grid %d CTAs\n", kC2Cluster, n,
+            cudaGetErrorString(e), chain2_smem_bytes(), n_clusters * kC2Cluster);
+    printed = true;
+  }
   MT3_CUDA_CHECK(cudaLaunchKernelEx(&cfg, dec_chain2_kernel, a));
   MT3_LAUNCH_CHECK();
   return MT3_OK;

@@ -21,7 +21,6 @@
 #include "gemm_tc.cuh"
 #include "attention_tc.cuh"
 #include "decode.cuh"
-#include "decode_chain.cuh"
 #include "layers.cuh"
 
 namespace mt3 {
@@ -89,12 +88,6 @@ struct Model {
   bool fuse_q = true;             // MT3_DEC_FUSE=0: keep the self-attention out-projection and the cross-attention query
                                   // projection as two launches (default: one launch with a precomposed weight block)
   float *dy2 = nullptr, *dssq = nullptr;   // second residual-stream buffer (ping-pong) and [B][D/32] sum-of-squares partials
-  // cluster-owned GEMM chains (decode_chain.cuh): per-rank weight slices [16][K][nc(+pad)] of the decode-step weights
-  bool dec_chain = false;         // on when every stage shape fits the kernel; MT3_DEC_CHAIN=0 keeps the per-node GEMMs
-  float* slab_chain = nullptr;
-  struct ChainW { C2Gemm qkv, wo, wc1, wo_c, wi, wo2; };
-  std::vector<ChainW> chain_w;
-  C2Gemm chain_logits;
   bool tc = false, split3 = false;
   TcW t_w_in;
   Act a_x, a_h, a_ao, a_g, a_enc, a_qkv, a_vt; // tcgen05-path activation buffers (workspace); a_vt = per-head V^T
@@ -530,79 +523,6 @@ static int dec_layer_mlp(Model* m, DecBranch& b, int l) {
 // DEV [B,V]; greedy != 0 runs the argmax/bookkeeping kernel (tok_user optional), else only the position advances.
 // 7 launches per layer: [norm+QKV+KV-append] [self-attn] [out+residual | norm+q] [cross-attn] [out+residual]
 // [norm+gated-GELU MLP in] [MLP out+residual].
-// ---- the decode step with cluster-owned GEMM chains: 34 launches per step instead of 58 --------------------------
-static C2Stage c2_stage(const float* A, int lda, int K) {
-  C2Stage s;
-  memset(&s, 0, sizeof(s));
-  s.A = A; s.lda = lda; s.K0 = K; s.K = K; s.n_gemm = 1;
-  return s;
-}
-static C2Gemm c2_gemm(const C2Gemm& plan, int N, int norm, int epi, float* C, int ldc, const float* R = nullptr, int ldr = 0) {
-  C2Gemm g = plan;
-  g.norm = norm; g.epi = epi; g.C = C; g.ldc = ldc; g.R = R; g.ldr = ldr; g.n_split = N;
-  return g;
-}
-static void c2_kv(const Model* m, C2Gemm* g, int n_split, char* kv) {
-  g->n_split = n_split; g->kv = kv; g->kv_half = m->kv_half ? 1 : 0; g->kv_cap = m->L; g->kv_H = m->H;
-}
-static C2Args c2_args(Model* m, const char* name) {
-  C2Args a;
-  memset(&a, 0, sizeof(a));
-  a.B = m->B; a.eps = 1e-6f; a.pos = m->state; a.trace = trace_slot(m, name);
-  return a;
-}
-
-static int decode_step_chain(Model* m, float* logits, cudaStream_t s) {
-  const int D = m->D, Q = m->Q, F = m->F, V = m->V;
-  const Rows all{0, m->B};
-  float* y = m->dy;
-  {   // layer 0's q, k, v from the embedded input
-    C2Args a = c2_args(m, "chain_qkv0");
-    a.n_stages = 1;
-    a.st[0] = c2_stage(y, D, D);
-    a.st[0].g[0] = c2_gemm(m->chain_w[0].qkv, 3 * Q, 1, EPI_STORE, m->dq, Q);
-    c2_kv(m, &a.st[0].g[0], Q, kv_layer(m, m->skv, 0, m->L));
-    MT3_TRY(launch_chain2(a, s));
-  }
-  for (int l = 0; l < m->Ld; ++l) {
-    const Model::ChainW& w = m->chain_w[l];
-    MT3_TRY(launch_dec_attention(m, m->dq, kv_layer(m, m->skv, l, m->L), m->L, m->state, 1, m->dao, all, s));
-    {   // chain A: y' = y + o.Wo (+ per-tile sums of squares), q_raw = [o | y].[Wo.Wq ; Wq]
-      float* y_next = (y == m->dy) ? m->dy2 : m->dy;      // other CTAs still read y while y' is written: ping-pong
-      C2Args a = c2_args(m, "chain_out_q");
-      a.n_stages = 1;
-      a.st[0] = c2_stage(m->dao, Q, Q + D);
-      a.st[0].K0 = Q; a.st[0].A2 = y; a.st[0].lda2 = D;
-      a.st[0].n_gemm = 2;
-      a.st[0].g[0] = c2_gemm(w.wo, D, 0, EPI_RESIDUAL, y_next, D, y, D);
-      a.st[0].g[0].ssq_out = m->dssq; a.st[0].g[0].ssq_ld = D / 32;
-      a.st[0].g[1] = c2_gemm(w.wc1, Q, 0, EPI_STORE, m->dq, Q);
-      MT3_TRY(launch_chain2(a, s));
-      y = y_next;
-    }
-    MT3_TRY(launch_dec_attention(m, m->dq, kv_layer(m, m->ckv, l, m->T), m->T, nullptr, m->T, m->dao, all, s, m->dssq));
-    {   // chain B: cross out-projection -> gated-GELU MLP -> next layer's q, k, v (or the logits)
-      C2Args a = c2_args(m, "chain_mlp");
-      a.n_stages = 4;
-      a.st[0] = c2_stage(m->dao, Q, Q);
-      a.st[0].g[0] = c2_gemm(w.wo_c, D, 0, EPI_RESIDUAL, y, D, y, D);
-      a.st[1] = c2_stage(y, D, D);
-      a.st[1].g[0] = c2_gemm(w.wi, 2 * F, 1, EPI_GATED_GELU, m->dg, F);
-      a.st[2] = c2_stage(m->dg, F, F);
-      a.st[2].g[0] = c2_gemm(w.wo2, D, 0, EPI_RESIDUAL, y, D, y, D);
-      a.st[3] = c2_stage(y, D, D);
-      if (l + 1 < m->Ld) {
-        a.st[3].g[0] = c2_gemm(m->chain_w[l + 1].qkv, 3 * Q, 1, EPI_STORE, m->dq, Q);
-        c2_kv(m, &a.st[3].g[0], Q, kv_layer(m, m->skv, l + 1, m->L));
-      } else {
-        a.st[3].g[0] = c2_gemm(m->chain_logits, V, 1, EPI_STORE, logits, V);
-      }
-      MT3_TRY(launch_chain2(a, s));
-    }
-  }
-  return MT3_OK;
-}
-
 // loop_step: a step of mt3_generate's loop -- the decoder input m->dy was already written (by dec_embed before the first
 // step, by the previous step's argmax kernel afterwards), and this step's argmax kernel writes the next one.
 static int decode_step_impl(Model* m, const int* tok_in, float* logits, int greedy, int* tok_user, int use_finished,
@@ -610,18 +530,14 @@ static int decode_step_impl(Model* m, const int* tok_in, float* logits, int gree
   DecBranch b{Rows{0, m->B}, s, nullptr, MT3_ERR_UNSUPPORTED};
   if (loop_step) b.y = m->dy;
   else MT3_TRY(dec_embed(m, b, tok_in));
-  if (m->dec_chain) {
-    MT3_TRY(decode_step_chain(m, logits, s));
-  } else {
-    for (int l = 0; l < m->Ld; ++l) {
-      MT3_TRY(dec_layer_qkv(m, b, l));
-      MT3_TRY(dec_layer_self(m, b, l));
-      MT3_TRY(dec_layer_outq(m, b, l));
-      MT3_TRY(dec_layer_cross(m, b, l));
-      MT3_TRY(dec_layer_mlp(m, b, l));
-    }
-    MT3_TRY(dec_gemm(m, b.y, m->D, m->w_logits, m->V, m->D, 1, EPI_STORE, logits, m->V, m->V, nullptr, nullptr, b.rows, s));
+  for (int l = 0; l < m->Ld; ++l) {
+    MT3_TRY(dec_layer_qkv(m, b, l));
+    MT3_TRY(dec_layer_self(m, b, l));
+    MT3_TRY(dec_layer_outq(m, b, l));
+    MT3_TRY(dec_layer_cross(m, b, l));
+    MT3_TRY(dec_layer_mlp(m, b, l));
   }
+  MT3_TRY(dec_gemm(m, b.y, m->D, m->w_logits, m->V, m->D, 1, EPI_STORE, logits, m->V, m->V, nullptr, nullptr, b.rows, s));
   if (greedy == 2) {        // T5X beam_search bookkeeping at num_decodes = 1 (generate loop only)
     MT3_CUDA_CHECK(launch_kernel(beam1_step_kernel, dim3(m->B), dim3(256), 0, s, m->pdl, (const float*)logits, m->V, m->B, m->tok_cur,
                                  m->finished, tokens_ws, m->L, m->state, m->beam_f, m->beam_i, 0.6f, m->L, (const float*)m->emb,
@@ -864,45 +780,6 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
       if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: tc weight prep -> %s", cudaGetErrorString(e));
     }
   }
-  {
-    // cluster-owned GEMM chains: plan every stage shape, then slice the weights per rank
-    const char* e_ch = getenv("MT3_DEC_CHAIN");
-    m->dec_chain = !(e_ch && e_ch[0] == '0') && m->Ld % 2 == 0 && D % 32 == 0 && D / 32 == kC2Cluster;
-    m->chain_w.resize(m->Ld);
-    struct Item { const float* w; int K, N; C2Gemm* plan; };
-    std::vector<Item> items;
-    for (int i = 0; i < m->Ld && m->dec_chain; ++i) {
-      DecLayer& L = m->dec[i];
-      Model::ChainW& cw = m->chain_w[i];
-      items.push_back({L.wqkv, D, 3 * Q, &cw.qkv}); items.push_back({L.wo, Q, D, &cw.wo}); items.push_back({L.wc1, Q + D, Q, &cw.wc1});
-      items.push_back({L.wo_c, Q, D, &cw.wo_c}); items.push_back({L.wi, D, 2 * F, &cw.wi}); items.push_back({L.wo2, F, D, &cw.wo2});
-    }
-    items.push_back({m->w_logits, D, V, &m->chain_logits});
-    int64_t total = 0;
-    for (auto& it : items) {
-      memset(it.plan, 0, sizeof(C2Gemm));
-      if (!chain2_plan(it.N, it.K, it.plan)) { m->dec_chain = false; break; }
-      total += (int64_t)kC2Cluster * it.K * it.plan->ncp;
-    }
-    if (m->dec_chain && m->chain_w[0].wo.nc != 32) m->dec_chain = false;     // the per-tile sums of squares assume 32-column slices
-    if (rc == MT3_OK && m->dec_chain) {
-      e = cudaMalloc((void**)&m->slab_chain, (size_t)total * sizeof(float));
-      if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: cudaMalloc(chain slices) -> %s", cudaGetErrorString(e));
-      float* cur = m->slab_chain;
-      for (auto& it : items) {
-        if (rc != MT3_OK) break;
-        const long long n = (long long)kC2Cluster * it.K * it.plan->ncp;
-        chain2_slice_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(it.w, it.K, it.N, it.plan->nc, it.plan->ncp, cur);
-        if (cudaGetLastError() != cudaSuccess) { rc = fail(MT3_ERR_CUDA, "mt3_model_create: chain slice launch failed"); break; }
-        it.plan->W = cur;
-        cur += n;
-      }
-      if (rc == MT3_OK) {
-        e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: chain slice prep -> %s", cudaGetErrorString(e));
-      }
-    }
-  }
   if (rc == MT3_OK) {
     e = cudaMallocHost((void**)&m->h_flag, 4 * sizeof(int));
     if (e != cudaSuccess) rc = fail(MT3_ERR_CUDA, "mt3_model_create: cudaMallocHost -> %s", cudaGetErrorString(e));
@@ -910,7 +787,6 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
   if (rc != MT3_OK) {
     cudaFree(m->slab);
     cudaFree(m->slab_tc);
-    cudaFree(m->slab_chain);
     delete m;
     return rc;
   }
@@ -926,7 +802,6 @@ extern "C" int mt3_model_destroy(mt3_model* h) {
   if (m->h_flag) cudaFreeHost(m->h_flag);
   cudaFree(m->slab);
   cudaFree(m->slab_tc);
-  cudaFree(m->slab_chain);
   delete m;
   return MT3_OK;
 }
