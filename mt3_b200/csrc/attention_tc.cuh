@@ -62,7 +62,12 @@ __global__ void __launch_bounds__(kAtThreads, 1)
 enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                         const __grid_constant__ CUtensorMap tv_hi, const __grid_constant__ CUtensorMap tv_lo, int T, int H, int B,
                         float* __restrict__ out_hi, float* __restrict__ out_lo, int ldo, float* __restrict__ dbg_S,
-                        int variant, unsigned long long* __restrict__ dbg_t) {
+                        int variant, unsigned long long* __restrict__ dbg_t, int TK, int KS, float* __restrict__ part_o,
+                        float2* __restrict__ part_ml) {
+  // TK = keys per work item (<= 256), KS = key parts per query tile (T = KS * TK).  KS == 1: the item covers all keys and
+  // writes the normalised output.  KS > 1 (T = 512, ismir2021): an item covers keys [ks TK, (ks + 1) TK) and writes its
+  // UNNORMALISED O tile plus (row max, row sum) to part_o / part_ml; enc_attention_combine_kernel merges the parts
+  // (softmax is associative over key blocks: O = sum_k e^(m_k - m) O_k / sum_k e^(m_k - m) l_k).
   // dbg_S (bring-up tool only): raw S rows [B][H][T][T].  dbg_t (tool only): SM-clock stamps of CTA 0's first item ->
   // [0..31] and third item -> [32..63]: MMA thread in slots 0.., first softmax thread in slots 16..
   (void)variant;
@@ -90,9 +95,9 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Q = H * 64;
-  const int nchunk = (T + kAtKC - 1) / kAtKC;              // 1 or 2
+  const int nchunk = (TK + kAtKC - 1) / kAtKC;             // 1 or 2
   const int ntile = (T + kAtQ - 1) / kAtQ;
-  const int n_items = B * H * ntile;
+  const int n_items = B * H * ntile * KS;
   const int last_qc = nchunk * 4 - 1;                       // the quarter-chunk whose P.V MMAs are issued last
   constexpr uint32_t kSubBytes = kAtSub;
   const uint32_t lo_tiles = SPLIT3 ? 2u : 1u;
@@ -133,8 +138,9 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
       int it = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
         const uint32_t ph = it & 1, pph = ph ^ 1;
-        const int qt = item % ntile, h = (item / ntile) % H, b = item / (ntile * H);
-        const int row0 = b * T, q0 = qt * kAtQ;
+        const int ks = item % KS, it2 = item / KS;
+        const int qt = it2 % ntile, h = (it2 / ntile) % H, b = it2 / (ntile * H);
+        const int row0 = b * T, q0 = qt * kAtQ, koff = ks * TK;
         auto load_q = [&]() {
           tc::mbar_arrive_expect_tx(q_full, 2 * lo_tiles * kSubBytes);
           for (int sub = 0; sub < 2; ++sub) {
@@ -149,8 +155,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
         if (it > 0) tc::mbar_wait(&pv_done[3], pph);
         tc::mbar_arrive_expect_tx(&k_full[0], 2 * lo_tiles * kSubBytes);
         for (int sub = 0; sub < 2; ++sub) {
-          tc::tma_load_2d(slot[0] + sub * kAtSub, &tm_hi, &k_full[0], Q + h * 64 + sub * 32, row0);
-          if (SPLIT3) tc::tma_load_2d(slot[0] + (2 + sub) * kAtSub, &tm_lo, &k_full[0], Q + h * 64 + sub * 32, row0);
+          tc::tma_load_2d(slot[0] + sub * kAtSub, &tm_hi, &k_full[0], Q + h * 64 + sub * 32, row0 + koff);
+          if (SPLIT3) tc::tma_load_2d(slot[0] + (2 + sub) * kAtSub, &tm_lo, &k_full[0], Q + h * 64 + sub * 32, row0 + koff);
         }
         // Without P in tensor memory the Q region holds the previous item's P buffers until its last P.V MMA is done.
         if (it > 0) tc::mbar_wait(&pv_done[last_qc], pph);
@@ -159,8 +165,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
         if (nchunk > 1) {
           tc::mbar_arrive_expect_tx(&k_full[1], 2 * lo_tiles * kSubBytes);
           for (int sub = 0; sub < 2; ++sub) {
-            tc::tma_load_2d(slot[1] + sub * kAtSub, &tm_hi, &k_full[1], Q + h * 64 + sub * 32, row0 + kAtKC);
-            if (SPLIT3) tc::tma_load_2d(slot[1] + (2 + sub) * kAtSub, &tm_lo, &k_full[1], Q + h * 64 + sub * 32, row0 + kAtKC);
+            tc::tma_load_2d(slot[1] + sub * kAtSub, &tm_hi, &k_full[1], Q + h * 64 + sub * 32, row0 + koff + kAtKC);
+            if (SPLIT3) tc::tma_load_2d(slot[1] + (2 + sub) * kAtSub, &tm_lo, &k_full[1], Q + h * 64 + sub * 32, row0 + koff + kAtKC);
           }
         }
         // V^T chunks reuse the slots once every S MMA of THIS item has read K
@@ -169,8 +175,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
         for (int c = 0; c < nchunk; ++c) {
           tc::mbar_arrive_expect_tx(&v_full[c], 4 * lo_tiles * kVSub);
           for (int sub = 0; sub < 4; ++sub) {
-            tc::tma_load_2d(slot[c] + sub * kVSub, &tv_hi, &v_full[c], c * kAtKC + sub * 32, vrow);
-            if (SPLIT3) tc::tma_load_2d(slot[c] + (4 + sub) * kVSub, &tv_lo, &v_full[c], c * kAtKC + sub * 32, vrow);
+            tc::tma_load_2d(slot[c] + sub * kVSub, &tv_hi, &v_full[c], koff + c * kAtKC + sub * 32, vrow);
+            if (SPLIT3) tc::tma_load_2d(slot[c] + (4 + sub) * kVSub, &tv_lo, &v_full[c], koff + c * kAtKC + sub * 32, vrow);
           }
         }
       }
@@ -265,7 +271,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
     int it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
-      const int qt = item % ntile, h = (item / ntile) % H, b = item / (ntile * H);
+      const int ks = item % KS, it2 = item / KS;
+      const int qt = it2 % ntile, h = (it2 / ntile) % H, b = it2 / (ntile * H);
       const int row0 = b * T, q0 = qt * kAtQ;
       tslot = (dbg_t && blockIdx.x == 0 && threadIdx.x == 64 && (it == 0 || it == 2)) ? dbg_t + (it == 0 ? 0 : 32) : nullptr;
       tc::mbar_wait(s_done, ph);
@@ -274,17 +281,17 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
       float mx = -INFINITY;
       for (int c = 0; c < nchunk; ++c) {
         const int c0 = c * kAtKC + half * 64;                // this half's 64 columns of the chunk: both loads in flight
-        if (c0 >= T) continue;
+        if (c0 >= TK) continue;
         uint32_t v[32], w[32];
         tc::tmem_ld_32x32(tmem_S + lane_base + c0, v);
         tc::tmem_ld_32x32(tmem_S + lane_base + c0 + 32, w);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          if (c0 + j < T) mx = fmaxf(mx, __uint_as_float(v[j]));
-          if (c0 + 32 + j < T) mx = fmaxf(mx, __uint_as_float(w[j]));
+          if (c0 + j < TK) mx = fmaxf(mx, __uint_as_float(v[j]));
+          if (c0 + 32 + j < TK) mx = fmaxf(mx, __uint_as_float(w[j]));
         }
-        if (dbg_S && q0 + r < T) {
+        if (dbg_S && KS == 1 && q0 + r < T) {
           float* drow = dbg_S + (((long long)b * H + h) * T + q0 + r) * T + c0;
           for (int j = 0; j < 32; ++j) {
             if (c0 + j < T) drow[j] = __uint_as_float(v[j]);
@@ -313,7 +320,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             // ex2.approx (2 ulp) is ample: the value is rounded to tf32 (2^-11) on the next line
-            float e = (c0 + j < T) ? exp2f((__uint_as_float(v[j]) - mx) * 1.4426950408889634f) : 0.f;
+            float e = (c0 + j < TK) ? exp2f((__uint_as_float(v[j]) - mx) * 1.4426950408889634f) : 0.f;
             e = round_tf32(e);                              // exactly what the tensor core will read
             p[j] = e;
             sum += e;
@@ -349,7 +356,10 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
       tc::tc_fence_before();
       tc::mbar_arrive(o_free);                               // O is in registers: the next item may overwrite it
       asm volatile("bar.sync 1, 256;" ::: "memory");         // partial sums visible; previous item's staging reads done
-      const float inv = 1.0f / (s_sum[r] + s_sum[128 + r]);
+      const float rsum = s_sum[r] + s_sum[128 + r];
+      const float inv = KS == 1 ? 1.0f / rsum : 1.0f;       // key parts stay unnormalised: the combine kernel divides
+      if (KS > 1 && half == 0 && q0 + r < T)
+        part_ml[(((long long)ks * B + b) * H + h) * T + q0 + r] = make_float2(mx, rsum);
       // O row -> staging tile (rows of 256 B, 16-byte chunk c4 of row r stored at chunk c4 ^ (r & 7)), then coalesced stores
       {
         uint8_t* srow = reinterpret_cast<uint8_t*>(stage) + r * 256;
@@ -370,7 +380,9 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
         if (q < T) {
           const float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stage) + row * 256 + ((c4 ^ (row & 7)) << 4));
           const long long off = (long long)(row0 + q) * ldo + h * 64 + c4 * 4;
-          if (out_lo) {
+          if (KS > 1) {
+            *reinterpret_cast<float4*>(part_o + (long long)ks * B * T * ldo + off) = o;
+          } else if (out_lo) {
             float4 oh, ol;
             split_tf32(o.x, oh.x, ol.x); split_tf32(o.y, oh.y, ol.y); split_tf32(o.z, oh.z, ol.z); split_tf32(o.w, oh.w, ol.w);
             *reinterpret_cast<float4*>(out_hi + off) = oh;
@@ -389,13 +401,63 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_
   if (warp == 1) tc::tmem_dealloc(tmem_S, 512);
 }
 
+// Merge of KS key parts: out[row, h, :] = sum_k e^(m_k - m) O_k / sum_k e^(m_k - m) l_k.  One warp per (row, head).
+__global__ void enc_attention_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml, int B, int T, int H,
+                                             int KS, float* __restrict__ out_hi, float* __restrict__ out_lo) {
+  const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (b, t, h)
+  const int lane = threadIdx.x & 31;
+  if (item >= (long long)B * T * H) return;
+  const int h = (int)(item % H);
+  const long long row = item / H;                      // b * T + t
+  const int b = (int)(row / T), t = (int)(row % T);
+  const int ldo = H * 64;
+  float m = -INFINITY;
+  for (int k = 0; k < KS; ++k) m = fmaxf(m, part_ml[(((long long)k * B + b) * H + h) * T + t].x);
+  float den = 0.f;
+  float2 acc = make_float2(0.f, 0.f);
+  for (int k = 0; k < KS; ++k) {
+    const float2 ml = part_ml[(((long long)k * B + b) * H + h) * T + t];
+    const float w = expf(ml.x - m);
+    den = fmaf(w, ml.y, den);
+    const float2 o = *reinterpret_cast<const float2*>(part_o + (long long)k * B * T * ldo + row * ldo + h * 64 + lane * 2);
+    acc.x = fmaf(w, o.x, acc.x);
+    acc.y = fmaf(w, o.y, acc.y);
+  }
+  const float inv = 1.0f / den;
+  const float x = acc.x * inv, y = acc.y * inv;
+  const long long off = row * ldo + h * 64 + lane * 2;
+  if (out_lo) {
+    float xh, xl, yh, yl;
+    split_tf32(x, xh, xl);
+    split_tf32(y, yh, yl);
+    *reinterpret_cast<float2*>(out_hi + off) = make_float2(xh, yh);
+    *reinterpret_cast<float2*>(out_lo + off) = make_float2(xl, yl);
+  } else {
+    *reinterpret_cast<float2*>(out_hi + off) = make_float2(x, y);
+  }
+}
+
+// floats of scratch the key-split form needs (T > 256): KS unnormalised O tiles + KS (max, sum) pairs per (row, head)
+inline int64_t enc_attention_tc_scratch_floats(int B, int T, int H) {
+  if (T <= 2 * kAtKC) return 0;
+  const int64_t KS = T / (2 * kAtKC);
+  return KS * (int64_t)B * T * H * 64 + KS * (int64_t)B * H * T * 2;
+}
+inline bool enc_attention_tc_supported(int T) { return T % 8 == 0 && (T <= 2 * kAtKC || T % (2 * kAtKC) == 0); }
+
 // qkv_hi / qkv_lo: [B*T, 3*H*64] (q and k are read); vt: V^T [B*H*64, T] (box rows 64); out: [B*T, H*64]
-// (out_lo optional).  T <= 256, T % 8 == 0.
+// (out_lo optional).  T <= 256 (T % 8 == 0), or a multiple of 256 (ismir2021: 512) with `scratch`
+// (enc_attention_tc_scratch_floats) for the key-split form.
 inline int launch_enc_attention_tc(const TcOperand& qkv, const TcOperand& vt, int B, int T, int H, float* out_hi, float* out_lo,
                                    bool split3, cudaStream_t s, float* dbg_S = nullptr, int variant = 0,
-                                   unsigned long long* dbg_t = nullptr) {
-  MT3_REQUIRE(T <= 2 * kAtKC && T % 8 == 0, MT3_ERR_UNSUPPORTED, "tc attention: T=%d (needs T <= 256, multiple of 8)", T);
+                                   unsigned long long* dbg_t = nullptr, float* scratch = nullptr) {
+  MT3_REQUIRE(enc_attention_tc_supported(T), MT3_ERR_UNSUPPORTED, "tc attention: T=%d (needs T <= 256 and a multiple of 8, or a multiple of 256)", T);
   MT3_REQUIRE(!split3 || qkv.has_lo, MT3_ERR_BAD_ARG, "tc attention: TF32X3 needs hi/lo qkv");
+  const int KS = T <= 2 * kAtKC ? 1 : T / (2 * kAtKC);
+  const int TK = T / KS;
+  MT3_REQUIRE(KS == 1 || scratch != nullptr, MT3_ERR_WORKSPACE, "tc attention: T=%d needs the key-split scratch buffer", T);
+  float* part_o = scratch;
+  float2* part_ml = KS > 1 ? reinterpret_cast<float2*>(scratch + (int64_t)KS * B * T * H * 64) : nullptr;
   static bool attr_done = false;
   if (!attr_done) {
     MT3_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
@@ -408,13 +470,20 @@ inline int launch_enc_attention_tc(const TcOperand& qkv, const TcOperand& vt, in
     MT3_CUDA_CHECK(cudaGetDevice(&dev));
     MT3_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int n_items = B * H * cdiv(T, kAtQ);
+  const int n_items = B * H * cdiv(T, kAtQ) * KS;
   dim3 grid(n_items < sm_count ? n_items : sm_count);       // one persistent CTA per SM (198 KB of shared memory each)
   if (split3)
-    enc_attention_tc_kernel<true><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.lo, vt.hi, vt.lo, T, H, B, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t);
+    enc_attention_tc_kernel<true><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.lo, vt.hi, vt.lo, T, H, B, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t,
+                                                                    TK, KS, part_o, part_ml);
   else
-    enc_attention_tc_kernel<false><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.hi, vt.hi, vt.hi, T, H, B, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t);
+    enc_attention_tc_kernel<false><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.hi, vt.hi, vt.hi, T, H, B, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t,
+                                                                     TK, KS, part_o, part_ml);
   MT3_LAUNCH_CHECK();
+  if (KS > 1) {
+    const long long items = (long long)B * T * H;
+    enc_attention_combine_kernel<<<(unsigned)((items + 7) / 8), 256, 0, s>>>(part_o, part_ml, B, T, H, KS, out_hi, out_lo);
+    MT3_LAUNCH_CHECK();
+  }
   return MT3_OK;
 }
 

@@ -119,6 +119,7 @@ struct Model {
   char *ckv = nullptr, *skv = nullptr;   // head-major K/V (kv_elt bytes per element)
   float *dy = nullptr, *drstd = nullptr, *dq = nullptr, *dao = nullptr, *dg = nullptr, *dlogits = nullptr;
   int *tok_cur = nullptr, *finished = nullptr, *tokens = nullptr, *state = nullptr;
+  float* att_scratch = nullptr;   // key-split encoder attention (T > 256): unnormalised O parts + (max, sum) pairs
   float* beam_f = nullptr; int* beam_i = nullptr;   // beam-size-1 search state (MT3_GEN_BEAM1)
   float* dpartial = nullptr;      // split-K scratch of the non-cluster decode GEMM
   int dcounters_n = 0;
@@ -255,7 +256,7 @@ static int encode_tc_impl(Model* m, const float* x, float* encoded, cudaStream_t
   }
   const size_t attn_smem = (size_t)(32 * kHD + 32 * (m->T + 4) + 64 * 68) * sizeof(float);
   MT3_REQUIRE(attn_smem <= 200 * 1024, MT3_ERR_UNSUPPORTED, "encode: input_length %d too long for the attention kernel", m->T);
-  const bool tc_attn = m->tc_attn_ok && m->T <= 2 * kAtKC && m->T % 8 == 0;
+  const bool tc_attn = m->tc_attn_ok && enc_attention_tc_supported(m->T);
   for (int l = 0; l < m->Le; ++l) {
     const EncLayer& w = m->enc[l];
     row_rstd_kernel<<<cdiv(M, 8), 256, 0, s>>>(m->a_h.hi, m->a_h.lo, D, M, D, 1e-6f, m->rstd);
@@ -270,7 +271,8 @@ static int encode_tc_impl(Model* m, const float* x, float* encoded, cudaStream_t
       MT3_TRY(launch_tc_gemm(m->a_h.op, w.t_wqkv.op, a, m->split3, s));
     }
     if (tc_attn) {
-      MT3_TRY(launch_enc_attention_tc(m->a_qkv.op, m->a_vt.op, m->B, m->T, m->H, m->a_ao.hi, m->a_ao.lo, m->split3, s));
+      MT3_TRY(launch_enc_attention_tc(m->a_qkv.op, m->a_vt.op, m->B, m->T, m->H, m->a_ao.hi, m->a_ao.lo, m->split3, s, nullptr, 0, nullptr,
+                                      m->att_scratch));
     } else {
       enc_attention_kernel<<<dim3(cdiv(m->T, 32), m->H, m->B), 256, attn_smem, s>>>(m->qkv, 3 * Q, m->T, m->H, m->a_ao.hi,
                                                                                      m->a_ao.lo, Q);
@@ -810,7 +812,7 @@ namespace {
 struct WsLayout {
   int64_t x_hi, x_lo, h_lo, ao_lo, g_lo, enc_hi, enc_lo, qkv_lo, vt_hi, vt_lo;
   int64_t dy2, dssq;
-  int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, beam_f, beam_i, total;
+  int64_t h, rstd, qkv, ao, g, encoded, ckv, skv, dy, drstd, dq, dao, dg, dlogits, tok_cur, finished, tokens, state, dpartial, dcounters, beam_f, beam_i, att_scratch, total;
 };
 WsLayout ws_layout(const Model* m, int B, int T) {
   WsLayout w;
@@ -850,6 +852,7 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   w.state = take(64);
   w.dpartial = take((int64_t)16 * cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * kDecTileFloats * 4);   // up to 16 K chunks
   w.dcounters = take((int64_t)cdiv(std::max(std::max(3 * (int)Q, 2 * (int)F), (int)V), kDecBN) * 4);
+  w.att_scratch = take(m->tc ? enc_attention_tc_scratch_floats(B, T, m->H) * 4 : 0);
   w.beam_f = take((int64_t)B * 2 * 4);
   w.beam_i = take((int64_t)B * 4);
   w.total = off;
@@ -882,6 +885,7 @@ extern "C" int mt3_model_set_workspace(mt3_model* h, void* workspace, int64_t by
   m->finished = (int*)(b + w.finished); m->tokens = (int*)(b + w.tokens); m->state = (int*)(b + w.state);
   m->dpartial = (float*)(b + w.dpartial); m->dcounters = (int*)(b + w.dcounters);
   m->beam_f = (float*)(b + w.beam_f); m->beam_i = (int*)(b + w.beam_i);
+  m->att_scratch = (m->tc && enc_attention_tc_scratch_floats(batch, input_length, m->H) > 0) ? (float*)(b + w.att_scratch) : nullptr;
   m->dcounters_n = cdiv(std::max(std::max(3 * m->Q, 2 * m->F), m->V), kDecBN);
   m->have_cross = false;
   if (m->tc) {
@@ -1103,8 +1107,9 @@ extern "C" int mt3_debug_launch(mt3_model* h, int32_t kind, int32_t pos, int32_t
         break;
       }
       case MT3_K_ENC_ATTN: {
-        if (m->tc && m->tc_attn_ok && T <= 2 * kAtKC && T % 8 == 0) {
-          MT3_TRY(launch_enc_attention_tc(m->a_qkv.op, m->a_vt.op, B, T, m->H, m->a_ao.hi, m->a_ao.lo, m->split3, s));
+        if (m->tc && m->tc_attn_ok && enc_attention_tc_supported(T)) {
+          MT3_TRY(launch_enc_attention_tc(m->a_qkv.op, m->a_vt.op, B, T, m->H, m->a_ao.hi, m->a_ao.lo, m->split3, s, nullptr, 0, nullptr,
+                                          m->att_scratch));
           break;
         }
         MT3_TRY(set_attr_once());

@@ -264,6 +264,26 @@ def test_encoder_full_batch_vs_oracle(mt3_model):
     assert e_l <= LOGIT_TOL
 
 
+@pytest.mark.parametrize("attn", ["tc", "simt"])
+def test_encoder_parity_t512_ismir2021(attn, monkeypatch):
+    """ismir2021's input length (gin/ismir2021.gin:4): T = 512 keys do not fit one pass of the tcgen05 attention kernel (512 + 64
+    TMEM columns), so it runs two key parts of 256 and merges them (softmax is associative over key blocks); against the
+    float64 oracle, and against the exact-fp32 SIMT attention kernel on the same GEMMs."""
+    from mt3_b200 import _lib, network
+    monkeypatch.setenv("MT3_TC_ATTENTION", "1" if attn == "tc" else "0")
+    ocfg = O.T5Config(vocab_size=1664, num_encoder_layers=3, num_decoder_layers=1)
+    params = O.init_params(ocfg, seed=3, norm_scale_jitter=0.05)
+    cfg = _mt3_cfg(vocab_size=1664, num_encoder_layers=3, num_decoder_layers=1)
+    m = network.Transformer(cfg, params, device=DEV, max_batch=3, max_input_length=512, max_decode_length=8, gemm_mode=_lib.GEMM_TF32X3)
+    x = _inputs(3, t=512, seed=60)
+    enc = m.encode(torch.from_numpy(x).to(DEV)).cpu().numpy()
+    enc64 = O.encode(params, ocfg, x, np.float64)
+    scale = np.abs(enc64).max()
+    e = np.abs(enc - enc64).max() / scale
+    print(f"encoder T=512 [{attn}]: gpu vs fp64 {e:.3e}")
+    assert e <= 2e-5
+
+
 def test_model_tiny_golden_fixture():
     """Committed oracle fixture (mt3 layer sizes, 1+1 layers, T=32)."""
     from mt3_b200 import network
