@@ -57,13 +57,14 @@ constexpr int kAtThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 
 // still in item i, the TMA thread already streams item i+1: K chunk 0 as soon as the P.V MMAs that read V chunk 0 are
 // done, Q and K chunk 1 as soon as the last P.V MMA is done (the Q region doubles as the P buffers); the MMA thread
 // issues S(i+1) as soon as the softmax warps have finished reading S(i) out of TMEM, i.e. under the epilogue of i.
-template <bool SPLIT3>
+template <bool SPLIT3, bool KSPLIT>
 __global__ void __launch_bounds__(kAtThreads, 1)
 enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                         const __grid_constant__ CUtensorMap tv_hi, const __grid_constant__ CUtensorMap tv_lo, int T, int H, int B,
                         float* __restrict__ out_hi, float* __restrict__ out_lo, int ldo, float* __restrict__ dbg_S,
-                        int variant, unsigned long long* __restrict__ dbg_t, int TK, int KS, float* __restrict__ part_o,
+                        int variant, unsigned long long* __restrict__ dbg_t, int TK_arg, int KS_arg, float* __restrict__ part_o,
                         float2* __restrict__ part_ml) {
+  const int KS = KSPLIT ? KS_arg : 1, TK = KSPLIT ? TK_arg : T;       // compile-time 1 / T in the common single-pass form
   // TK = keys per work item (<= 256), KS = key parts per query tile (T = KS * TK).  KS == 1: the item covers all keys and
   // writes the normalised output.  KS > 1 (T = 512, ismir2021): an item covers keys [ks TK, (ks + 1) TK) and writes its
   // UNNORMALISED O tile plus (row max, row sum) to part_o / part_ml; enc_attention_combine_kernel merges the parts
@@ -460,8 +461,10 @@ inline int launch_enc_attention_tc(const TcOperand& qkv, const TcOperand& vt, in
   float2* part_ml = KS > 1 ? reinterpret_cast<float2*>(scratch + (int64_t)KS * B * T * H * 64) : nullptr;
   static bool attr_done = false;
   if (!attr_done) {
-    MT3_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
-    MT3_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmem));
     attr_done = true;
   }
   static int sm_count = 0;
@@ -472,12 +475,14 @@ inline int launch_enc_attention_tc(const TcOperand& qkv, const TcOperand& vt, in
   }
   const int n_items = B * H * cdiv(T, kAtQ) * KS;
   dim3 grid(n_items < sm_count ? n_items : sm_count);       // one persistent CTA per SM (198 KB of shared memory each)
-  if (split3)
-    enc_attention_tc_kernel<true><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.lo, vt.hi, vt.lo, T, H, B, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t,
-                                                                    TK, KS, part_o, part_ml);
-  else
-    enc_attention_tc_kernel<false><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, qkv.hi, vt.hi, vt.hi, T, H, B, out_hi, out_lo, H * 64, dbg_S, variant, dbg_t,
-                                                                     TK, KS, part_o, part_ml);
+#define MT3_AT_LAUNCH(S3, KSP, LO_Q, LO_V)                                                                                       \
+  enc_attention_tc_kernel<S3, KSP><<<grid, kAtThreads, kAtSmem, s>>>(qkv.hi, LO_Q, vt.hi, LO_V, T, H, B, out_hi, out_lo, H * 64, dbg_S, variant, \
+                                                                     dbg_t, TK, KS, part_o, part_ml)
+  if (split3 && KS > 1) MT3_AT_LAUNCH(true, true, qkv.lo, vt.lo);
+  else if (split3) MT3_AT_LAUNCH(true, false, qkv.lo, vt.lo);
+  else if (KS > 1) MT3_AT_LAUNCH(false, true, qkv.hi, vt.hi);
+  else MT3_AT_LAUNCH(false, false, qkv.hi, vt.hi);
+#undef MT3_AT_LAUNCH
   MT3_LAUNCH_CHECK();
   if (KS > 1) {
     const long long items = (long long)B * T * H;
