@@ -52,8 +52,6 @@ struct DecGemmArgs {
   // optional: per (row, 32-column tile) sum of squares of the OUTPUT row slice, [M][ssq_ld]; the consumer of the
   // output sums the N/32 partials in order and gets the RMSNorm statistic without re-reading the row
   float* ssq_out; int ssq_ld;
-  int pdl_late;                   // 1: release the dependent launch only after the multiply (its prologue overlaps the exchange /
-                                  // reduce tail instead of the whole kernel); 0: right after this kernel's own dependency wait
   unsigned long long* trace;      // debug timeline slot (mt3_debug_trace_step) or null: [0] min start, [1] max end (ns,
                                   // %globaltimer); [2..6] clock64 deltas of CTA (0,0) at its phase boundaries
 };
@@ -371,7 +369,7 @@ __device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int
                  "r"(ok ? 16 : 0) : "memory");
   }
   pdl_wait();
-  if (!p.pdl_late) pdl_trigger();
+  pdl_trigger();
   for (int idx = tid; idx < KC * 16; idx += NT) {
     const int row = idx / (KC / 4), kq = idx % (KC / 4);
     const bool ok = row < p.M;
@@ -442,7 +440,6 @@ __device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int
     }
   }
   if (tr0) p.trace[3] = (unsigned long long)(clock64() - c0);      // multiply done
-  if (p.pdl_late) pdl_trigger();
   asm volatile("barrier.cluster.wait.aligned;" ::: "memory");      // every peer is running
 
   const uint32_t red_base = tc::smem_u32(Red) + rank * (R * BN * 4);     // my slot [rank][..] in the owner's Red

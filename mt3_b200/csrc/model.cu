@@ -94,8 +94,6 @@ struct Model {
   bool pdl = false;               // MT3_PDL=1: programmatic dependent launch between all decode-step kernels
   bool pdl_attn = true;           // MT3_PDL=2 (default): only the attention launches (K/V prefetch under the preceding GEMM)
   bool pdl_gemm = false;          // MT3_PDL=4: only the GEMM launches; bits combine (6 = attention + GEMM); 0 = off
-  bool pdl_gemm_late = false;     // MT3_PDL=8: GEMMs that follow a GEMM launch programmatically, and a GEMM followed by a GEMM releases
-                                  // its dependent only after its multiply (10 = attention launches + this)
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
   bool kv_half = false;           // cfg.kv_cache_format == MT3_KV_F16: self and cross K/V rows stored as fp16
   int kv_elt = 4;                 // bytes per K/V element
@@ -400,10 +398,8 @@ static unsigned long long* trace_slot(Model* m, const char* name) {
 
 // Decode-step GEMM on M = B rows: split-K exact-fp32 cluster kernel with the RMSNorm statistic fused (decode.cuh), in every
 // gemm_mode (the tcgen05 variants of both rounds are correct but slower: csrc/experiments/).
-// after_gemm / before_gemm: the neighbours of this node in the step (MT3_PDL=8 chains GEMM -> GEMM edges programmatically)
 static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, int K, int norm, int epi, float* C, int ldc,
-                    int n_split, char* kv, const int* pos, const Rows& rows, cudaStream_t s, bool after_gemm = false,
-                    bool before_gemm = false) {
+                    int n_split, char* kv, const int* pos, const Rows& rows, cudaStream_t s) {
   for (int r0 = rows.begin; r0 < rows.begin + rows.count; r0 += kDecBM) {
     DecGemmArgs a;
     memset(&a, 0, sizeof(a));
@@ -418,12 +414,10 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
     }
     a.partial = m->dpartial;
     a.counters = m->dcounters;
-    a.pdl_late = (m->pdl_gemm_late && before_gemm) ? 1 : 0;
-    const bool pdl_launch = m->pdl_gemm || (m->pdl_gemm_late && after_gemm);
     a.trace = trace_slot(m, K == m->F ? "gemm_mlp_out" : (N == 2 * m->F ? "gemm_mlp_in" : (kv ? "gemm_qkv_append" : (N == m->V ? "gemm_logits" : (K == m->Q ? "gemm_attn_out" : "gemm_cross_q")))));
     int rc = MT3_ERR_UNSUPPORTED;
-    if (m->dec_cluster) rc = launch_dec_gemm_cluster(a, s, pdl_launch);
-    if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, s, pdl_launch);   // shapes the cluster kernel does not tile
+    if (m->dec_cluster) rc = launch_dec_gemm_cluster(a, s, m->pdl_gemm);
+    if (rc == MT3_ERR_UNSUPPORTED) rc = launch_dec_gemm(a, s, m->pdl_gemm);   // shapes the cluster kernel does not tile
     MT3_TRY(rc);
   }
   return MT3_OK;
@@ -492,7 +486,7 @@ static int dec_embed(Model* m, DecBranch& b, const int* tok_in) {
 // fused RMSNorm + QKV projection + K/V cache append (layers.py:238-240, :272-289)
 static int dec_layer_qkv(Model* m, DecBranch& b, int l) {
   return dec_gemm(m, b.y, m->D, m->dec[l].wqkv, 3 * m->Q, m->D, 1, EPI_STORE, m->dq, m->Q, m->Q, kv_layer(m, m->skv, l, m->L), m->state,
-                  b.rows, b.s, /*after_gemm=*/l > 0, /*before_gemm=*/false);
+                  b.rows, b.s);
 }
 static int dec_layer_self(Model* m, DecBranch& b, int l) {
   return launch_dec_attention(m, m->dq, kv_layer(m, m->skv, l, m->L), m->L, m->state, 1, m->dao, b.rows, b.s);
@@ -521,9 +515,9 @@ static int dec_layer_cross(Model* m, DecBranch& b, int l) {
 static int dec_layer_mlp(Model* m, DecBranch& b, int l) {
   const DecLayer& w = m->dec[l];
   const int D = m->D, Q = m->Q, F = m->F;
-  MT3_TRY(dec_gemm(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s, false, true));
-  MT3_TRY(dec_gemm(m, b.y, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr, nullptr, b.rows, b.s, true, true));
-  MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s, true, true));
+  MT3_TRY(dec_gemm(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s));
+  MT3_TRY(dec_gemm(m, b.y, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr, nullptr, b.rows, b.s));
+  MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s));
   return MT3_OK;
 }
 
@@ -545,7 +539,7 @@ static int decode_step_impl(Model* m, const int* tok_in, float* logits, int gree
     MT3_TRY(dec_layer_cross(m, b, l));
     MT3_TRY(dec_layer_mlp(m, b, l));
   }
-  MT3_TRY(dec_gemm(m, b.y, m->D, m->w_logits, m->V, m->D, 1, EPI_STORE, logits, m->V, m->V, nullptr, nullptr, b.rows, s, true, false));
+  MT3_TRY(dec_gemm(m, b.y, m->D, m->w_logits, m->V, m->D, 1, EPI_STORE, logits, m->V, m->V, nullptr, nullptr, b.rows, s));
   if (greedy == 2) {        // T5X beam_search bookkeeping at num_decodes = 1 (generate loop only)
     MT3_CUDA_CHECK(launch_kernel(beam1_step_kernel, dim3(m->B), dim3(256), 0, s, m->pdl, (const float*)logits, m->V, m->B, m->tok_cur,
                                  m->finished, tokens_ws, m->L, m->state, m->beam_f, m->beam_i, 0.6f, m->L, (const float*)m->emb,
@@ -757,7 +751,6 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     m->pdl = (pdl_bits & 1) != 0;
     m->pdl_attn = (pdl_bits & 3) != 0;
     m->pdl_gemm = (pdl_bits & 5) != 0;
-    m->pdl_gemm_late = (pdl_bits & 8) != 0;
     const char* e_fuse = getenv("MT3_DEC_FUSE");
     m->fuse_q = !(e_fuse && e_fuse[0] == '0');
     const char* e_clu = getenv("MT3_DEC_CLUSTER");
