@@ -653,9 +653,8 @@ extern "C" int mt3_logmel_f32(const mt3_frontend* h, const float* audio, int64_t
     return MT3_OK;
   }
   // 12 frames per CTA on 6 warps (~111 KB of smem incl. all tables, two CTAs per SM = 12 warps per SM, 168 registers per
-  // thread): 137 us per 64 segments; MT3_LOGMEL_CFG=0 selects the earlier 16 frames on 4 warps (8 warps per SM, 175 us)
-  static const int cfg_sel = [] { const char* e = getenv("MT3_LOGMEL_CFG"); return e ? atoi(e) : 1; }();
-  static bool attr_set[2] = {false, false};
+  // thread): 134 us per 64 segments (the earlier 16 frames on 4 warps: 175 us)
+  static bool attr_set = false;
   const int n_mel = fe->cfg.num_mel_bins;
   auto launch = [&](auto kern, int F, int W) -> int {
     const int chunk = (F - 1) * hop + kFft;
@@ -665,9 +664,9 @@ extern "C" int mt3_logmel_f32(const mt3_frontend* h, const float* audio, int64_t
     const int mel_in_smem = base + mel_bytes <= 113 * 1024;
     const size_t smem = base + (mel_in_smem ? mel_bytes : 0);
     MT3_REQUIRE(smem <= 227 * 1024, MT3_ERR_UNSUPPORTED, "mt3_logmel_f32: hop %d needs %zu B of shared memory", hop, smem);
-    if (!attr_set[W == 6]) {
+    if (!attr_set) {
       MT3_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      attr_set[W == 6] = true;
+      attr_set = true;
     }
     dim3 grid((T + F - 1) / F, num_segments);
     kern<<<grid, W * 32, smem, (cudaStream_t)stream>>>(audio, audio_stride, n_samples, hop, n_valid_frames, T, fe->d_window,
@@ -675,7 +674,7 @@ extern "C" int mt3_logmel_f32(const mt3_frontend* h, const float* audio, int64_t
                                                        mel_in_smem, n_mel, fe->cfg.log_eps, out);
     return MT3_OK;
   };
-  const int rc = cfg_sel == 1 ? launch(logmel2048_kernel<12, 6>, 12, 6) : launch(logmel2048_kernel<16, 4>, 16, 4);
+  const int rc = launch(logmel2048_kernel<12, 6>, 12, 6);
   if (rc != MT3_OK) return rc;
   MT3_LAUNCH_CHECK();
   return MT3_OK;

@@ -579,13 +579,18 @@ static void select_graph(Model* m, int mode = 1) {
   }
 }
 
-static int ensure_graph(Model* m, int mode) {       // mode: 1 greedy, 2 beam-size-1 search
-  if (m->graph_mode != mode) select_graph(m, mode);
+// mode: 1 greedy, 2 beam-size-1 search; nsteps consecutive decode steps per graph (the position lives on the device, so a
+// graph of 16 steps is the single-step graph 16 times over: one graph launch and its ~3 us of inter-launch latency per 16 steps)
+static int ensure_graph(Model* m, int mode, int nsteps = 1) {
+  const int key = mode | (nsteps << 8);
+  if (m->graph_mode != key) select_graph(m, key);
   if (m->graph_exec) return MT3_OK;
   if (!m->cap_stream) MT3_CUDA_CHECK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
   const uint64_t before = g_launch_count.load();
   MT3_CUDA_CHECK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
-  int r = decode_step_impl(m, m->tok_cur, m->dlogits, mode, nullptr, 1, m->tokens, m->cap_stream, true);
+  int r = MT3_OK;
+  for (int i = 0; i < nsteps && r == MT3_OK; ++i)
+    r = decode_step_impl(m, m->tok_cur, m->dlogits, mode, nullptr, 1, m->tokens, m->cap_stream, true);
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(m->cap_stream, &g);
   if (r != MT3_OK) {
@@ -597,13 +602,13 @@ static int ensure_graph(Model* m, int mode) {       // mode: 1 greedy, 2 beam-si
   m->graph_kernels = g_launch_count.load() - before;
   g_launch_count.fetch_sub(m->graph_kernels);   // capture does not execute
   MT3_CUDA_CHECK(cudaGraphInstantiate(&m->graph_exec, m->graph, 0));
-  if (m->graphs.size() >= 8) {                  // bound the cache: forget everything but the new graph
+  if (m->graphs.size() >= 12) {                 // bound the cache: forget everything but the new graph
     const Model::StepGraph keep{m->graph, m->graph_exec, m->graph_kernels};
     m->graph = nullptr; m->graph_exec = nullptr;
     drop_graphs(m);
     m->graph = keep.g; m->graph_exec = keep.e; m->graph_kernels = keep.kernels;
   }
-  m->graphs[std::make_tuple((const void*)m->ws, m->B, m->T, mode)] = Model::StepGraph{m->graph, m->graph_exec, m->graph_kernels};
+  m->graphs[std::make_tuple((const void*)m->ws, m->B, m->T, key)] = Model::StepGraph{m->graph, m->graph_exec, m->graph_kernels};
   return MT3_OK;
 }
 
@@ -960,22 +965,40 @@ extern "C" int mt3_generate(mt3_model* h, const float* x, int32_t num_steps, int
     MT3_CUDA_CHECK(cudaStreamSynchronize(s));        // `init` is stack-owned pageable memory
     MT3_CUDA_CHECK(cudaMemsetAsync(m->beam_i, 0, (size_t)m->B * sizeof(int), s));
   }
-  if (use_graph) MT3_TRY(ensure_graph(m, mode));
+  constexpr int kBlock = 16;                    // steps per graph launch (and between two polls of the all-finished flag)
+  cudaGraphExec_t g1 = nullptr, gN = nullptr;
+  uint64_t k1 = 0, kN = 0;
+  if (use_graph) {
+    if (num_steps >= kBlock) {
+      MT3_TRY(ensure_graph(m, mode, kBlock));
+      gN = m->graph_exec; kN = m->graph_kernels;
+    }
+    if (num_steps % kBlock != 0) {
+      MT3_TRY(ensure_graph(m, mode, 1));
+      g1 = m->graph_exec; k1 = m->graph_kernels;
+    }
+  }
   if (num_steps > 0) {     // decoder input of step 0: BOS (tok_cur was zeroed by cross_kv) at position 0; later ones come from the argmax kernel
     DecBranch b0{Rows{0, m->B}, s, nullptr, MT3_ERR_UNSUPPORTED};
     MT3_TRY(dec_embed(m, b0, m->tok_cur));
   }
   int ran = 0;
-  for (int step = 0; step < num_steps; ++step) {
-    if (use_graph) {
-      MT3_CUDA_CHECK(cudaGraphLaunch(m->graph_exec, s));
-      count_launch(m->graph_kernels);
+  for (int step = 0; step < num_steps;) {
+    int n = 1;
+    if (use_graph && gN && num_steps - step >= kBlock) {
+      MT3_CUDA_CHECK(cudaGraphLaunch(gN, s));
+      count_launch(kN);
+      n = kBlock;
+    } else if (use_graph) {
+      MT3_CUDA_CHECK(cudaGraphLaunch(g1, s));
+      count_launch(k1);
     } else {
       MT3_TRY(decode_step_impl(m, m->tok_cur, m->dlogits, mode, nullptr, 1, m->tokens, s, true));
     }
-    ++ran;
-    m->host_pos += 1;
-    if (stop && ((step & 15) == 15 || step == num_steps - 1)) {
+    step += n;
+    ran += n;
+    m->host_pos += n;
+    if (stop && ((step & 15) == 0 || step == num_steps)) {
       MT3_CUDA_CHECK(cudaMemcpyAsync(m->h_flag, m->state + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
       MT3_CUDA_CHECK(cudaStreamSynchronize(s));
       if (m->h_flag[0]) break;
