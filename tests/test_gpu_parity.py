@@ -677,6 +677,17 @@ def test_logmel_other_fft_sizes(fft):
     z = spectral_ops.compute_logmel(torch.zeros(1000, device=DEV), lo_hz=20.0, hi_hz=7600.0, bins=bins, fft_size=fft,
                                     overlap=1.0 - hop / fft).cpu().numpy()
     np.testing.assert_allclose(z, np.log(np.float32(1e-5)), rtol=1e-6)
+    # frames depend only on their own window: a long stream cut at a frame boundary gives the same frames (bit-exact) as the
+    # whole stream wherever the window does not cross the cut -- exercises every frame slot of a CTA and many CTAs
+    long = np.concatenate([O.sine_mix(40 * 1024, 950), np.random.default_rng(2).uniform(-0.5, 0.5, 3000).astype(np.float32)])
+    whole = spectral_ops.compute_logmel(torch.from_numpy(long).to(DEV), lo_hz=20.0, hi_hz=7600.0, bins=bins, fft_size=fft,
+                                        overlap=1.0 - hop / fft)
+    cut = 100 * hop
+    tail = spectral_ops.compute_logmel(torch.from_numpy(long[cut:]).to(DEV), lo_hz=20.0, hi_hz=7600.0, bins=bins, fft_size=fft,
+                                       overlap=1.0 - hop / fft)
+    assert torch.equal(whole[100:], tail)
+    _mel_close(whole.cpu().numpy(), O.compute_logmel(long.astype(np.float64), bins=bins, lo_hz=20.0, hi_hz=7600.0, fft_size=fft, hop=hop,
+                                                      dtype=np.float64))
 
 
 def test_baseline_config5_long_form_three_minutes():
