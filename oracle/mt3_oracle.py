@@ -29,6 +29,15 @@ PARITY STATUS
     `t5x` decode loop; setup.py:39-56 lists bare names / git HEADs) and none of
     them is installable here.  Those pieces are restated from their published
     algorithms (noted "[3p]" below) and anchored on the reference's call sites.
+  * CROSS-CHECKED (tests/test_oracle_crosscheck.py) against independent
+    third-party implementations of the same published algorithms that ARE in this
+    image -- not the reference, but a shared misreading would have to be shared
+    with them: the HTK mel matrix == transformers.audio_utils.mel_filter_bank
+    (triangles in mel space) to 2e-13; the STFT magnitude (periodic Hann, hop 128,
+    pad_end) == torch.stft to 1e-11 at FFT 1024 / 2048 / 4096; tanh-GELU and
+    un-scaled biased attention == torch; one encoder layer and one decoder layer
+    (pre-RMSNorm, un-scaled attention, gated-GELU MLP) == transformers' T5 v1.1
+    T5Block with the same weights to 1e-6 (its RMS statistic is float32).
 
 Every function takes `dtype` (np.float32 = what the reference computes in,
 np.float64 = the truth the CUDA path and the fp32 oracle are both judged by).
