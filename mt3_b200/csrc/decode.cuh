@@ -5,14 +5,13 @@
 // cross-attention K/V rows (HBM).  The kernels:
 //
 //  sgemm_dec_cluster_kernel   exact-fp32 GEMM for M <= 64 rows, the default.  One thread-block CLUSTER (8 CTAs; 16 for
-//                      the long-K MLP-out projection) per 64 x 32 output tile splits K; inside a CTA two groups of four
-//                      warps split the CTA's K chunk once more (latency hiding: 2-4 warps per scheduler) and are summed
-//                      through shared memory; the multiply loop issues packed FFMA2 (two fp32 FMAs per issue slot).
+//                      the long-K MLP-out projection) per 64 x 32 output tile splits K; 4 x 4 register tiles, packed FFMA2.
 //                      Every CTA pushes the rows owned by rank r into rank r's shared memory and, after one cluster
 //                      barrier, each rank sums its rows in rank order (deterministic) and runs the fused epilogue:
 //                      RMSNorm factor (statistic computed from the A tiles the GEMM loads anyway, layers.py:613-616),
 //                      residual, gated GELU, head-major KV-cache append (fp32 or fp16 cache), per-tile sums of squares
-//                      of the output.
+//                      of the output.  (A second warp group per CTA splitting the K chunk once more is written in the
+//                      body as G = 2 and measured slower: kDecGroups below.)
 //  sgemm_dec_cluster2_kernel  two such GEMMs that read the same inputs in one launch (out-projection + the
 //                      cross-attention query projection through a precomposed weight block).
 //  sgemm_dec_kernel    the same GEMM without clusters (MT3_DEC_CLUSTER=0 / shapes the cluster kernel does not
