@@ -172,6 +172,11 @@ def cpu_port_sample(params, audio, nb, dec_steps, budget_s):
     return nb * SEG_SECONDS / full, cores, desc, 1000.0 * (t_fixed + t_dec)
 
 
+def KV_FORMATS():
+    from mt3_b200 import _lib
+    return {'f32': _lib.KV_F32, 'f16': _lib.KV_F16, 'p24': _lib.KV_P24}
+
+
 def load_traffic(kernel):
     """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/), or None."""
     try:
@@ -249,7 +254,7 @@ def run_ours(args):
     # ---- weights: rank 0 draws them, ONE NCCL broadcast at load (north_star) -------------------
     # (InferenceModel.restore_from_checkpoint: only rank 0 materialises the checkpoint, then broadcast_params)
     gm = {'simt': _lib.GEMM_FP32_SIMT, 'tf32x3': _lib.GEMM_TF32X3, 'tf32': _lib.GEMM_TF32}[args.gemm_mode]
-    kvf = {'f32': _lib.KV_F32, 'f16': _lib.KV_F16}[args.kv]
+    kvf = KV_FORMATS()[args.kv]
     im = inference.InferenceModel('synthetic:0', 'mt3', device=dev, batch_size=B, use_graph=True, gemm_mode=gm, kv_format=kvf)
 
     # ---- inputs: contiguous shard of the global segment list ---------------------------------
@@ -312,12 +317,11 @@ def run_ours(args):
         e2e_times.append(time.perf_counter() - t0)
     e2e_ms = 1000.0 * float(np.median(e2e_times))
 
-    # ---- the same device-resident pass with the OTHER K/V storage format (fp32 rows when the headline uses fp16) -------
-    alt_ms = None
-    if not args.no_alt_kv:
-        alt_name = 'f32' if args.kv == 'f16' else 'f16'
+    # ---- the same device-resident pass with the OTHER K/V storage formats (fp32 and 24-bit rows when the headline uses fp16) ----
+    alt_ms = {}
+    for alt_name in ([] if args.no_alt_kv else [n for n in ('f32', 'p24', 'f16') if n != args.kv]):
         im_alt = inference.InferenceModel('synthetic:0', 'mt3', device=dev, batch_size=B, use_graph=True, gemm_mode=gm,
-                                          kv_format={'f32': _lib.KV_F32, 'f16': _lib.KV_F16}[alt_name])
+                                          kv_format=KV_FORMATS()[alt_name])
 
         def alt_pass():
             spec = spectrograms.compute_spectrogram(audio_dev, im_alt.spectrogram_config)
@@ -334,7 +338,7 @@ def run_ours(args):
             e1.record()
             torch.cuda.synchronize(dev)
             ts.append(e0.elapsed_time(e1))
-        alt_ms = float(np.mean(ts))
+        alt_ms[alt_name] = float(np.mean(ts))
         del im_alt
         torch.cuda.empty_cache()
 
@@ -358,11 +362,12 @@ def run_ours(args):
 
     # ---- all-gather of the decoded token streams at the end (north_star) -----------------------
     if world > 1:
-        t = torch.tensor([total_ms, e2e_ms, alt_ms or 0.0, d256_ms or 0.0], dtype=torch.float64, device=dev)
+        alt_names = sorted(alt_ms)
+        t = torch.tensor([total_ms, e2e_ms, d256_ms or 0.0] + [alt_ms[n] for n in alt_names], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_ms = float(t[0]), float(t[1])
-        alt_ms = float(t[2]) if alt_ms is not None else None
-        d256_ms = float(t[3]) if d256_ms is not None else None
+        d256_ms = float(t[2]) if d256_ms is not None else None
+        alt_ms = {n: float(t[3 + i]) for i, n in enumerate(alt_names)}
         ln = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(ln)
         launches = int(ln[0])
@@ -382,7 +387,7 @@ def run_ours(args):
         stream = torch.cuda.current_stream(dev).cuda_stream
         pos = 511                                   # mean cache length of a 1024-step decode
         H, D = 6, 64
-        elt = 2 if args.kv == 'f16' else 4          # bytes per stored K/V element
+        elt = {'f32': 4, 'f16': 2, 'p24': 3}[args.kv]   # bytes per stored K/V element
         alg_bytes = B * H * (pos + 1) * D * elt * 2 + B * H * D * 4 * 2   # K and V rows read once + q in, o out
         iters = 64
         for _ in range(2):
@@ -506,10 +511,9 @@ def run_ours(args):
             "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
             "clocks": clocks, "roofline": roofline,
         }
-        if alt_ms is not None:
-            alt_name = 'f32' if args.kv == 'f16' else 'f16'
-            line["value_kv_" + alt_name] = world * B * SEG_SECONDS / (alt_ms / 1000.0)
-            line["ms_per_step_kv_" + alt_name] = alt_ms
+        for alt_name, ms in sorted(alt_ms.items()):
+            line["value_kv_" + alt_name] = world * B * SEG_SECONDS / (ms / 1000.0)
+            line["ms_per_step_kv_" + alt_name] = ms
         if d256_ms is not None:
             line["dec_steps_256"] = {"ms_per_step": d256_ms, "value": world * B * SEG_SECONDS / (d256_ms / 1000.0), "unit": "audio-s/s"}
         if cpu_baseline:
@@ -535,7 +539,7 @@ def run_longform(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    kvf = {'f32': _lib.KV_F32, 'f16': _lib.KV_F16}[args.kv]
+    kvf = KV_FORMATS()[args.kv]
     im = inference.InferenceModel('synthetic:0' if rank == 0 else None, 'mt3', device=dev, batch_size=BATCH_PER_GPU, kv_format=kvf)
     n = 3 * 60 * 16000
     audio = synth_audio(-(-n // SEG_SAMPLES), 100).reshape(-1)[:n]
@@ -591,7 +595,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dec-steps", type=int, default=1024)
     ap.add_argument("--ref-batch", type=int, default=BATCH_PER_GPU, help="CPU sample: segments per batch (the GPU arm's 64)")
-    ap.add_argument("--kv", default="f16", choices=["f32", "f16"], help="storage format of the decoder's K/V rows")
+    ap.add_argument("--kv", default="p24", choices=["f32", "f16", "p24"], help="storage format of the decoder's K/V rows")
     ap.add_argument("--no-alt-kv", action="store_true", help="skip timing the other K/V storage format")
     ap.add_argument("--ref-budget-s", type=float, default=15.0, help="CPU sample: wall-time budget of the decode loop")
     ap.add_argument("--no-cpu-baseline", action="store_true")

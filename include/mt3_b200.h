@@ -115,11 +115,15 @@ enum {
 
 /* Storage format of the decoder's K/V rows -- the self-attention cache (layers.py:249-289) and the hoisted
  * cross-attention K/V.  All arithmetic (projections, scores, softmax, P.V) stays float32; only the stored rows are
- * rounded.  F32 keeps the reference's values exactly; F16 halves the bytes the decode step streams from HBM
- * (measured logit error 1.3e-4 of the logit scale against the float64 oracle, bar 5e-4: DESIGN.md section 4). */
+ * rounded, and the rounding of a stored row is amplified by every later softmax, the more the sharper the attention
+ * (error against the float64 oracle, diffuse / sharp attention):
+ *   F32  the reference's values exactly                                   4e-6 / 2e-6    100 % of the bytes
+ *   P24  float32 cut to 16 mantissa bits, a u16 + u8 plane inside a row   5e-6 / 3e-5     75 %   (default of InferenceModel)
+ *   F16  IEEE half                                                        1.6e-4 / 1.2e-3  50 %   (bar: 5e-4)          */
 enum {
   MT3_KV_F32 = 0,
-  MT3_KV_F16 = 1
+  MT3_KV_F16 = 1,
+  MT3_KV_P24 = 2
 };
 
 /* Number of float32 elements in the flat weight blob and the offset of a named

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libmt3b200.so")
 
 MT3_OK = 0
 GEMM_FP32_SIMT, GEMM_TF32X3, GEMM_TF32 = 0, 1, 2
-KV_F32, KV_F16 = 0, 1
+KV_F32, KV_F16, KV_P24 = 0, 1, 2
 GEN_STOP_AT_EOS, GEN_USE_GRAPH, GEN_BEAM1 = 1, 2, 4
 ABI_VERSION = 2
 K_DEC_SELF_ATTN, K_DEC_CROSS_ATTN, K_DEC_QKV_GEMM, K_ENC_QKV_GEMM, K_ENC_ATTN = 0, 1, 2, 3, 4

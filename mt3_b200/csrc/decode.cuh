@@ -42,7 +42,7 @@ struct DecGemmArgs {
   int epi;
   const float* R; int ldr;
   float* C; int ldc;
-  int n_split; void* C1; int kv_half; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // KV append (kv_half: fp16 cache)
+  int n_split; void* C1; int kv_fmt; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // KV append (kv_fmt: see kv_dest())
   float* partial;                 // [splits][n_tiles][64*32 + 64] scratch (non-cluster fallback)
   int* counters;                  // [n_tiles], zero on entry, left zero on exit
   // optional second activation source: columns [K0, K) of the virtual A come from A2[:, k - K0] (fused launches
@@ -71,14 +71,10 @@ __device__ __forceinline__ void dec_store4(const DecGemmArgs& p, int m, int n, f
     *reinterpret_cast<float4*>(p.C + (long long)m * p.ldc + n) = v;
     return;
   }
-  const long long d = kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, p.hm_pos ? *p.hm_pos : 0);
-  if (p.kv_half) {
-    __half2* dst = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.C1) + d);
-    dst[0] = __floats2half2_rn(v.x, v.y);
-    dst[1] = __floats2half2_rn(v.z, v.w);
-  } else {
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C1) + d) = v;
-  }
+  int d;
+  char* row = reinterpret_cast<char*>(p.C1) + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, p.hm_pos ? *p.hm_pos : 0, p.kv_fmt, d);
+  const float v4[4] = {v.x, v.y, v.z, v.w};
+  kv_store<4>(row, p.kv_fmt, d, v4);
 }
 
 // Non-cluster fallback.  Each CTA handles ONE K chunk of 64: all of its global loads (8 KB of weights, 16 KB of
@@ -302,16 +298,9 @@ __device__ __forceinline__ void dec_reduce_epilogue(const DecGemmArgs& p, const 
         if (CPT == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
         else dst[0] = v[0];
       } else {
-        const long long d = kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, p.hm_pos ? *p.hm_pos : 0);
-        if (p.kv_half) {
-          __half* dst = reinterpret_cast<__half*>(p.C1) + d;
-          if (CPT == 2) *reinterpret_cast<__half2*>(dst) = __floats2half2_rn(v[0], v[1]);
-          else dst[0] = __float2half_rn(v[0]);
-        } else {
-          float* dst = reinterpret_cast<float*>(p.C1) + d;
-          if (CPT == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
-          else dst[0] = v[0];
-        }
+        int d;
+        char* row = reinterpret_cast<char*>(p.C1) + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, p.hm_pos ? *p.hm_pos : 0, p.kv_fmt, d);
+        kv_store<CPT>(row, p.kv_fmt, d, v);
       }
     }
   }
@@ -566,12 +555,21 @@ inline int launch_dec_gemm(const DecGemmArgs& a, cudaStream_t s, bool pdl = fals
 }
 
 // ---------------------------------------------------------------------------------------------
-// Decode attention over head-major K/V, bulk-copy pipelined.  HALF = false: fp32 cache rows (256 B, 32 keys per
-// 8 KB tile); HALF = true: fp16 rows (128 B, 64 keys per tile), converted to fp32 on the way into the FMAs.
+// Decode attention over head-major K/V, bulk-copy pipelined.  FMT is the row format (kv_dest()): 0 = fp32 rows
+// (256 B, 32 keys per 8 KB tile, 6 stages); 1 = fp16 rows (128 B, 64 keys per 8 KB tile, 6 stages); 2 = p24 rows
+// (192 B, 64 keys per 12 KB tile, 4 stages).  Rows are widened to fp32 on the way into the FMAs.
 // ---------------------------------------------------------------------------------------------
-constexpr int kAttTileBytes = 8192;
-constexpr int kAttStages = 6;
+constexpr int kAttRingBytes = 48 * 1024;
 constexpr int kAttThreads = 160;                 // 4 consumer warps + 1 producer warp
+
+// element e (0..7) of a p24 chunk: hi = four 32-bit words holding eight u16, lo = two words holding eight u8
+__device__ __forceinline__ float p24_elt(const uint4& hi, const uint2& lo, int e) {
+  const uint32_t h = e < 2 ? hi.x : (e < 4 ? hi.y : (e < 6 ? hi.z : hi.w));
+  const uint32_t l = e < 4 ? lo.x : lo.y;
+  const uint32_t lb = 4u + (uint32_t)(e & 3);                              // byte of l (second operand: indices 4..7)
+  const uint32_t sel = (e & 1) ? (0x3200u | (lb << 4) | lb) : (0x1000u | (lb << 4) | lb);
+  return __uint_as_float(__byte_perm(h, l, sel));
+}
 
 // K/V rows are read once per step and are 10x the size of L2: stream them with an evict-first policy so
 // that the 104 MB of decoder weights (re-read every step) stay L2-resident.
@@ -589,27 +587,30 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 }
 
 inline size_t dec_attention_smem(int max_len) {
-  return (size_t)kAttStages * kAttTileBytes + (size_t)(4 * ((max_len + 3) & ~3) + 16 * 64 + 64) * sizeof(float) + 2 * kAttStages * 8 + 64;
+  return (size_t)kAttRingBytes + (size_t)(4 * ((max_len + 3) & ~3) + 16 * 64 + 64) * sizeof(float) + 2 * 6 * 8 + 64;
 }
 
-// q [B, ldq], head h at column q_off + h*64.  kv: head-major [b][2][H][cap][64] (float or __half).  out [B, ldo].
+// q [B, ldq], head h at column q_off + h*64.  kv: head-major [b][2][H][cap] rows of format FMT.  out [B, ldo].
 // len = (len_ptr ? *len_ptr : 0) + len_add.
-template <bool HALF, bool TRACE>
+template <int FMT, bool TRACE>
 __global__ void __launch_bounds__(kAttThreads)
 dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const void* __restrict__ kv_raw, int H, int cap,
                           const int* __restrict__ len_ptr, int len_add, int max_len, float* __restrict__ out, int ldo,
                           const float* __restrict__ q_ssq, int q_ssq_n, int q_ssq_ld, float q_dim, float q_eps,
                           unsigned long long* trace) {
-  constexpr int KT = HALF ? 64 : 32;                             // keys per tile
-  constexpr int ROWB = HALF ? 128 : 256;                         // bytes per key row
+  constexpr bool HALF = FMT == 1, P24 = FMT == 2;
+  constexpr int KT = FMT == 0 ? 32 : 64;                         // keys per tile
+  constexpr int ROWB = FMT == 0 ? 256 : (FMT == 1 ? 128 : 192);  // bytes per key row
+  constexpr int kAttTileBytes = KT * ROWB;                       // 8 KB / 8 KB / 12 KB
+  constexpr int kAttStages = kAttRingBytes / kAttTileBytes;      // 6 / 6 / 4
   extern __shared__ __align__(128) unsigned char sm_raw[];
   const int ml4 = (max_len + 3) & ~3;
-  unsigned char* ring = sm_raw;                                  // [stages][8 KB]
+  unsigned char* ring = sm_raw;                                  // [stages][tile]
   float* sP = reinterpret_cast<float*>(ring + kAttStages * kAttTileBytes);   // [4][ml4]: per-warp partial scores; row 0 becomes P
   float* sRed = sP + 4 * ml4;                                    // [16][64]
   float* sQ = sRed + 16 * 64;                                    // [64] the (scaled) query
   uint64_t* full = reinterpret_cast<uint64_t*>(sQ + 64);         // [stages]
-  uint64_t* empty = full + kAttStages;
+  uint64_t* empty = full + 6;
   __shared__ float s_stat[8];
 
   const int h = blockIdx.x, b = blockIdx.y;
@@ -690,7 +691,7 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
     float4 qa[4], qb[4];
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      if (HALF) {
+      if (HALF || P24) {
         const int c = (4 * (warp >> 1) + jj + (lane & 7)) & 7;
         qa[jj] = q4s[2 * c];
         qb[jj] = q4s[2 * c + 1];
@@ -719,6 +720,20 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
           d = fmaf(qb[jj].x, k45.x, d); d = fmaf(qb[jj].y, k45.y, d); d = fmaf(qb[jj].z, k67.x, d); d = fmaf(qb[jj].w, k67.y, d);
         }
         if (k0 + key < len) sP[(warp >> 1) * ml4 + k0 + key] = d;
+      } else if (P24) {
+        const int key = (warp & 1) * 32 + lane;
+        const unsigned char* row = ring + s * kAttTileBytes + key * ROWB;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int c = (4 * (warp >> 1) + jj + (lane & 7)) & 7;
+          const uint4 hi = *reinterpret_cast<const uint4*>(row + c * 16);
+          const uint2 lo = *reinterpret_cast<const uint2*>(row + 128 + c * 8);
+          d = fmaf(qa[jj].x, p24_elt(hi, lo, 0), d); d = fmaf(qa[jj].y, p24_elt(hi, lo, 1), d);
+          d = fmaf(qa[jj].z, p24_elt(hi, lo, 2), d); d = fmaf(qa[jj].w, p24_elt(hi, lo, 3), d);
+          d = fmaf(qb[jj].x, p24_elt(hi, lo, 4), d); d = fmaf(qb[jj].y, p24_elt(hi, lo, 5), d);
+          d = fmaf(qb[jj].z, p24_elt(hi, lo, 6), d); d = fmaf(qb[jj].w, p24_elt(hi, lo, 7), d);
+        }
+        if (k0 + key < len) sP[(warp >> 1) * ml4 + k0 + key] = d;
       } else {
         const float4* row = reinterpret_cast<const float4*>(ring + s * kAttTileBytes + lane * ROWB);
 #pragma unroll
@@ -736,7 +751,7 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
   asm volatile("bar.sync 1, 128;" ::: "memory");                // all partial rows are complete
   float lmax = -INFINITY;
   for (int k = tid; k < len; k += 128) {
-    const float sc = HALF ? sP[k] + sP[ml4 + k] : ((sP[k] + sP[ml4 + k]) + sP[2 * ml4 + k]) + sP[3 * ml4 + k];
+    const float sc = (HALF || P24) ? sP[k] + sP[ml4 + k] : ((sP[k] + sP[ml4 + k]) + sP[2 * ml4 + k]) + sP[3 * ml4 + k];
     sP[k] = sc;
     lmax = fmaxf(lmax, sc);
   }
@@ -758,8 +773,8 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
 
   // pass 2: O = P V.  fp32: thread -> key group tid / 16 (8 groups) x 4 dims (tid % 16); fp16: key group tid / 8
   // (16 groups) x 8 dims (tid % 8, one 16-byte chunk of the row)
-  constexpr int NG = HALF ? 16 : 8;
-  if (HALF) {
+  constexpr int NG = FMT == 0 ? 8 : 16;
+  if (HALF || P24) {
     const int kg = tid >> 3, d8 = tid & 7;
     float acc[8];
 #pragma unroll
@@ -775,10 +790,17 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
         if (k0 + kk < len) {
           const float pk = sP[k0 + kk];
           const uint4 vx = *reinterpret_cast<const uint4*>(tile + kk * ROWB + d8 * 16);
-          const float2 v01 = __half22float2(*reinterpret_cast<const __half2*>(&vx.x));
-          const float2 v23 = __half22float2(*reinterpret_cast<const __half2*>(&vx.y));
-          const float2 v45 = __half22float2(*reinterpret_cast<const __half2*>(&vx.z));
-          const float2 v67 = __half22float2(*reinterpret_cast<const __half2*>(&vx.w));
+          float2 v01, v23, v45, v67;
+          if (P24) {
+            const uint2 lo = *reinterpret_cast<const uint2*>(tile + kk * ROWB + 128 + d8 * 8);
+            v01 = make_float2(p24_elt(vx, lo, 0), p24_elt(vx, lo, 1)); v23 = make_float2(p24_elt(vx, lo, 2), p24_elt(vx, lo, 3));
+            v45 = make_float2(p24_elt(vx, lo, 4), p24_elt(vx, lo, 5)); v67 = make_float2(p24_elt(vx, lo, 6), p24_elt(vx, lo, 7));
+          } else {
+            v01 = __half22float2(*reinterpret_cast<const __half2*>(&vx.x));
+            v23 = __half22float2(*reinterpret_cast<const __half2*>(&vx.y));
+            v45 = __half22float2(*reinterpret_cast<const __half2*>(&vx.z));
+            v67 = __half22float2(*reinterpret_cast<const __half2*>(&vx.w));
+          }
           acc[0] = fmaf(pk, v01.x, acc[0]); acc[1] = fmaf(pk, v01.y, acc[1]);
           acc[2] = fmaf(pk, v23.x, acc[2]); acc[3] = fmaf(pk, v23.y, acc[3]);
           acc[4] = fmaf(pk, v45.x, acc[4]); acc[5] = fmaf(pk, v45.y, acc[5]);

@@ -35,18 +35,80 @@ struct GemmArgs {
   const float* pe; int pe_T; int pe_ld;  // EPI_ADD_PE
   float* C; int ldc;
   int n_split;                 // columns >= n_split -> head-major K/V store at C1 (N if unused)
-  void* C1; int kv_half; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // head-major K/V store (fp32 / fp16), see kv_dest()
+  void* C1; int kv_fmt; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // head-major K/V store, see kv_dest()
 };
 
 // Head-major K/V layout shared by the self-attention cache and the hoisted cross K/V:
-//   kv[b][which(0=K,1=V)][head][cap][64]
+//   kv[b][which(0=K,1=V)][head][cap] rows of 64 elements
 // Row m of the GEMM is (b, t) = (m / rows_per_b, m % rows_per_b + pos); column c (relative to n_split) is
 // (which, head, d) = (c / (H*64), (c % (H*64)) / 64, c % 64).  Decode: rows_per_b = 1, pos = cache index
 // (the fused KV-cache append, layers.py:272-289); cross K/V: rows_per_b = T, pos = 0.
-__device__ __forceinline__ long long kv_dest(int m, int c, int rows_per_b, int cap, int H, int pos) {
+// kv_fmt (mt3_model_config.kv_cache_format) is the storage format of a row:
+//   0  64 x float                                                           256 B
+//   1  64 x __half                                                          128 B
+//   2  "p24": 64 x u16 (bits 31..16 of the float) then 64 x u8 (bits 15..8)  192 B.  The decoder rebuilds a float
+//      with ONE byte permute per element by repeating the third byte as the fourth (value bits = hi16:lo8:lo8), and
+//      the encoder picks the nearest value of that form: 16 mantissa bits, relative error <= 2^-17.
+__host__ __device__ __forceinline__ int kv_row_bytes(int kv_fmt) { return kv_fmt == 0 ? 256 : (kv_fmt == 1 ? 128 : 192); }
+
+__device__ __forceinline__ long long kv_dest(int m, int c, int rows_per_b, int cap, int H, int pos, int kv_fmt, int& d) {
   const int b = m / rows_per_b, t = m % rows_per_b + pos;
-  const int which = c / (H * 64), h = (c % (H * 64)) >> 6, d = c & 63;
-  return ((((long long)b * 2 + which) * H + h) * cap + t) * 64 + d;
+  const int which = c / (H * 64), h = (c % (H * 64)) >> 6;
+  d = c & 63;
+  return ((((long long)b * 2 + which) * H + h) * cap + t) * kv_row_bytes(kv_fmt);
+}
+
+// the 24 stored bits (hi16 << 8 | lo8) of the p24 value nearest to x
+__device__ __forceinline__ uint32_t p24_encode(float x) {
+  const uint32_t bits = __float_as_uint(x);
+  const uint32_t t = bits >> 8;
+  uint32_t best = t;
+  uint32_t v = (t << 8) | (t & 255u);
+  uint32_t err = v > bits ? v - bits : bits - v;
+  const uint32_t tu = t + 1;                                   // same sign: the sign bit is far above the carry
+  v = (tu << 8) | (tu & 255u);
+  uint32_t e = v > bits ? v - bits : bits - v;
+  if (e < err) { err = e; best = tu; }
+  if ((t & 0x7fffffu) != 0u) {
+    const uint32_t td = t - 1;
+    v = (td << 8) | (td & 255u);
+    e = v > bits ? v - bits : bits - v;
+    if (e < err) best = td;
+  }
+  return best;
+}
+__device__ __forceinline__ float p24_decode(uint32_t t) { return __uint_as_float((t << 8) | (t & 255u)); }
+
+// store N (1, 2 or 4) consecutive elements d..d+N-1 (d % N == 0) of one K/V row
+template <int N>
+__device__ __forceinline__ void kv_store(char* row, int kv_fmt, int d, const float* v) {
+  if (kv_fmt == 0) {
+    float* dst = reinterpret_cast<float*>(row) + d;
+    if (N == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    else if (N == 2) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+    else dst[0] = v[0];
+  } else if (kv_fmt == 1) {
+    __half* dst = reinterpret_cast<__half*>(row) + d;
+    if (N == 1) dst[0] = __float2half_rn(v[0]);
+#pragma unroll
+    for (int i = 0; i + 1 < N; i += 2) reinterpret_cast<__half2*>(dst)[i / 2] = __floats2half2_rn(v[i], v[i + 1]);
+  } else {
+    uint32_t t[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) t[i] = p24_encode(v[i]);
+    unsigned short* hi = reinterpret_cast<unsigned short*>(row) + d;
+    unsigned char* lo = reinterpret_cast<unsigned char*>(row) + 128 + d;
+    if (N == 4) {
+      *reinterpret_cast<uint2*>(hi) = make_uint2((t[0] >> 8) | ((t[1] >> 8) << 16), (t[2] >> 8) | ((t[3] >> 8) << 16));
+      *reinterpret_cast<uint32_t*>(lo) = (t[0] & 255u) | ((t[1] & 255u) << 8) | ((t[2] & 255u) << 16) | ((t[3] & 255u) << 24);
+    } else if (N == 2) {
+      *reinterpret_cast<uint32_t*>(hi) = (t[0] >> 8) | ((t[1] >> 8) << 16);
+      *reinterpret_cast<unsigned short*>(lo) = (unsigned short)((t[0] & 255u) | ((t[1] & 255u) << 8));
+    } else {
+      hi[0] = (unsigned short)(t[0] >> 8);
+      lo[0] = (unsigned char)(t[0] & 255u);
+    }
+  }
 }
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -183,14 +245,10 @@ sgemm_kernel(const GemmArgs p) {
           *reinterpret_cast<float4*>(p.C + (long long)m * p.ldc + n) = v;
         } else {
           const int pos = p.hm_pos ? *p.hm_pos : 0;
-          const long long d = kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos);
-          if (p.kv_half) {
-            __half2* dst = reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.C1) + d);
-            dst[0] = __floats2half2_rn(v.x, v.y);
-            dst[1] = __floats2half2_rn(v.z, v.w);
-          } else {
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C1) + d) = v;
-          }
+          int d;
+          char* row = reinterpret_cast<char*>(p.C1) + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos, p.kv_fmt, d);
+          const float v4[4] = {v.x, v.y, v.z, v.w};
+          kv_store<4>(row, p.kv_fmt, d, v4);
         }
       }
     }

@@ -36,7 +36,7 @@ struct TcGemmArgs {
   const float* R_hi; const float* R_lo; int ldr;
   const float* pe; int pe_T; int pe_ld;
   float* C_hi; float* C_lo; int ldc;       // C_lo != null: write hi/lo split of the result
-  int n_split; void* C1; int kv_half; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // head-major K/V store (fp32 / fp16), see kv_dest()
+  int n_split; void* C1; int kv_fmt; int hm_rows_per_b; int hm_cap; int hm_H; const int* hm_pos;   // head-major K/V store, see kv_dest()
   // Transposed per-head store for columns >= vt_col0 (the V third of a fused QKV projection), enabled by VT_hi:
   // vt[((b*H + h)*64 + d)*vt_T + t] with row m = b*vt_T + t, column = vt_col0 + h*64 + d.  This is the K-major
   // (keys contiguous) operand the tcgen05 attention kernel reads for P.V.
@@ -222,9 +222,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         if (p.C_lo) cl = p.C_lo + (long long)m * p.ldc + n;
       } else {
         const int pos = p.hm_pos ? *p.hm_pos : 0;
-        const long long d = kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos);
-        if (p.kv_half) {                     // 32 consecutive columns of one head: 64 contiguous bytes of fp16
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.C1) + d);
+        int d;
+        char* row = reinterpret_cast<char*>(p.C1) + kv_dest(m, n - p.n_split, p.hm_rows_per_b, p.hm_cap, p.hm_H, pos, p.kv_fmt, d);
+        if (p.kv_fmt == 1) {                 // 32 consecutive columns of one head: 64 contiguous bytes of fp16
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(row) + d);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             __half2 h0 = __floats2half2_rn(v[8 * q], v[8 * q + 1]), h1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
@@ -236,7 +237,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           }
           continue;
         }
-        ch = reinterpret_cast<float*>(p.C1) + d;
+        if (p.kv_fmt == 2) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) kv_store<4>(row, 2, d + 4 * q, v + 4 * q);
+          continue;
+        }
+        ch = reinterpret_cast<float*>(row) + d;
       }
 #pragma unroll
       for (int q = 0; q < 8; ++q) {

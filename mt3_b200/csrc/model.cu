@@ -95,8 +95,8 @@ struct Model {
   bool pdl_attn = true;           // MT3_PDL=2 (default): only the attention launches (K/V prefetch under the preceding GEMM)
   bool pdl_gemm = false;          // MT3_PDL=4: only the GEMM launches; bits combine (6 = attention + GEMM); 0 = off
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
-  bool kv_half = false;           // cfg.kv_cache_format == MT3_KV_F16: self and cross K/V rows stored as fp16
-  int kv_elt = 4;                 // bytes per K/V element
+  int kv_fmt = 0;                 // cfg.kv_cache_format: storage format of the self and cross K/V rows (kv_dest())
+  int kv_row = 256;               // bytes per K/V row of 64 elements
   // debug timeline (mt3_debug_trace_step): while `tracing` is set every decode GEMM / attention launch gets a slot
   unsigned long long* trace = nullptr;
   bool tracing = false;
@@ -116,7 +116,7 @@ struct Model {
   int64_t ws_bytes = 0;
   int B = 0, T = 0;
   float *h = nullptr, *rstd = nullptr, *qkv = nullptr, *ao = nullptr, *g = nullptr, *encoded = nullptr;
-  char *ckv = nullptr, *skv = nullptr;   // head-major K/V (kv_elt bytes per element)
+  char *ckv = nullptr, *skv = nullptr;   // head-major K/V rows (kv_row bytes each)
   float *dy = nullptr, *drstd = nullptr, *dq = nullptr, *dao = nullptr, *dg = nullptr, *dlogits = nullptr;
   int *tok_cur = nullptr, *finished = nullptr, *tokens = nullptr, *state = nullptr;
   float* att_scratch = nullptr;   // key-split encoder attention (T > 256): unnormalised O parts + (max, sum) pairs
@@ -140,9 +140,9 @@ struct Model {
   int* h_flag = nullptr;          // pinned
 };
 
-// byte address of layer l's K/V block: [B][K|V][H][cap][64] elements of kv_elt bytes
+// byte address of layer l's K/V block: [B][K|V][H][cap] rows of kv_row bytes
 static char* kv_layer(const Model* m, char* base, int l, int cap) {
-  return base + (int64_t)l * m->B * cap * 2 * m->Q * m->kv_elt;
+  return base + (int64_t)l * m->B * cap * 2 * m->H * m->kv_row;
 }
 
 static int64_t prepared_floats(const mt3_model_config& c) {
@@ -314,7 +314,7 @@ static int cross_kv_tc_impl(Model* m, const float* encoded, cudaStream_t s) {
   }
   for (int l = 0; l < m->Ld; ++l) {
     TcGemmArgs a = tc_args(M, 2 * Q, D, nullptr, nullptr, 2 * Q);
-    a.n_split = 0; a.C1 = kv_layer(m, m->ckv, l, m->T); a.kv_half = m->kv_half ? 1 : 0; a.hm_rows_per_b = m->T; a.hm_cap = m->T; a.hm_H = m->H;
+    a.n_split = 0; a.C1 = kv_layer(m, m->ckv, l, m->T); a.kv_fmt = m->kv_fmt; a.hm_rows_per_b = m->T; a.hm_cap = m->T; a.hm_H = m->H;
     MT3_TRY(launch_tc_gemm(ope, m->dec[l].t_wkv_c.op, a, m->split3, s));
   }
   return MT3_OK;
@@ -373,7 +373,7 @@ static int cross_kv_impl(Model* m, const float* encoded, cudaStream_t s) {
   } else {
     for (int l = 0; l < m->Ld; ++l) {
       GemmArgs a = gemm_args(encoded, D, m->dec[l].wkv_c, 2 * Q, M, 2 * Q, D, nullptr, 2 * Q);
-      a.n_split = 0; a.C1 = kv_layer(m, m->ckv, l, m->T); a.kv_half = m->kv_half ? 1 : 0; a.hm_rows_per_b = m->T; a.hm_cap = m->T; a.hm_H = m->H;
+      a.n_split = 0; a.C1 = kv_layer(m, m->ckv, l, m->T); a.kv_fmt = m->kv_fmt; a.hm_rows_per_b = m->T; a.hm_cap = m->T; a.hm_H = m->H;
       MT3_TRY(gemm(m, a, s));
     }
   }
@@ -408,8 +408,8 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
     a.norm = norm; a.eps = 1e-6f; a.epi = epi;
     a.R = C + (int64_t)r0 * ldc; a.ldr = ldc;                  // residual is always added in place
     a.C = C + (int64_t)r0 * ldc; a.ldc = ldc; a.n_split = n_split;
-    if (kv) {  // rows_per_b = 1: skip r0 sequences, each 2*H*cap*64 elements
-      a.C1 = kv + (int64_t)r0 * 2 * m->H * m->L * 64 * m->kv_elt; a.kv_half = m->kv_half ? 1 : 0;
+    if (kv) {  // rows_per_b = 1: skip r0 sequences, each 2*H*cap rows
+      a.C1 = kv + (int64_t)r0 * 2 * m->H * m->L * m->kv_row; a.kv_fmt = m->kv_fmt;
       a.hm_rows_per_b = 1; a.hm_cap = m->L; a.hm_H = m->H; a.hm_pos = pos;
     }
     a.partial = m->dpartial;
@@ -423,19 +423,19 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
   return MT3_OK;
 }
 
-template <bool HALF>
+template <int FMT>
 static int launch_dec_attention_t(Model* m, const float* q, const char* kv, int cap, const int* len_ptr, int len_add,
                                   float* out, const Rows& rows, cudaStream_t s, const float* q_ssq, size_t smem, int max_len) {
   static bool attr_done = false;
   if (!attr_done) {
-    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel<HALF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel<HALF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel<FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel<FMT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
-  MT3_CUDA_CHECK(launch_kernel(m->tracing ? dec_attention_bulk_kernel<HALF, true> : dec_attention_bulk_kernel<HALF, false>,
+  MT3_CUDA_CHECK(launch_kernel(m->tracing ? dec_attention_bulk_kernel<FMT, true> : dec_attention_bulk_kernel<FMT, false>,
                                dim3(m->H, rows.count), dim3(kAttThreads), smem, s, m->pdl_attn,
                                q + (int64_t)rows.begin * m->Q, m->Q, 0,
-                               (const void*)(kv + (int64_t)rows.begin * 2 * m->H * cap * 64 * m->kv_elt), m->H, cap,
+                               (const void*)(kv + (int64_t)rows.begin * 2 * m->H * cap * m->kv_row), m->H, cap,
                                len_ptr, len_add, max_len, out + (int64_t)rows.begin * m->Q, m->Q,
                                q_ssq ? q_ssq + (int64_t)rows.begin * (m->D / 32) : (const float*)nullptr, m->D / 32, m->D / 32,
                                (float)m->D, 1e-6f, trace_slot(m, len_ptr ? "attn_self" : "attn_cross")));
@@ -448,8 +448,11 @@ static int launch_dec_attention(Model* m, const float* q, const char* kv, int ca
   const int max_len = std::max(m->L, m->T);
   const size_t smem = dec_attention_smem(max_len);
   MT3_REQUIRE(smem <= 100 * 1024, MT3_ERR_UNSUPPORTED, "decode attention: length %d too long", max_len);
-  return m->kv_half ? launch_dec_attention_t<true>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len)
-                    : launch_dec_attention_t<false>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len);
+  switch (m->kv_fmt) {
+    case MT3_KV_F16: return launch_dec_attention_t<1>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len);
+    case MT3_KV_P24: return launch_dec_attention_t<2>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len);
+    default: return launch_dec_attention_t<0>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len);
+  }
 }
 
 // y_out = y_in + o.Wo  and  q_raw = [o | y_in].[Wo.Wq ; Wq]  in ONE launch; the RMSNorm factor of y_out is applied to
@@ -644,7 +647,7 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
               "mt3_model_create: lengths above FixedEmbed.max_length=2048 (layers.py:565)");
   MT3_REQUIRE(cfg->gemm_mode == MT3_GEMM_FP32_SIMT || cfg->gemm_mode == MT3_GEMM_TF32X3 || cfg->gemm_mode == MT3_GEMM_TF32,
               MT3_ERR_BAD_ARG, "mt3_model_create: unknown gemm_mode %d", cfg->gemm_mode);
-  MT3_REQUIRE(cfg->kv_cache_format == MT3_KV_F32 || cfg->kv_cache_format == MT3_KV_F16, MT3_ERR_BAD_ARG,
+  MT3_REQUIRE(cfg->kv_cache_format == MT3_KV_F32 || cfg->kv_cache_format == MT3_KV_F16 || cfg->kv_cache_format == MT3_KV_P24, MT3_ERR_BAD_ARG,
               "mt3_model_create: unknown kv_cache_format %d", cfg->kv_cache_format);
   if (cfg->gemm_mode != MT3_GEMM_FP32_SIMT)
     MT3_REQUIRE(cfg->emb_dim % 32 == 0 && cfg->mlp_dim % 32 == 0 && cfg->input_depth % 32 == 0, MT3_ERR_UNSUPPORTED,
@@ -763,8 +766,8 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     const char* e_attn = getenv("MT3_TC_ATTENTION");
     m->tc_attn_ok = !(e_attn && e_attn[0] == '0');
   }
-  m->kv_half = cfg->kv_cache_format == MT3_KV_F16;
-  m->kv_elt = m->kv_half ? 2 : 4;
+  m->kv_fmt = cfg->kv_cache_format;
+  m->kv_row = kv_row_bytes(m->kv_fmt);
   m->tc = cfg->gemm_mode != MT3_GEMM_FP32_SIMT;
   m->split3 = cfg->gemm_mode == MT3_GEMM_TF32X3;
   if (rc == MT3_OK && m->tc) {
@@ -841,8 +844,8 @@ WsLayout ws_layout(const Model* m, int B, int T) {
   w.ao = take(M * Q * 4);
   w.g = take(M * F * 4);
   w.encoded = take(M * D * 4);
-  w.ckv = take((int64_t)m->Ld * M * 2 * Q * m->kv_elt);
-  w.skv = take((int64_t)m->Ld * B * L * 2 * Q * m->kv_elt);
+  w.ckv = take((int64_t)m->Ld * M * 2 * m->H * m->kv_row);
+  w.skv = take((int64_t)m->Ld * B * L * 2 * m->H * m->kv_row);
   w.dy = take((int64_t)B * D * 4);
   w.drstd = take((int64_t)B * 4);
   w.dy2 = take((int64_t)B * D * 4);

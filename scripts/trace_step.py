@@ -16,7 +16,7 @@ SM_GHZ = 1.965
 def main():
     B = int(os.environ.get("TRACE_B", "64"))
     dev = torch.device("cuda:0")
-    kv = {"f32": _lib.KV_F32, "f16": _lib.KV_F16}[os.environ.get("TRACE_KV", "f16")]
+    kv = {"f32": _lib.KV_F32, "f16": _lib.KV_F16, "p24": _lib.KV_P24}[os.environ.get("TRACE_KV", "p24")]
     im = inference.InferenceModel("synthetic:0", "mt3", device=dev, batch_size=B, kv_format=kv)
     rng = np.random.default_rng(0)
     audio = torch.from_numpy((0.1 * rng.standard_normal((B, 32768))).astype(np.float32))

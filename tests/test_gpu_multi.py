@@ -41,7 +41,7 @@ def _worker(rank, world, port, steps, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         # only rank 0 has the checkpoint: the other ranks receive the weights through the one broadcast
-        im = inference.InferenceModel("synthetic:0" if rank == 0 else None, "mt3", device=dev, batch_size=32, kv_format=_lib.KV_F16)
+        im = inference.InferenceModel("synthetic:0" if rank == 0 else None, "mt3", device=dev, batch_size=32)
         im.outputs_length = 1024
         audio = _audio()
         ds = im.preprocess(im.audio_to_dataset(audio))

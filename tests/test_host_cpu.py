@@ -213,6 +213,8 @@ def test_abi_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/mt3_b200.h but not exported"
     assert set(_lib.EXPORTS) == declared
     assert lib.mt3_abi_version() == 2
+    for name, val in (("MT3_KV_F32", _lib.KV_F32), ("MT3_KV_F16", _lib.KV_F16), ("MT3_KV_P24", _lib.KV_P24), ("MT3_GEN_BEAM1", _lib.GEN_BEAM1)):
+        assert int(re.search(name + r"\s*=\s*(\d+)", header).group(1)) == val, name
     assert isinstance(lib.mt3_kernel_launch_count(), int)
     # argument validation happens before any CUDA call -> testable without a GPU
     assert lib.mt3_frontend_create(None, None, None) == -1
