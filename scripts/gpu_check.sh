@@ -30,7 +30,7 @@ prof () {  # name, kernel regex, launch-skip, count
      -o gpurun_out/prof_$1 -f python bench.py $NCU_ARGS > gpurun_out/ncu_full_$1.log 2>&1
   tail -1 gpurun_out/ncu_full_$1.log | cut -c1-160
 }
-prof dec_attention dec_attention_bulk 400 2    # the roofline leg's launches at cache length 512 (fp16 K/V rows)
+prof dec_attention dec_attention_bulk 400 2    # the roofline leg's launches at cache length 512 (24-bit K/V rows)
 prof dec_gemm sgemm_dec_cluster 60 5           # decode-step GEMMs (single and fused dual launch)
 prof enc_gemm gemm_tf32 45 3                   # encoder GEMMs (3xTF32)
 prof enc_attention enc_attention_tc 9 2
