@@ -12,10 +12,11 @@ so the worst case is what is timed; nothing is skipped).
 
 `value`  device-resident inputs, timed with CUDA events per step (L2 flushed between steps),
          max over ranks, whole-job aggregate over N GPUs (weak scaling: 64 segments per GPU).
-         Arithmetic is float32 everywhere; the decoder's K/V rows are STORED as fp16 by default
-         (--kv f16: half the bytes the decode step streams; parity-tested against the float64
-         oracle at cache lengths up to 1024, logit error ~1.3e-4 of the 5e-4 bar).  The same pass
-         with fp32 K/V rows is timed too and reported as `value_kv_f32`.
+         Arithmetic is float32 everywhere; the decoder's K/V rows are STORED with 24 bits per element by
+         default (--kv p24: three quarters of the bytes the decode step streams; logit error ~5e-6 of the
+         scale against the float64 oracle at cache lengths up to 1024, the level of the float32
+         arithmetic).  The same pass with fp32 and with fp16 rows is timed too and reported as
+         `value_kv_f32` / `value_kv_f16` (fp16 rows leave the 5e-4 bar when attention is sharp: DESIGN.md 4).
 `e2e`    same metric through InferenceModel.transcribe_segments with pinned HOST audio in and
          HOST tokens out (H2D + D2H inside the timed region).
 `roofline` the dominant kernel (decode self-attention over the KV cache), algorithmic bytes per
@@ -317,7 +318,7 @@ def run_ours(args):
         e2e_times.append(time.perf_counter() - t0)
     e2e_ms = 1000.0 * float(np.median(e2e_times))
 
-    # ---- the same device-resident pass with the OTHER K/V storage formats (fp32 and 24-bit rows when the headline uses fp16) ----
+    # ---- the same device-resident pass with the OTHER K/V storage formats (fp32 and fp16 rows when the headline uses 24-bit rows) ----
     alt_ms = {}
     for alt_name in ([] if args.no_alt_kv else [n for n in ('f32', 'p24', 'f16') if n != args.kv]):
         im_alt = inference.InferenceModel('synthetic:0', 'mt3', device=dev, batch_size=B, use_graph=True, gemm_mode=gm,
