@@ -434,6 +434,47 @@ def test_decode_variants(gm, pdl, cluster, kv, monkeypatch):
         np.testing.assert_allclose(l, base_l, rtol=0, atol=2e-5 * np.abs(base_l).max())
 
 
+@pytest.mark.parametrize("kv", ["f32", "f16", "p24"])
+@pytest.mark.parametrize("env", [{"MT3_PF_ATTN": "3"}, {"MT3_PF_ATTN": "64", "MT3_PF_GEMM": "2", "MT3_PF_HINT": "1"},
+                                 {"MT3_PF_GEMM": "5"}, {"MT3_L2_PERSIST_MB": "32", "MT3_PF_ATTN": "8"}],
+                         ids=["attn3", "attn64+gemm2+hint", "gemm5", "persist32+attn8"])
+def test_kv_l2_prefetch_is_value_neutral(env, kv, monkeypatch):
+    """The L2 knobs of the decode step -- prefetch of the K/V tiles beyond the attention kernel's ring by its own producer
+    warp (MT3_PF_ATTN) and by the GEMMs that run while the HBM is idle (MT3_PF_GEMM), with or without the evict_first hint,
+    and the persisting-L2 window over the decoder weights (MT3_L2_PERSIST_MB) -- only change cache state: tokens of a
+    graph-replayed greedy run over 300 cache positions (5 / 10 tiles per stream, ragged last tile, cache capacity not a
+    multiple of the tile) and step-by-step logits are bit-identical to the run without them, in every K/V row format."""
+    from mt3_b200 import network
+    ocfg = O.T5Config(vocab_size=1536, num_encoder_layers=1, num_decoder_layers=3)
+    params = O.init_params(ocfg, seed=21)
+    cfg = _mt3_cfg(num_encoder_layers=1, num_decoder_layers=3)
+    x = torch.from_numpy(_inputs(8, seed=700)).to(DEV)         # T = 256: the cross K/V has tiles beyond the ring too
+    gmode, kvf = _mode_ids(("tf32x3", kv))
+    forced = torch.from_numpy(np.random.default_rng(5).integers(3, 1500, size=(8, 70)).astype(np.int32)).to(DEV)
+    knobs = ("MT3_PF_ATTN", "MT3_PF_GEMM", "MT3_PF_HINT", "MT3_L2_PERSIST_MB")
+
+    def run():
+        m = network.Transformer(cfg, params, device=DEV, max_batch=8, max_input_length=256, max_decode_length=300, gemm_mode=gmode,
+                                kv_format=kvf)
+        toks = m.generate(x, stop_at_eos=False, use_graph=True).cpu().numpy()
+        lg = m.teacher_forced_logits(m.encode(x), forced).cpu().numpy()
+        return toks, lg
+
+    for k in knobs:
+        monkeypatch.delenv(k, raising=False)
+    base_t, base_l = run()
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    t, l = run()
+    monkeypatch.setenv("MT3_L2_PERSIST_MB", "0")     # an explicit 0 returns the carve-out at the next mt3_model_create
+    for k in knobs[:3]:
+        monkeypatch.delenv(k, raising=False)
+    t2, _ = run()
+    np.testing.assert_array_equal(t, base_t)
+    np.testing.assert_array_equal(l, base_l)
+    np.testing.assert_array_equal(t2, base_t)
+
+
 def test_kv_cache_formats_vs_fp32():
     """fp16 rows (MT3_KV_F16) and 24-bit rows (MT3_KV_P24) against fp32 rows, everything else equal: the logits move by
     the rounding of the stored rows only (measured ~1e-4 of the logit scale for fp16 with these weights, ~5e-6 for
