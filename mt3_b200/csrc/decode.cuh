@@ -36,53 +36,17 @@ namespace mt3 {
 // ---------------------------------------------------------------------------------------------
 // L2 prefetch of head-major K/V rows.  The decode attention kernel reads, per (sequence b, head h), the K rows
 // 0..len-1 and then the V rows 0..len-1 of one layer in tiles of KT keys: "virtual tile" j < nt is K tile j, virtual
-// tile nt + t is V tile t (nt = ceil(len / KT)) -- the order its producer warp streams them in.  While the decode
-// GEMMs run the HBM is idle, so a GEMM launch (or the attention kernel's own producer, which starts under the
-// preceding GEMM) can pull the tiles BEYOND the attention kernel's shared-memory ring into L2 ahead of time with
-// cp.async.bulk.prefetch.L2 (UBLKPF): the later bulk copies then hit L2.  Nothing but cache state changes.
+// tile nt + t is V tile t (nt = ceil(len / KT)) -- the order its producer warp streams them in.  The kernel starts
+// under the preceding GEMM (programmatic dependent launch) while the HBM is idle, but its shared-memory ring only
+// holds the first 4-6 tiles; the producer therefore also pulls the next `pf_tiles` tiles into L2 with
+// cp.async.bulk.prefetch.L2 (UBLKPF) and the later bulk copies hit L2.  Nothing but cache state changes (bit-identical
+// results: tests/test_gpu_parity.py::test_kv_l2_prefetch_is_value_neutral).  Measured (profiles/r02_call63_*): 16 tiles
+// -1.6 % per batch; the same prefetch issued earlier, from the GEMMs of the previous layer, +0.8 .. +3.4 % (the
+// prefetched rows compete with the decoder weights for L2), a persisting-L2 window over the weights 0 .. +1.2 % --
+// both removed again.
 // ---------------------------------------------------------------------------------------------
-struct KvPrefetch {
-  const char* kv;                 // layer base: [b][K|V][H][cap] rows of row_bytes; null = no prefetch
-  const int* pos;                 // device position; len = *pos + len_add (clamped to cap)
-  int len_add, cap, H, B, row_bytes, kt;
-  int j0, j1;                     // virtual tiles [j0, j1) of every (b, h) pair
-  int hint;                       // 1: mark the prefetched lines evict_first
-};
-
-__device__ __forceinline__ void l2_prefetch_bulk(const void* gsrc, uint32_t bytes, int hint) {
-  if (hint) {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "l"(pol)
-                 : "memory");
-  } else {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes) : "memory");
-  }
-}
-
-// virtual tile j of pair (b, h) at length len (nt = tiles per stream); does nothing past the end
-__device__ __forceinline__ void kv_prefetch_tile(const KvPrefetch& f, int b, int h, int len, int nt, int j) {
-  if (j >= 2 * nt) return;
-  const int t = j < nt ? j : j - nt;
-  const int keys = min(f.kt, len - t * f.kt);
-  const char* base = f.kv + (((long long)b * 2 + (j < nt ? 0 : 1)) * f.H + h) * (long long)f.cap * f.row_bytes;
-  l2_prefetch_bulk(base + (long long)t * f.kt * f.row_bytes, (uint32_t)(keys * f.row_bytes), f.hint);
-}
-
-// one thread of CTA `cta` of `n_cta`: the (pair, tile) items are dealt round-robin, tile-major so that the tiles needed
-// first are requested first
-__device__ __forceinline__ void kv_prefetch_share(const KvPrefetch& f, int cta, int n_cta) {
-  if (f.kv == nullptr) return;
-  const int len = min(f.cap, (f.pos ? *f.pos : 0) + f.len_add);
-  if (len <= 0) return;
-  const int nt = (len + f.kt - 1) / f.kt;
-  const int pairs = f.B * f.H;
-  const int j1 = min(f.j1, 2 * nt);
-  const int items = (j1 - f.j0) * pairs;
-  for (int i = cta; i < items; i += n_cta) {
-    const int pr = i % pairs;
-    kv_prefetch_tile(f, pr / f.H, pr % f.H, len, nt, f.j0 + i / pairs);
-  }
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes) : "memory");
 }
 
 struct DecGemmArgs {
@@ -105,9 +69,6 @@ struct DecGemmArgs {
   float* ssq_out; int ssq_ld;
   unsigned long long* trace;      // debug timeline slot (mt3_debug_trace_step) or null: [0] min start, [1] max end (ns,
                                   // %globaltimer); [2..6] clock64 deltas of CTA (0,0) at its phase boundaries
-  // optional L2 prefetch of K/V rows a LATER attention launch will stream (value-neutral: it only warms L2 while the
-  // HBM is idle under this GEMM): tiles [pf_j0, pf_j1) of every (sequence, head) stream pair of pf_kv, see KvPrefetch
-  KvPrefetch pf;
 };
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -422,7 +383,6 @@ __device__ __forceinline__ void dec_cluster_body(const DecGemmArgs& p, const int
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(&As[row * LDA + kq * 4])), "l"(src),
                  "r"(ok ? 16 : 0) : "memory");
   }
-  if (tid == 0) kv_prefetch_share(p.pf, (int)(blockIdx.x + gridDim.x * blockIdx.y), (int)(gridDim.x * gridDim.y));
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   if (tr0) p.trace[2] = (unsigned long long)(clock64() - c0);      // loads landed
@@ -653,7 +613,7 @@ __global__ void __launch_bounds__(kAttThreads)
 dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const void* __restrict__ kv_raw, int H, int cap,
                           const int* __restrict__ len_ptr, int len_add, int max_len, float* __restrict__ out, int ldo,
                           const float* __restrict__ q_ssq, int q_ssq_n, int q_ssq_ld, float q_dim, float q_eps,
-                          unsigned long long* trace, int pf_j0, int pf_j1, int pf_hint) {
+                          unsigned long long* trace, int pf_tiles) {
   constexpr bool HALF = FMT == 1, P24 = FMT == 2;
   constexpr int KT = FMT == 0 ? 32 : 64;                         // keys per tile
   constexpr int ROWB = FMT == 0 ? 256 : (FMT == 1 ? 128 : 192);  // bytes per key row
@@ -701,18 +661,18 @@ dec_attention_bulk_kernel(const float* __restrict__ q, int ldq, int q_off, const
     if (lane == 0) {
       const uint64_t policy = l2_evict_first_policy();
       bool waited = len_ptr == nullptr;
-      // L2 prefetch of the virtual tiles [pf_j0, pf_j1) that do not fit the ring (KvPrefetch above): requested once, AFTER
-      // the ring's own loads are in flight and before this warp first blocks (on a ring slot or on the PDL wait)
-      bool prefetched = pf_j1 <= pf_j0;
+      // L2 prefetch of the pf_tiles virtual tiles that follow the ring's: requested once, AFTER the ring's own loads are
+      // in flight and before this warp first blocks (on a ring slot, or on the PDL wait when the cache is still short)
+      bool prefetched = pf_tiles <= 0;
       for (int j = 0; j < 2 * nt; ++j) {
         const int s = j % kAttStages;
         const uint32_t ph = (j / kAttStages) & 1;
         const int t = j < nt ? j : j - nt;
         if (!prefetched && (j >= kAttStages || (!waited && t == nt - 1))) {
-          KvPrefetch f;
-          f.kv = reinterpret_cast<const char*>(kv_raw); f.pos = nullptr; f.len_add = len; f.cap = cap; f.H = H; f.B = 0;
-          f.row_bytes = ROWB; f.kt = KT; f.j0 = pf_j0; f.j1 = pf_j1; f.hint = pf_hint;
-          for (int jj = max(pf_j0, j); jj < min(pf_j1, 2 * nt); ++jj) kv_prefetch_tile(f, b, h, len, nt, jj);
+          for (int jj = max(kAttStages, j); jj < min(kAttStages + pf_tiles, 2 * nt); ++jj) {
+            const int tt = jj < nt ? jj : jj - nt;
+            l2_prefetch_bulk((jj < nt ? kbase : vbase) + (long long)tt * kAttTileBytes, (uint32_t)(min(KT, len - tt * KT) * ROWB));
+          }
           prefetched = true;
         }
         if (!waited && t == nt - 1) {

@@ -95,13 +95,9 @@ struct Model {
   bool pdl_attn = true;           // MT3_PDL=2 (default): only the attention launches (K/V prefetch under the preceding GEMM)
   bool pdl_gemm = false;          // MT3_PDL=4: only the GEMM launches; bits combine (6 = attention + GEMM); 0 = off
   bool dec_cluster = true;        // MT3_DEC_CLUSTER=0: split-K reduction through global scratch instead of DSMEM
-  // L2 prefetch of K/V tiles beyond the attention kernel's shared-memory ring (KvPrefetch, decode.cuh); value-neutral.
-  int pf_attn = 0;                // MT3_PF_ATTN=n: the attention kernel's producer warp prefetches n tiles per (sequence, head)
-  int pf_gemm = 0;                // MT3_PF_GEMM=n: the cross-out, MLP-in and MLP-out GEMMs of layer l each prefetch n tiles per
-                                  // (sequence, head) of layer l+1's self K/V (the logits GEMM: 3n of layer 0's, for the next step)
-  int pf_hint = 0;                // MT3_PF_HINT=1: prefetched lines are marked evict_first
-  int l2_persist_mb = 0;          // MT3_L2_PERSIST_MB=n: n MB of L2 set aside for the decoder weights (access policy window on
-                                  // every kernel node of the step graph)
+  int pf_attn = 16;               // MT3_PF_ATTN=n: the decode-step attention kernels prefetch the n K/V tiles that follow their
+                                  // shared-memory ring into L2 while they wait under the preceding GEMM (decode.cuh; value-neutral;
+                                  // 0 = off: 449.6 -> 442.3 ms per batch at 16, profiles/r02_call63_ab_l2_prefetch.txt)
   int kv_fmt = 0;                 // cfg.kv_cache_format: storage format of the self and cross K/V rows (kv_dest())
   int kv_row = 256;               // bytes per K/V row of 64 elements
   // debug timeline (mt3_debug_trace_step): while `tracing` is set every decode GEMM / attention launch gets a slot
@@ -405,15 +401,8 @@ static unsigned long long* trace_slot(Model* m, const char* name) {
 
 // Decode-step GEMM on M = B rows: split-K exact-fp32 cluster kernel with the RMSNorm statistic fused (decode.cuh), in every
 // gemm_mode (the tcgen05 variants of both rounds are correct but slower: csrc/experiments/).
-// tiles of the attention kernel's shared-memory ring / keys per tile, by K/V row format (dec_attention_bulk_kernel)
-static int kv_ring_tiles(int fmt) { return fmt == MT3_KV_P24 ? 4 : 6; }
-static int kv_tile_keys(int fmt) { return fmt == MT3_KV_F32 ? 32 : 64; }
-
-// pf_layer >= 0: this launch also prefetches tiles [ring + pf_slot * pf_gemm, ring + (pf_slot + pf_n) * pf_gemm) of that decoder
-// layer's self K/V into L2 (cache length = position + pf_len_add when the attention kernel runs)
 static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, int K, int norm, int epi, float* C, int ldc,
-                    int n_split, char* kv, const int* pos, const Rows& rows, cudaStream_t s, int pf_layer = -1, int pf_slot = 0,
-                    int pf_n = 1, int pf_len_add = 1) {
+                    int n_split, char* kv, const int* pos, const Rows& rows, cudaStream_t s) {
   for (int r0 = rows.begin; r0 < rows.begin + rows.count; r0 += kDecBM) {
     DecGemmArgs a;
     memset(&a, 0, sizeof(a));
@@ -428,12 +417,6 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
     }
     a.partial = m->dpartial;
     a.counters = m->dcounters;
-    if (pf_layer >= 0 && m->pf_gemm > 0 && rows.count <= kDecBM) {
-      a.pf.kv = kv_layer(m, m->skv, pf_layer, m->L) + (int64_t)r0 * 2 * m->H * m->L * m->kv_row;
-      a.pf.pos = m->state; a.pf.len_add = pf_len_add; a.pf.cap = m->L; a.pf.H = m->H; a.pf.B = a.M;
-      a.pf.row_bytes = m->kv_row; a.pf.kt = kv_tile_keys(m->kv_fmt);
-      a.pf.j0 = kv_ring_tiles(m->kv_fmt) + pf_slot * m->pf_gemm; a.pf.j1 = a.pf.j0 + pf_n * m->pf_gemm; a.pf.hint = m->pf_hint;
-    }
     a.trace = trace_slot(m, K == m->F ? "gemm_mlp_out" : (N == 2 * m->F ? "gemm_mlp_in" : (kv ? "gemm_qkv_append" : (N == m->V ? "gemm_logits" : (K == m->Q ? "gemm_attn_out" : "gemm_cross_q")))));
     int rc = MT3_ERR_UNSUPPORTED;
     if (m->dec_cluster) rc = launch_dec_gemm_cluster(a, s, m->pdl_gemm);
@@ -443,14 +426,11 @@ static int dec_gemm(Model* m, const float* A, int lda, const float* W, int N, in
   return MT3_OK;
 }
 
-// pf_kind: 0 = no L2 prefetch, 1 = decode-step self-attention (the GEMMs before it cover the first 3 * pf_gemm tiles beyond the
-// ring), 2 = decode-step cross-attention
+// prefetch: the launch is part of a decode step (the kernel starts under the preceding GEMM): L2 prefetch of m->pf_attn tiles
 template <int FMT>
 static int launch_dec_attention_t(Model* m, const float* q, const char* kv, int cap, const int* len_ptr, int len_add,
                                   float* out, const Rows& rows, cudaStream_t s, const float* q_ssq, size_t smem, int max_len,
-                                  int pf_kind) {
-  const int pf_j0 = kv_ring_tiles(m->kv_fmt) + (pf_kind == 1 ? 3 * m->pf_gemm : 0);
-  const int pf_j1 = pf_kind ? pf_j0 + m->pf_attn : pf_j0;
+                                  bool prefetch) {
   static bool attr_done = false;
   if (!attr_done) {
     MT3_CUDA_CHECK(cudaFuncSetAttribute(dec_attention_bulk_kernel<FMT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -463,20 +443,20 @@ static int launch_dec_attention_t(Model* m, const float* q, const char* kv, int 
                                (const void*)(kv + (int64_t)rows.begin * 2 * m->H * cap * m->kv_row), m->H, cap,
                                len_ptr, len_add, max_len, out + (int64_t)rows.begin * m->Q, m->Q,
                                q_ssq ? q_ssq + (int64_t)rows.begin * (m->D / 32) : (const float*)nullptr, m->D / 32, m->D / 32,
-                               (float)m->D, 1e-6f, trace_slot(m, len_ptr ? "attn_self" : "attn_cross"), pf_j0, pf_j1, m->pf_hint));
+                               (float)m->D, 1e-6f, trace_slot(m, len_ptr ? "attn_self" : "attn_cross"), prefetch ? m->pf_attn : 0));
   MT3_LAUNCH_CHECK();
   return MT3_OK;
 }
 
 static int launch_dec_attention(Model* m, const float* q, const char* kv, int cap, const int* len_ptr, int len_add,
-                                float* out, const Rows& rows, cudaStream_t s, const float* q_ssq = nullptr, int pf_kind = 0) {
+                                float* out, const Rows& rows, cudaStream_t s, const float* q_ssq = nullptr, bool prefetch = false) {
   const int max_len = std::max(m->L, m->T);
   const size_t smem = dec_attention_smem(max_len);
   MT3_REQUIRE(smem <= 100 * 1024, MT3_ERR_UNSUPPORTED, "decode attention: length %d too long", max_len);
   switch (m->kv_fmt) {
-    case MT3_KV_F16: return launch_dec_attention_t<1>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len, pf_kind);
-    case MT3_KV_P24: return launch_dec_attention_t<2>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len, pf_kind);
-    default: return launch_dec_attention_t<0>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len, pf_kind);
+    case MT3_KV_F16: return launch_dec_attention_t<1>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len, prefetch);
+    case MT3_KV_P24: return launch_dec_attention_t<2>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len, prefetch);
+    default: return launch_dec_attention_t<0>(m, q, kv, cap, len_ptr, len_add, out, rows, s, q_ssq, smem, max_len, prefetch);
   }
 }
 
@@ -517,7 +497,7 @@ static int dec_layer_qkv(Model* m, DecBranch& b, int l) {
                   b.rows, b.s);
 }
 static int dec_layer_self(Model* m, DecBranch& b, int l) {
-  return launch_dec_attention(m, m->dq, kv_layer(m, m->skv, l, m->L), m->L, m->state, 1, m->dao, b.rows, b.s, nullptr, 1);
+  return launch_dec_attention(m, m->dq, kv_layer(m, m->skv, l, m->L), m->L, m->state, 1, m->dao, b.rows, b.s, nullptr, true);
 }
 // self-attention out-projection + residual, cross-attention query projection (one launch when fused)
 static int dec_layer_outq(Model* m, DecBranch& b, int l) {
@@ -538,16 +518,14 @@ static int dec_layer_outq(Model* m, DecBranch& b, int l) {
 }
 static int dec_layer_cross(Model* m, DecBranch& b, int l) {
   return launch_dec_attention(m, m->dq, kv_layer(m, m->ckv, l, m->T), m->T, nullptr, m->T, m->dao, b.rows, b.s,
-                              b.fused == MT3_OK ? m->dssq : nullptr, 2);
+                              b.fused == MT3_OK ? m->dssq : nullptr, true);
 }
 static int dec_layer_mlp(Model* m, DecBranch& b, int l) {
   const DecLayer& w = m->dec[l];
   const int D = m->D, Q = m->Q, F = m->F;
-  // the HBM is idle under these three launches: each pulls a share of the NEXT layer's self K/V tiles into L2 (MT3_PF_GEMM)
-  const int nl = l + 1 < m->Ld ? l + 1 : -1;
-  MT3_TRY(dec_gemm(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s, nl, 0));
-  MT3_TRY(dec_gemm(m, b.y, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr, nullptr, b.rows, b.s, nl, 1));
-  MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s, nl, 2));
+  MT3_TRY(dec_gemm(m, m->dao, Q, w.wo_c, D, Q, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s));
+  MT3_TRY(dec_gemm(m, b.y, D, w.wi, 2 * F, D, 1, EPI_GATED_GELU, m->dg, F, 2 * F, nullptr, nullptr, b.rows, b.s));
+  MT3_TRY(dec_gemm(m, m->dg, F, w.wo2, D, F, 0, EPI_RESIDUAL, b.y, D, D, nullptr, nullptr, b.rows, b.s));
   return MT3_OK;
 }
 
@@ -569,9 +547,7 @@ static int decode_step_impl(Model* m, const int* tok_in, float* logits, int gree
     MT3_TRY(dec_layer_cross(m, b, l));
     MT3_TRY(dec_layer_mlp(m, b, l));
   }
-  // the logits GEMM prefetches layer 0's tiles for the NEXT step (the position advances after it: length = position + 2)
-  MT3_TRY(dec_gemm(m, b.y, m->D, m->w_logits, m->V, m->D, 1, EPI_STORE, logits, m->V, m->V, nullptr, nullptr, b.rows, s,
-                   loop_step ? 0 : -1, 0, 3, 2));
+  MT3_TRY(dec_gemm(m, b.y, m->D, m->w_logits, m->V, m->D, 1, EPI_STORE, logits, m->V, m->V, nullptr, nullptr, b.rows, s));
   if (greedy == 2) {        // T5X beam_search bookkeeping at num_decodes = 1 (generate loop only)
     MT3_CUDA_CHECK(launch_kernel(beam1_step_kernel, dim3(m->B), dim3(256), 0, s, m->pdl, (const float*)logits, m->V, m->B, m->tok_cur,
                                  m->finished, tokens_ws, m->L, m->state, m->beam_f, m->beam_i, 0.6f, m->L, (const float*)m->emb,
@@ -611,39 +587,6 @@ static void select_graph(Model* m, int mode = 1) {
   }
 }
 
-// MT3_L2_PERSIST_MB: set aside part of L2 for the decoder weights (re-read every step, while ~1 GB of K/V rows streams
-// through L2 in between) by giving every kernel node of the step graph an access-policy window over them.  Value-neutral.
-static void apply_l2_window(Model* m, cudaGraph_t g) {
-  int dev = 0, max_win = 0, max_persist = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return;
-  cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-  cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-  const size_t persist = std::min((size_t)m->l2_persist_mb << 20, (size_t)std::max(0, max_persist));
-  if (persist == 0 || max_win <= 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist) != cudaSuccess) {
-    cudaGetLastError();
-    return;
-  }
-  const char* base = reinterpret_cast<const char*>(m->dec[0].wqkv);           // decoder layers + logits kernel are contiguous in the slab
-  const size_t bytes = std::min((size_t)(reinterpret_cast<const char*>(m->w_logits + (int64_t)m->D * m->V) - base), (size_t)max_win);
-  cudaKernelNodeAttrValue v;
-  memset(&v, 0, sizeof(v));
-  v.accessPolicyWindow.base_ptr = const_cast<char*>(base);
-  v.accessPolicyWindow.num_bytes = bytes;
-  v.accessPolicyWindow.hitRatio = std::min(1.0f, (float)persist / (float)bytes);
-  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-  v.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-  size_t n = 0;
-  if (cudaGraphGetNodes(g, nullptr, &n) != cudaSuccess || n == 0) { cudaGetLastError(); return; }
-  std::vector<cudaGraphNode_t> nodes(n);
-  if (cudaGraphGetNodes(g, nodes.data(), &n) != cudaSuccess) { cudaGetLastError(); return; }
-  for (size_t i = 0; i < n; ++i) {
-    cudaGraphNodeType t;
-    if (cudaGraphNodeGetType(nodes[i], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel)
-      cudaGraphKernelNodeSetAttribute(nodes[i], cudaKernelNodeAttributeAccessPolicyWindow, &v);
-  }
-  cudaGetLastError();
-}
-
 // mode: 1 greedy, 2 beam-size-1 search; nsteps consecutive decode steps per graph (the position lives on the device, so a
 // graph of 16 steps is the single-step graph 16 times over: one graph launch and its ~3 us of inter-launch latency per 16 steps)
 static int ensure_graph(Model* m, int mode, int nsteps = 1) {
@@ -666,7 +609,6 @@ static int ensure_graph(Model* m, int mode, int nsteps = 1) {
   m->graph = g;
   m->graph_kernels = g_launch_count.load() - before;
   g_launch_count.fetch_sub(m->graph_kernels);   // capture does not execute
-  if (m->l2_persist_mb > 0) apply_l2_window(m, g);
   MT3_CUDA_CHECK(cudaGraphInstantiate(&m->graph_exec, m->graph, 0));
   if (m->graphs.size() >= 12) {                 // bound the cache: forget everything but the new graph
     const Model::StepGraph keep{m->graph, m->graph_exec, m->graph_kernels};
@@ -829,20 +771,7 @@ extern "C" int mt3_model_create(const mt3_model_config* cfg, const float* weight
     const char* e_attn = getenv("MT3_TC_ATTENTION");
     m->tc_attn_ok = !(e_attn && e_attn[0] == '0');
     const char* e_pfa = getenv("MT3_PF_ATTN");
-    const char* e_pfg = getenv("MT3_PF_GEMM");
-    const char* e_pfh = getenv("MT3_PF_HINT");
-    const char* e_l2p = getenv("MT3_L2_PERSIST_MB");
     if (e_pfa) m->pf_attn = std::max(0, atoi(e_pfa));
-    if (e_pfg) m->pf_gemm = std::max(0, atoi(e_pfg));
-    if (e_pfh) m->pf_hint = atoi(e_pfh) != 0;
-    if (e_l2p) {
-      m->l2_persist_mb = std::max(0, atoi(e_l2p));
-      if (m->l2_persist_mb == 0) {             // explicit 0: give a carve-out left by an earlier handle back
-        cudaCtxResetPersistingL2Cache();
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
-        cudaGetLastError();
-      }
-    }
   }
   m->kv_fmt = cfg->kv_cache_format;
   m->kv_row = kv_row_bytes(m->kv_fmt);
