@@ -504,6 +504,7 @@ def run_ours(args):
             "config": workload_config(dec_steps),
             "impl_config": {"gemm_mode": args.gemm_mode, "kv_cache": args.kv + " rows, fp32 arithmetic",
                             "l2": "flushed between steps (256 MB write)",
+                            "kv_l2_prefetch_tiles": os.environ.get("MT3_PF_ATTN", "16 (library default)"),
                             "parallelism": f"dp{world} (segments sharded, 1 weight broadcast, 1 token all-gather)"},
             "segments_per_second": value / SEG_SECONDS,
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": int(B * SEG_SAMPLES * 4),
