@@ -213,6 +213,39 @@ def event_predictions_to_ns(predictions: Sequence[Mapping[str, Any]], codec: eve
 
 
 # ---------------------------------------------------------------------------------------------
+# Frame-level view of a NoteSequence (metrics_utils.py:149-196)
+# ---------------------------------------------------------------------------------------------
+def note_sequence_to_pianoroll(ns: NoteSequence, fps: float, is_drum: bool = False) -> np.ndarray:
+    """[128, frames] piano roll of velocities (metrics_utils.get_prettymidi_pianoroll without pretty_midi, which is not
+    installable here): every drum hit lasts 50 ms, every other note at least 50 ms; a note covers the frames
+    int(start * fps) .. int(end * fps) - 1 and simultaneous notes of one pitch add their velocities (pretty_midi's
+    get_piano_roll summed over instruments).  The input is not modified."""
+    ends = [n.start_time + 0.05 if (is_drum or n.end_time - n.start_time < 0.05) else n.end_time for n in ns.notes]
+    frames = int(max(ends, default=0.0) * fps)
+    roll = np.zeros((128, frames), np.float64)
+    for n, end in zip(ns.notes, ends):
+        roll[n.pitch, int(n.start_time * fps):int(end * fps)] += n.velocity
+    return roll
+
+
+def frame_metrics(ref_pianoroll: np.ndarray, est_pianoroll: np.ndarray, velocity_threshold: int) -> Tuple[float, float, float]:
+    """Frame precision, recall and F1 (metrics_utils.py:175-196): the shorter roll is zero-padded, reference frames count
+    when louder than `velocity_threshold`, estimated frames when non-zero; an empty denominator gives 0 (sklearn's
+    zero_division default, which the reference inherits)."""
+    ref, est = np.asarray(ref_pianoroll), np.asarray(est_pianoroll)
+    width = max(ref.shape[1], est.shape[1])
+    ref = np.pad(ref, [(0, 0), (0, width - ref.shape[1])])
+    est = np.pad(est, [(0, 0), (0, width - est.shape[1])])
+    ref_on, est_on = ref > velocity_threshold, est > 0
+    tp = int(np.count_nonzero(ref_on & est_on))
+    n_est, n_ref = int(np.count_nonzero(est_on)), int(np.count_nonzero(ref_on))
+    precision = tp / n_est if n_est else 0.0
+    recall = tp / n_ref if n_ref else 0.0
+    f1 = 2 * precision * recall / (precision + recall) if precision + recall else 0.0
+    return precision, recall, f1
+
+
+# ---------------------------------------------------------------------------------------------
 # Standard MIDI file writer (SURVEY 8(f2); the notebook's note_seq.sequence_proto_to_midi_file)
 # ---------------------------------------------------------------------------------------------
 def _vlq(n: int) -> bytes:

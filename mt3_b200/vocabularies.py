@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
-from typing import Optional, Sequence
+from typing import Callable, Optional, Sequence
 
 import numpy as np
 import torch
@@ -63,6 +63,34 @@ def velocity_to_bin(velocity, num_velocity_bins):
 
 def bin_to_velocity(velocity_bin, num_velocity_bins):
     return 0 if velocity_bin == 0 else int(MAX_MIDI_VELOCITY * velocity_bin / num_velocity_bins)
+
+
+def drop_programs(tokens, codec: event_codec.Codec):
+    """Drops program change events from a token sequence (vocabularies.py:77-80)."""
+    tokens = np.asarray(tokens)
+    lo, hi = codec.event_type_range('program')
+    return tokens[(tokens < lo) | (tokens > hi)]
+
+
+def programs_to_midi_classes(tokens, codec: event_codec.Codec):
+    """Program events -> the first program of their MIDI class of 8 (vocabularies.py:83-90)."""
+    tokens = np.asarray(tokens)
+    lo, hi = codec.event_type_range('program')
+    return np.where((tokens >= lo) & (tokens <= hi), lo + 8 * ((tokens - lo) // 8), tokens)
+
+
+@dataclasses.dataclass
+class ProgramGranularity:
+    """How programs are collapsed in token streams and in NoteSequences; both maps are idempotent (vocabularies.py:93-97)."""
+    tokens_map_fn: Callable
+    program_map_fn: Callable[[int], int]
+
+
+PROGRAM_GRANULARITIES = {
+    'flat': ProgramGranularity(tokens_map_fn=drop_programs, program_map_fn=lambda program: 0),            # no program tokens
+    'midi_class': ProgramGranularity(tokens_map_fn=programs_to_midi_classes, program_map_fn=lambda program: 8 * (program // 8)),
+    'full': ProgramGranularity(tokens_map_fn=lambda tokens, codec: np.asarray(tokens), program_map_fn=lambda program: program),
+}
 
 
 def build_codec(vocab_config: VocabularyConfig):

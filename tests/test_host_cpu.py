@@ -305,3 +305,46 @@ def test_t5x_checkpoint_reader_roundtrip(tmp_path, top_level_target):
     r = checkpoints.read_zarr_array(str(z))
     np.testing.assert_array_equal(r[:2], a[:2])
     assert (r[2] == 7.0).all()
+
+
+def test_vocabulary_reference_tests_literal():
+    """vocabularies_test.py:28-45 (velocity quantisation, every bin), :85-102 (encode range errors), :104-109 (dtypes)."""
+    from mt3_b200 import vocabularies as V
+    assert V.velocity_to_bin(0, num_velocity_bins=1) == 0 and V.velocity_to_bin(0, num_velocity_bins=127) == 0
+    assert V.bin_to_velocity(0, num_velocity_bins=1) == 0 and V.bin_to_velocity(0, num_velocity_bins=127) == 0
+    assert V.velocity_to_bin(V.bin_to_velocity(1, num_velocity_bins=1), num_velocity_bins=1) == 1
+    for velocity_bin in range(1, 128):
+        assert V.velocity_to_bin(V.bin_to_velocity(velocity_bin, num_velocity_bins=127), num_velocity_bins=127) == velocity_bin
+    vocab = V.GenericTokenVocabulary(32)
+    assert list(vocab.encode([0, 15, 31])) == [3, 18, 34]
+    np.testing.assert_array_equal(vocab.encode_tf(np.array([0, 15, 31])), [3, 18, 34])
+    for bad in ([-1, 15, 31], [0, 15, 32]):
+        with pytest.raises(ValueError):
+            vocab.encode(bad)
+        with pytest.raises(ValueError):
+            vocab.encode_tf(np.array(bad))
+    assert vocab.encode_tf(np.array([0, 15, 31], np.int32)).dtype == np.int32
+    assert vocab.encode_tf(np.array([0, 15, 31], np.int64)).dtype == np.int64
+
+
+def test_program_granularities():
+    """vocabularies.PROGRAM_GRANULARITIES (vocabularies.py:77-116): 'flat' drops program tokens, 'midi_class' maps a program to
+    the first of its class of 8, 'full' is the identity; token and program maps are idempotent and agree with each other."""
+    from mt3_b200 import event_codec, vocabularies as V
+    codec = V.build_codec(V.VocabularyConfig(num_velocity_bins=1))
+    E = event_codec.Event
+    toks = np.array([codec.encode_event(e) for e in (E('shift', 10), E('program', 42), E('velocity', 1), E('pitch', 60),
+                                                     E('program', 7), E('pitch', 62), E('tie', 0), E('drum', 38))])
+    prog = lambda p: codec.encode_event(E('program', p))
+    flat = V.PROGRAM_GRANULARITIES['flat'].tokens_map_fn(toks, codec)
+    np.testing.assert_array_equal(flat, [t for t in toks if t not in (prog(42), prog(7))])
+    cls = V.PROGRAM_GRANULARITIES['midi_class'].tokens_map_fn(toks, codec)
+    np.testing.assert_array_equal(cls, [prog(40) if t == prog(42) else prog(0) if t == prog(7) else t for t in toks])
+    np.testing.assert_array_equal(V.PROGRAM_GRANULARITIES['full'].tokens_map_fn(toks, codec), toks)
+    for name, g in V.PROGRAM_GRANULARITIES.items():
+        once = g.tokens_map_fn(toks, codec)
+        np.testing.assert_array_equal(g.tokens_map_fn(once, codec), once)
+        for p in (0, 7, 8, 42, 127):
+            assert g.program_map_fn(g.program_map_fn(p)) == g.program_map_fn(p)
+            mapped = g.tokens_map_fn(np.array([prog(p)]), codec)
+            assert (len(mapped) == 0 and name == 'flat') or mapped[0] == prog(g.program_map_fn(p))

@@ -247,3 +247,38 @@ def test_write_inferences_to_file(tmp_path):
         nd.write_inferences_to_file(str(path), [], [], 'score', vocabulary=vocab, vocab_config=vc)
     with pytest.raises(ValueError):
         nd.write_inferences_to_file(str(path), [], [], 'predict', vocabulary=vocab, vocab_config=vc, onsets_only=True, use_ties=True)
+
+
+def test_frame_metrics_reference_kat_and_sklearn():
+    ref, est = np.zeros((128, 5)), np.zeros((128, 5))                 # metrics_utils_test.py:240-256
+    ref[10, 0] = ref[10, 1] = ref[10, 2] = 127                        # one overlapping frame, two false positives, two false negatives
+    est[10, 2] = est[10, 3] = est[10, 4] = 127
+    prec, rec, f1 = nd.frame_metrics(ref, est, velocity_threshold=1)
+    assert prec == pytest.approx(1 / 3) and rec == pytest.approx(1 / 3) and f1 == pytest.approx(1 / 3)
+    # rolls of different lengths, a quiet reference frame below the threshold; against the call the reference makes
+    skm = pytest.importorskip("sklearn.metrics")
+    rng = np.random.default_rng(0)
+    ref = (rng.random((128, 40)) < 0.05) * rng.integers(1, 128, (128, 40))
+    est = (rng.random((128, 33)) < 0.05) * rng.integers(1, 128, (128, 33))
+    got = nd.frame_metrics(ref, est, velocity_threshold=30)
+    est_p = np.pad(est, [(0, 0), (0, 7)])
+    p, r, f, _ = skm.precision_recall_fscore_support((ref > 30).flatten(), (est_p > 0).flatten(), labels=[True, False])
+    assert got == pytest.approx((p[0], r[0], f[0]))
+    assert nd.frame_metrics(np.zeros((128, 3)), np.zeros((128, 0)), 0) == (0.0, 0.0, 0.0)
+
+
+def test_note_sequence_to_pianoroll():
+    ns = nd.NoteSequence()
+    ns.add(0.0, 1.0, 60, 100)
+    ns.add(0.5, 0.51, 60, 20)            # shorter than 50 ms: lengthened to 50 ms; overlaps the first note -> velocities add
+    ns.add(2.0, 2.25, 36, 90, is_drum=True)
+    roll = nd.note_sequence_to_pianoroll(ns, fps=100)
+    assert roll.shape == (128, 225)
+    assert roll[60, 0] == 100 and roll[60, 99] == 100 and roll[60, 100] == 0
+    assert (roll[60, 50:55] == 120).all() and roll[60, 55] == 100
+    assert (roll[36, 200:225] == 90).all()
+    drums = nd.note_sequence_to_pianoroll(ns, fps=100, is_drum=True)          # fixed 50 ms for every note
+    n = int((2.0 + 0.05) * 100)                                                # 204: int() of the float product, as pretty_midi does
+    assert drums.shape == (128, n) and (drums[36, 200:n] == 90).all() and drums[60, 5] == 0 and drums[60, 4] == 100
+    assert ns.notes[1].end_time == 0.51                                       # unlike the reference helper, the input is left alone
+    assert nd.note_sequence_to_pianoroll(nd.NoteSequence(), 100).shape == (128, 0)

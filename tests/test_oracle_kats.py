@@ -216,3 +216,99 @@ def test_audio_to_frames_always_pads():
     frames, times = O.audio_to_frames(np.ones(32000, np.float32))
     assert frames.shape == (251, 128)
     np.testing.assert_allclose(times[:3], [0.0, 0.008, 0.016])
+
+
+# ------------------------------------------------------------------------------------------------
+# Mask helpers of the layer API (mt3_b200/layers.py; numpy on the host): the literal vectors of layers_test.py:117-283
+# ------------------------------------------------------------------------------------------------
+def _L():
+    from mt3_b200 import layers
+    return layers
+
+
+def test_make_attention_mask_reference_vectors():
+    L = _L()
+    toks = np.array([[7, 0, 0], [8, 5, 0]])
+    m = L.make_attention_mask(toks > 0, toks > 0, dtype=np.int32)                            # layers_test.py:117-125
+    assert m.shape == (2, 1, 3, 3)
+    np.testing.assert_array_equal(m[0, 0], [[1, 0, 0], [0, 0, 0], [0, 0, 0]])
+    np.testing.assert_array_equal(m[1, 0], [[1, 1, 0], [1, 1, 0], [0, 0, 0]])
+    seg = np.array([[1, 1, 2, 2, 2, 0], [1, 1, 1, 2, 0, 0]])
+    m = L.make_attention_mask(seg, seg, pairwise_fn=np.equal, dtype=np.int32)                # :127-141 (padding is not special)
+    assert m.shape == (2, 1, 6, 6)
+    np.testing.assert_array_equal(m[0, 0], [[1, 1, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0], [0, 0, 1, 1, 1, 0], [0, 0, 1, 1, 1, 0],
+                                            [0, 0, 1, 1, 1, 0], [0, 0, 0, 0, 0, 1]])
+    np.testing.assert_array_equal(m[1, 0], [[1, 1, 1, 0, 0, 0], [1, 1, 1, 0, 0, 0], [1, 1, 1, 0, 0, 0], [0, 0, 0, 1, 0, 0],
+                                            [0, 0, 0, 0, 1, 1], [0, 0, 0, 0, 1, 1]])
+
+
+def test_make_causal_mask_reference_vectors():
+    L = _L()
+    tri = np.array([[1., 0., 0.], [1., 1., 0.], [1., 1., 1.]], np.float32)
+    y = L.make_causal_mask(np.array([[7, 0, 0], [8, 5, 0]]))                                # :143-152
+    assert y.shape == (2, 1, 3, 3) and y.dtype == np.float32
+    np.testing.assert_array_equal(y[0, 0], tri)
+    np.testing.assert_array_equal(y[1, 0], tri)
+    assert L.make_causal_mask(np.ones((3, 3, 5)), extra_batch_dims=2).shape == (1, 1, 3, 3, 1, 5, 5)   # :154-157
+    np.testing.assert_array_equal(L.make_causal_mask(np.ones((1, 3))), tri[None, None])     # :159-165
+
+
+def test_combine_masks_and_biases_reference_vectors():
+    L = _L()
+    f = lambda *v: np.array(v, np.float32)
+    np.testing.assert_array_equal(L.combine_masks(f(0, 1, 0, 1), None, f(1, 1, 1, 1), f(1, 1, 1, 0)), f(0, 1, 0, 0))   # :167-174
+    np.testing.assert_array_equal(L.combine_biases(f(0, 1, 0, 1), None, f(0, 1, 1, 1), f(0, 1, 1, 0)), f(0, 3, 2, 2))  # :176-183
+    assert L.combine_masks(None, None) is None and L.combine_biases() is None
+    with pytest.raises(AssertionError):
+        L.combine_masks(np.ones((2, 2)), np.ones((2,)))
+
+
+def test_make_decoder_mask_reference_vectors():
+    L = _L()
+    m = L.make_decoder_mask(np.array([6, 7, 3, 0]), np.float32)                             # lm, unpacked :185-191
+    np.testing.assert_array_equal(m, [[[1, 0, 0, 0], [1, 1, 0, 0], [1, 1, 1, 0], [0, 0, 0, 0]]])
+    m = L.make_decoder_mask(np.array([[6, 7, 3, 4, 5, 0]]), np.float32, decoder_segment_ids=np.array([[1, 1, 1, 2, 2, 0]]))   # :193-203
+    np.testing.assert_array_equal(m, [[[[1, 0, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0], [1, 1, 1, 0, 0, 0], [0, 0, 0, 1, 0, 0],
+                                        [0, 0, 0, 1, 1, 0], [0, 0, 0, 0, 0, 0]]]])
+    m = L.make_decoder_mask(np.array([[5, 6, 7, 3, 4, 0]]), np.float32,
+                            decoder_causal_attention=np.array([[1, 1, 1, 0, 0, 0]]))        # prefix lm :205-216
+    np.testing.assert_array_equal(m, [[[[1, 1, 1, 0, 0, 0], [1, 1, 1, 0, 0, 0], [1, 1, 1, 0, 0, 0], [1, 1, 1, 1, 0, 0],
+                                        [1, 1, 1, 1, 1, 0], [0, 0, 0, 0, 0, 0]]]])
+    m = L.make_decoder_mask(np.array([[5, 6, 7, 8, 3, 4, 0]]), np.float32,
+                            decoder_causal_attention=np.array([[1, 1, 0, 1, 1, 0, 0]]),
+                            decoder_segment_ids=np.array([[1, 1, 1, 2, 2, 2, 0]]))          # prefix lm, packed :218-231
+    np.testing.assert_array_equal(m, [[[[1, 1, 0, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0, 0], [1, 1, 1, 0, 0, 0, 0], [0, 0, 0, 1, 1, 0, 0],
+                                        [0, 0, 0, 1, 1, 0, 0], [0, 0, 0, 1, 1, 1, 0], [0, 0, 0, 0, 0, 0, 0]]]])
+    m = L.make_decoder_mask(np.array([[6, 7, 3, 0], [4, 5, 0, 0]]), np.float32,
+                            decoder_causal_attention=np.array([[1, 1, 0, 0], [1, 0, 0, 0]]))   # :233-246
+    assert m.shape == (2, 1, 4, 4)
+    np.testing.assert_array_equal(m[0, 0], [[1, 1, 0, 0], [1, 1, 0, 0], [1, 1, 1, 0], [0, 0, 0, 0]])
+    np.testing.assert_array_equal(m[1, 0], [[1, 0, 0, 0], [1, 1, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0]])
+    m = L.make_decoder_mask(np.array([[6, 7, 3, 4, 8, 9, 0]]), np.float32,
+                            decoder_causal_attention=np.array([[1, 1, 0, 0, 1, 1, 0]]))     # composite :248-261
+    assert m.shape == (1, 1, 7, 7)
+    np.testing.assert_array_equal(m[0, 0], [[1, 1, 0, 0, 1, 1, 0], [1, 1, 0, 0, 1, 1, 0], [1, 1, 1, 0, 0, 0, 0], [1, 1, 1, 1, 0, 0, 0],
+                                            [1, 1, 1, 1, 1, 1, 0], [1, 1, 1, 1, 1, 1, 0], [0, 0, 0, 0, 0, 0, 0]])
+    m = L.make_decoder_mask(np.array([[6, 7, 3, 4, 8, 9, 2, 3, 4]]), np.float32,
+                            decoder_causal_attention=np.array([[1, 1, 0, 0, 1, 1, 1, 1, 0]]),
+                            decoder_segment_ids=np.array([[1, 1, 1, 1, 1, 1, 2, 2, 2]]))    # composite, packed :263-283
+    assert m.shape == (1, 1, 9, 9)
+    np.testing.assert_array_equal(m[0, 0], [[1, 1, 0, 0, 1, 1, 0, 0, 0], [1, 1, 0, 0, 1, 1, 0, 0, 0], [1, 1, 1, 0, 0, 0, 0, 0, 0],
+                                            [1, 1, 1, 1, 0, 0, 0, 0, 0], [1, 1, 1, 1, 1, 1, 0, 0, 0], [1, 1, 1, 1, 1, 1, 0, 0, 0],
+                                            [0, 0, 0, 0, 0, 0, 1, 1, 0], [0, 0, 0, 0, 0, 0, 1, 1, 0], [0, 0, 0, 0, 0, 0, 1, 1, 1]])
+
+
+def test_mask_to_bias_and_masked_attention_in_the_oracle():
+    """mask -> bias the way MultiHeadDotProductAttention does (layers.py:316-328), and the effect through the oracle's
+    dot_product_attention: a key masked out for a query gets exactly zero weight (exp(-1e10 - max) underflows to 0)."""
+    L = _L()
+    mask = L.make_decoder_mask(np.array([[6, 7, 3, 0]]), np.float32)
+    bias = L.mask_to_bias(mask)
+    assert bias.dtype == np.float32 and set(np.unique(bias)) == {np.float32(0.0), np.float32(-1e10)}
+    np.testing.assert_array_equal(bias, O.mask_to_bias(mask, np.float32))
+    rng = np.random.default_rng(0)
+    q, k, v = (rng.standard_normal((1, 4, 2, 8)) for _ in range(3))
+    full = O.dot_product_attention(q, k, v, bias=bias.astype(np.float64))
+    for i in range(3):                      # query i sees keys 0..i only: same as attention over the truncated key set
+        part = O.dot_product_attention(q[:, i:i + 1], k[:, :i + 1], v[:, :i + 1])
+        np.testing.assert_allclose(full[:, i:i + 1], part, rtol=0, atol=1e-12)
