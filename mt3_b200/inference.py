@@ -235,6 +235,48 @@ class InferenceModel(object):
         tokens = self.transcribe_segments_sharded(segs, n_valid_frames=n_valid)
         return [self.postprocess(t, ex) for t, ex in zip(tokens, ds)]
 
+    # ---------------------------------------------------------------------------------
+    # Batch inference over many recordings (T5X `infer` with gin/infer.gin + inference.write_inferences_to_file)
+    # ---------------------------------------------------------------------------------
+    def build_infer_dataset(self, records):
+        """records: [{'id': str, 'audio': float samples at 16 kHz}, ...] -> (task_ds, segments, n_valid_frames): the
+        per-segment examples the reference's inference tasks produce (tasks.py:196-232: unique_id, input_times, the reference
+        sequence -- here the id -- on the FIRST segment of a recording only) and the zero-padded audio of ALL segments of all
+        recordings in one [S, inputs_length * hop] array, so that decode batches are filled across recordings."""
+        hop = self.spectrogram_config.hop_width
+        seg_len = self.inputs_length * hop
+        task_ds, rows, n_valid = [], [], []
+        for rec in records:
+            first = True
+            for ex in self.preprocess(self.audio_to_dataset(rec['audio'])):
+                flat = np.asarray(ex['inputs'], np.float32).reshape(-1)
+                row = np.zeros((seg_len,), np.float32)
+                row[:flat.size] = flat
+                rows.append(row)
+                n_valid.append(flat.size // hop)
+                task_ds.append({'unique_id': [rec['id']], 'input_times': ex['input_times'], 'raw_inputs': [],
+                                'sequence': [rec['id'] if first else '']})
+                first = False
+        segs = np.stack(rows) if rows else np.zeros((0, seg_len), np.float32)
+        return task_ds, segs, np.asarray(n_valid, np.int32)
+
+    def infer_to_file(self, records, path: str) -> int:
+        """Transcribe many recordings and write one JSON line of notes per recording ({'id', 'est_notes'}, the reference's
+        inference.write_inferences_to_file format).  Segments of all recordings share the decode batches; under
+        torch.distributed they are sharded over the GPUs and rank 0 writes.  Returns the number of segments decoded."""
+        from . import distributed as mt3_dist
+        task_ds, segs, n_valid = self.build_infer_dataset(records)
+        if len(task_ds) == 0:
+            inferences = np.zeros((0, self.outputs_length), np.int32)
+        else:
+            inferences = self.transcribe_segments_sharded(segs, n_valid_frames=n_valid, decoded=False)    # raw model ids
+        if mt3_dist.world()[0] == 0:
+            note_decoding.write_inferences_to_file(
+                path, list(inferences), task_ds, 'predict', vocabulary=self.vocabulary,
+                vocab_config=vocabularies.VocabularyConfig(num_velocity_bins=vocabularies.num_velocity_bins_from_codec(self.codec)),
+                onsets_only=self.encoding_spec == 'NoteOnsetEncodingSpec', use_ties=self.encoding_spec == 'NoteEncodingWithTiesSpec')
+        return len(task_ds)
+
     def audio_to_dataset(self, audio):
         """Create a dataset (list with one example) of frames from input audio (notebook :310-316)."""
         frames, frame_times = self._audio_to_frames(audio)

@@ -224,3 +224,46 @@ def test_segment_targets_onsets_only_and_errors():
         ne.note_sequence_to_segment_targets(ns, codec, frame_times, 256, onsets_only=True, include_ties=True)
     with pytest.raises(IndexError):
         ne.encode_and_index_events(None, [], [], ne.note_event_data_to_events, codec, [])
+
+
+def test_batch_infer_dataset_and_jsonl_from_encoded_targets(tmp_path):
+    """The T5X-infer style flow on the CPU, with the label encoder standing in for the model: two recordings -> per-segment
+    examples (InferenceModel.build_infer_dataset) -> 'inferences' = the reference transcription's own target tokens as raw
+    model ids (+3, EOS, zero padding) -> write_inferences_to_file -> the JSON lines carry the notes of each recording."""
+    import json
+    from mt3_b200 import inference, spectrograms
+    im = inference.InferenceModel.__new__(inference.InferenceModel)          # host-side pieces only: no GPU, no weights
+    im.spectrogram_config = spectrograms.SpectrogramConfig()
+    im.inputs_length, im.outputs_length = 256, 1024
+    vc = vocabularies.VocabularyConfig(num_velocity_bins=1)
+    im.codec = vocabularies.build_codec(vc)
+    im.vocabulary = vocabularies.vocabulary_from_codec(im.codec)
+    rng = np.random.default_rng(7)
+    recs, truth = [], {}
+    for name, seconds in (('song-b', 5.0), ('song-a', 3.0)):
+        recs.append({'id': name, 'audio': np.zeros(int(seconds * 16000), np.float32)})
+        truth[name] = _random_ns(rng, seconds, 25)
+    task_ds, segs, n_valid = im.build_infer_dataset(recs)
+    assert segs.shape == (3 + 2, 256 * 128) and [d['sequence'][0] for d in task_ds] == ['song-b', '', '', 'song-a', '']
+    assert list(n_valid) == [256, 256, 114, 256, 120]                        # 80 000 + 128 and 48 000 + 128 padded samples
+    inferences, i = [], 0
+    for rec in recs:
+        n_frames = sum(len(d['input_times']) for d in task_ds if d['unique_id'][0] == rec['id'])
+        frame_times = np.arange(n_frames) / 125.0
+        for toks in ne.note_sequence_to_segment_targets(truth[rec['id']], im.codec, frame_times, 256):
+            row = np.zeros(1024, np.int32)
+            ids = list(im.vocabulary.encode(toks)) + [1]
+            row[:len(ids)] = ids
+            inferences.append(row)
+            i += 1
+    assert i == len(task_ds)
+    path = tmp_path / 'inferences.jsonl'
+    nd.write_inferences_to_file(str(path), inferences, task_ds, 'predict', vocabulary=im.vocabulary, vocab_config=vc,
+                                onsets_only=False, use_ties=True)
+    lines = [json.loads(l) for l in path.read_text().splitlines()]
+    assert [l['id'] for l in lines] == ['song-a', 'song-b']
+    for l in lines:
+        got = sorted((n['is_drum'], n['program'], n['pitch'], round(n['start_time'], 6), round(n['end_time'], 6)) for n in l['est_notes'])
+        want = sorted((n.is_drum, 0 if n.is_drum else n.program, n.pitch, round(n.start_time, 6),
+                       round(n.start_time + 0.01 if n.is_drum else n.end_time, 6)) for n in truth[l['id']].notes)
+        assert got == want
