@@ -312,3 +312,37 @@ def test_mask_to_bias_and_masked_attention_in_the_oracle():
     for i in range(3):                      # query i sees keys 0..i only: same as attention over the truncated key set
         part = O.dot_product_attention(q[:, i:i + 1], k[:, :i + 1], v[:, :i + 1])
         np.testing.assert_allclose(full[:, i:i + 1], part, rtol=0, atol=1e-12)
+
+
+def test_baseline_config1_ismir2021_single_clip_cpu_plumbing():
+    """BASELINE.json configs[0]: the ismir2021 (piano) configuration on ONE 2 s / 16 kHz synthetic clip through the CPU
+    restatement only -- the plumbing case: 32 000 samples -> +128 pad -> 251 frames -> one segment of 512 ->
+    log-mel [251, 512] -> 0.0 rows up to 512 -> encoder -> greedy decode -> vocabulary decode.  V = 1664 (1514 classes + 3 +
+    100 extra ids, rounded up to a multiple of 128), velocity vocabulary of 127 bins, NoteEncodingSpec without
+    ties.  The transformer runs with one layer on each side to stay in CPU-test time; shapes and the token contract do
+    not depend on depth."""
+    from mt3_b200 import note_decoding, vocabularies as V
+    codec = V.build_codec(V.VocabularyConfig(num_velocity_bins=127))
+    vocab = V.vocabulary_from_codec(codec)
+    assert codec.num_classes == 1514 == O.codec_num_classes(127) and V.num_embeddings(vocab) == 1664 == O.num_embeddings(1514)
+    audio = O.sine_mix(32000, seed=1234)
+    frames, times = O.audio_to_frames(audio)
+    assert frames.shape == (251, 128)
+    segs = O.split_to_segments(frames, times, 512)
+    assert len(segs) == 1 and segs[0][0].shape == (251, 128) and segs[0][1][0] == 0.0
+    spec = O.compute_spectrogram(segs[0][0].reshape(-1))
+    assert spec.shape == (251, 512) and np.isfinite(spec).all()
+    x = O.pad_inputs(spec, 512)
+    assert x.shape == (512, 512) and (x[251:] == 0.0).all() and (x[:251] != 0.0).any()
+    cfg = O.T5Config(vocab_size=1664, num_encoder_layers=1, num_decoder_layers=1)
+    params = O.init_params(cfg, seed=0)
+    enc = O.encode(params, cfg, x[None], np.float32)
+    assert enc.shape == (1, 512, 512)
+    toks = O.greedy_decode(params, cfg, enc, 6, np.float32, stop_at_eos=True)
+    assert toks.shape[0] == 1 and toks.dtype.kind == 'i' and (toks >= 0).all() and (toks < 1664).all()
+    decoded = O.trim_eos(O.vocab_decode(toks, codec.num_classes)[0])
+    assert ((decoded >= -2) & (decoded < codec.num_classes)).all() and (decoded != -1).all()
+    np.testing.assert_array_equal(O.vocab_decode(toks, codec.num_classes), vocab.decode_tf(np.asarray(toks)))
+    # the stitch accepts whatever came out (random weights: mostly invalid / out-of-context events, counted not raised)
+    res = note_decoding.event_predictions_to_ns([{'est_tokens': decoded, 'start_time': 0.0, 'raw_inputs': []}], codec, 'NoteEncodingSpec')
+    assert res['est_invalid_events'] + res['est_dropped_events'] <= len(decoded)
