@@ -12,7 +12,7 @@ CODEC = V.build_codec(V.VocabularyConfig(num_velocity_bins=1))
 VOCAB = V.vocabulary_from_codec(CODEC)
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(st.lists(st.integers(min_value=-5, max_value=1700), min_size=0, max_size=40))
 def test_vocabulary_decode_forms_agree(ids):
     """decode_tf (array form: EOS and everything after it -> -1, invalid -> -2, length kept) cut at the first -1 equals the
@@ -30,7 +30,7 @@ def test_vocabulary_decode_forms_agree(ids):
     assert list(VOCAB.decode(VOCAB.encode(good))) == good                 # encode / decode are inverse on regular ids
 
 
-@settings(max_examples=200, deadline=None)
+@settings(max_examples=200, deadline=None, derandomize=True)
 @given(st.lists(st.tuples(st.integers(0, 350), st.integers(0, 127)), min_size=0, max_size=30))
 def test_run_length_encoded_shifts_restate_absolute_steps(events):
     """Any sequence of (gap in steps, pitch): written as single-step shifts and run-length encoded, the shift tokens in
@@ -61,7 +61,7 @@ def test_run_length_encoded_shifts_restate_absolute_steps(events):
     assert not any(CODEC.is_shift_event_index(t) and t == 0 for t in rle)
 
 
-@settings(max_examples=25, deadline=None)
+@settings(max_examples=25, deadline=None, derandomize=True)
 @given(st.sampled_from([8000, 11025, 22050, 32000, 44100, 48000]), st.integers(1, 4000), st.integers(0, 2 ** 31 - 1),
        st.floats(-2, 2), st.floats(-2, 2))
 def test_resample_is_linear_and_keeps_the_length_convention(rate, n, seed, a, b):
